@@ -78,8 +78,13 @@ def impute_block(X: np.ndarray, method: str, rng=np.random) -> np.ndarray:
 
 # --------------------------------------------------------------------------- fp32 operator boundary
 def _t32(a):
-    """mat_mul.py:4-15 -- numpy -> torch float32."""
-    return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.array(a, copy=None) if np.asarray(a).flags.writeable else np.array(a)).float()
+    """mat_mul.py:4-15 -- numpy -> torch float32 (strides kept: they select the BLAS path)."""
+    if isinstance(a, torch.Tensor):
+        return a
+    a = np.asarray(a)
+    if not a.flags.writeable:
+        a = a.copy(order="K")
+    return torch.from_numpy(a).float()
 
 
 def mm(*mats) -> np.ndarray:
