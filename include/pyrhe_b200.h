@@ -1,0 +1,125 @@
+/* pyrhe_b200 -- C ABI of the B200 (sm_100a) replacement for PyRHE's per-jackknife-block
+ * trace-estimation hot path.
+ *
+ * Reference interfaces replaced (all under /root/reference/pyrhe/src/):
+ *   util/mat_mul.py:17-48          mat_mul / elem_mul  (the only tensor call site)
+ *   base/base.py:338-359           read_geno           (.bed decode + 0<->2 flip)
+ *   base/base.py:265-289           impute_geno         (mean / binary)
+ *   base/base.py:291-296           standardize_geno
+ *   base/base.py:315-336,362-379   partition_bins / _get_jacknife_subsample
+ *   base/base.py:403-417           _compute_XXz / _UXXz / _XXUz / _yXXy
+ *   models/rhe_dom/rhe_dom.py:15-41 dominance encoding + scaling
+ *   models/genie/genie.py:61-82    GxE row scaling
+ *   base/base.py:465-500           aggregate (totals, leave-one-out by subtraction)
+ *   base/base.py:578-581           the O(J E^2 B N) Gram of the leave-one-out vectors
+ *
+ * Conventions: plain C, no C++ types, no exceptions across the boundary.  Every function
+ * returns 0 or a negative RHE_ERR_* code; the message is available from rhe_last_error()
+ * (thread local).  All device pointers are caller owned (the Python host passes
+ * torch tensors' data_ptr()); the context owns only its workspaces.  One context per GPU /
+ * rank; calls on one context are serialised by the caller; work is ordered on the
+ * `stream` argument (a cudaStream_t passed as void*); no function synchronises the host
+ * except rhe_ctx_create / rhe_ctx_destroy.
+ *
+ * Data layout:
+ *   packed genotypes  uint8 [n_snps][pitch_bytes]   PLINK-1 SNP-major rows, 4 genotypes/byte,
+ *                     LSB first, codes 00->0, 10->1, 11->2 (A2 count), 01->missing; row pitch
+ *                     padded to a multiple of 128 bytes, padding zero.  Np = 4 * pitch_bytes.
+ *   right-hand sides  float [n_sets * n_cols_set][Np]   column c of set t at row t*Rs + c, file
+ *                     order of individuals, rows of dropped / padded individuals zero.
+ *   rowscale          float [n_sets][Np]    keep mask (x env for the GxE set)
+ *   keep2             uint32 [Np / 16]      2 bits per individual, 0b11 = kept
+ *   P / S             float [E_reg][n_vec][Np]   X (X^T Z) per estimate e = group * K + bin
+ *   gram              double [E_reg][Rs][Rs]    sum over the (block, bin) SNPs of t t^T,
+ *                     t = X_s^T [Z | W | y]
+ */
+#ifndef PYRHE_B200_H
+#define PYRHE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RHE_ABI_VERSION 1
+
+#define RHE_OK 0
+#define RHE_ERR_INVALID (-1)   /* bad argument */
+#define RHE_ERR_CUDA (-2)      /* CUDA runtime error (message holds cudaGetErrorString) */
+#define RHE_ERR_STATE (-3)     /* call order violated (e.g. accumulate before set_rhs) */
+#define RHE_ERR_UNSUPPORTED (-4)
+
+#define RHE_PATH_SIMT 0        /* fp32/fp64 CUDA-core kernels (validation path)            */
+#define RHE_PATH_TCGEN05 1     /* int8 tcgen05 tensor-core kernels with TMEM accumulators   */
+
+typedef struct rhe_ctx rhe_ctx;
+
+typedef struct rhe_config {
+  int32_t device;          /* CUDA device ordinal */
+  int32_t n_indv;          /* N0: individuals in the .bed / .fam (file order) */
+  int32_t n_kept;          /* N : individuals after filtering (base.py:156) */
+  int32_t pitch_bytes;     /* device row pitch, multiple of 128, >= ceil(N0 / 4) */
+  int32_t n_cols_set;      /* Rs = B + C + Ty */
+  int32_t n_sets;          /* 1, or 2 when a GxE (env-scaled) set is present */
+  int32_t n_ops;           /* 1, or 2 for RHE-DOM (additive + dominance operand) */
+  int32_t n_vec;           /* B: leading columns of every set that go through pass B */
+  int32_t n_bins;          /* K */
+  int32_t max_block_snps;  /* largest jackknife block */
+  int32_t impute_binary;   /* 1 = "binary" (base.py:283-285), 0 = "mean" (base.py:287) */
+  int32_t kernel_path;     /* RHE_PATH_* */
+} rhe_config;
+
+int rhe_version(void);
+const char* rhe_last_error(void);
+
+/* mat_mul.py:4-15 / base.py:195-206: device selection and workspace allocation. */
+int rhe_ctx_create(rhe_ctx** out, const rhe_config* cfg);
+int rhe_ctx_destroy(rhe_ctx* ctx);
+
+/* base.py:176-178,396-401 (Z, covariates, regressed phenotype as right-hand sides). */
+int rhe_set_rhs(rhe_ctx* ctx, const float* rhs_dev, const float* rowscale_dev,
+                const uint32_t* keep2_dev, void* stream);
+
+/* base.py:281-285,510: the uniforms np.random.random() yields after np.random.seed(seed);
+ * block-local SNP s uses uniforms[s].  double [count] on the device. */
+int rhe_set_uniforms(rhe_ctx* ctx, const double* uniforms_dev, int32_t count);
+
+/* base.py:100,341: host .bed rows -> padded device rows (one pitched async copy). */
+int rhe_upload_rows(const void* host_src, int64_t row_bytes, int64_t n_rows,
+                    void* dev_dst, int64_t pitch_bytes, void* stream);
+
+/* base.py:277-289 statistics: per SNP {n0, n1, n2, n_missing} over kept individuals.
+ * counts_dev int32 [n_snps][4]. */
+int rhe_block_stats(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
+                    int32_t* counts_dev, void* stream);
+
+/* base.py:338-359 (+277-289 when apply_impute != 0): decoded A2 counts, one byte per
+ * genotype, int8 [n_snps][Np]; missing = 3 when apply_impute == 0.  Test hook for the
+ * bit-exact decode check. */
+int rhe_decode_block(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
+                     int32_t apply_impute, int8_t* out_dev, void* stream);
+
+/* rhe.py:13-22 / rhe_dom.py:43-68 / genie.py:46-82 for ONE jackknife block:
+ *   bin_rows_dev     int32 [bin_offsets[K]]  block-local SNP rows of every bin, concatenated
+ *   bin_offsets_host int32 [K + 1]           (host memory)
+ *   P_out_dev        float [E_reg][B][Np] or NULL   this block's X (X^T Z)
+ *   S_accum_dev      float [E_reg][B][Np] or NULL   running totals (+=)
+ *   gram_out_dev     double [E_reg][Rs][Rs]         overwritten */
+int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
+                         const int32_t* bin_rows_dev, const int32_t* bin_offsets_host,
+                         float* P_out_dev, float* S_accum_dev, double* gram_out_dev,
+                         void* stream);
+
+/* base.py:578-581 after aggregate (base.py:483-486): out[a][c] = sum (S_a - P_a)(S_c - P_c)
+ * over `len` floats per estimate; P_dev may be NULL (totals).  out_dev double [n_est][n_est]. */
+int rhe_loo_gram(rhe_ctx* ctx, const float* S_dev, const float* P_dev, int32_t n_est,
+                 int64_t len, double* out_dev, void* stream);
+
+/* Number of kernels this library has launched on behalf of `ctx` (bench.py gpu_launches). */
+int64_t rhe_launch_count(const rhe_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRHE_B200_H */

@@ -1,0 +1,604 @@
+// pyrhe_b200 C ABI + CUDA-core (SIMT) kernels.  See include/pyrhe_b200.h for the contract and
+// DESIGN.md §3 for the algorithm.  The tensor-core (tcgen05) kernels live in rhe_tc.cu and
+// replace pass A / pass B when cfg.kernel_path == RHE_PATH_TCGEN05.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "rhe_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local char g_err[512] = "";
+
+void rhe_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* rhe_last_error(void) { return g_err; }
+extern "C" int rhe_version(void) { return RHE_ABI_VERSION; }
+extern "C" int64_t rhe_launch_count(const rhe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// kernels
+
+// Column sums of the right-hand sides (used by the rank-1 mean correction of X^T R).
+__global__ void k_colsum(const float* __restrict__ rhs, int Np, double* __restrict__ colsum) {
+  const float* col = rhs + (size_t)blockIdx.x * Np;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < Np; i += blockDim.x) acc += (double)col[i];
+  __shared__ double red[32];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) colsum[blockIdx.x] = acc;
+  }
+}
+
+// Masked popcount statistics: one warp per SNP row (base.py:277-289 needs the observed mean).
+__global__ void __launch_bounds__(256)
+k_stats(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t* __restrict__ keep2,
+        int n_kept, int32_t* __restrict__ counts) {
+  int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (s >= m) return;
+  int lane = threadIdx.x & 31;
+  const uint32_t* row = reinterpret_cast<const uint32_t*>(bed + (size_t)s * pitch);
+  int n1 = 0, n2 = 0, nm = 0;
+  for (int w = lane; w < pitch / 4; w += 32) {
+    uint32_t x = __ldg(row + w), k = __ldg(keep2 + w) & 0x55555555u;
+    uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+    n2 += __popc(hi & lo & k);
+    n1 += __popc(hi & ~lo & k);
+    nm += __popc(~hi & lo & k);
+  }
+  for (int o = 16; o; o >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    nm += __shfl_xor_sync(0xffffffffu, nm, o);
+  }
+  if (lane == 0) {
+    int4 c = make_int4(n_kept - n1 - n2 - nm, n1, n2, nm);
+    reinterpret_cast<int4*>(counts)[s] = c;
+  }
+}
+
+// Per-SNP imputation fill + moments.  The fill decision replays numpy's float32 arithmetic of
+// base.py:265-285 bit for bit (round-to-nearest intrinsics, no FMA contraction); its host
+// specification is pyrhe_b200/hostmath.py:binary_fill_values.
+__global__ void k_snp_params(const int32_t* __restrict__ counts, int m, int n_kept, int binary,
+                             const double* __restrict__ uniforms, uint8_t* __restrict__ fill,
+                             double* __restrict__ mu, double* __restrict__ f2) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  int4 c = reinterpret_cast<const int4*>(counts)[s];
+  int n1 = c.y, n2 = c.z, nm = c.w, f = 0;
+  if (binary) {
+    float mean32 = (float)((double)(n1 + 2 * n2) / (double)(n_kept - nm));
+    float p = __fmul_rn(mean32, 0.5f);
+    float om = __fsub_rn(1.0f, p);
+    float d0 = __fmul_rn(om, om);
+    float d1 = __fmul_rn(__fmul_rn(2.0f, p), om);
+    float u = (float)uniforms[s];
+    f = (u < d0) ? 0 : ((u < __fadd_rn(d0, d1)) ? 1 : 2);
+  }
+  if (f == 1) n1 += nm;
+  if (f == 2) n2 += nm;
+  fill[s] = (uint8_t)f;
+  mu[s] = (double)(n1 + 2 * n2) / (double)n_kept;
+  f2[s] = (double)n2 / (double)n_kept;
+}
+
+// Test hook: decoded (optionally imputed) A2 counts, one byte per genotype.
+__global__ void k_decode(const uint8_t* __restrict__ bed, int pitch, int m,
+                         const uint8_t* __restrict__ fill, int apply_impute, int8_t* __restrict__ out) {
+  int Np = pitch * 4;
+  size_t total = (size_t)m * pitch;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int s = (int)(idx / pitch), byte = (int)(idx % pitch);
+    uint32_t b = bed[idx];
+    int f = apply_impute ? fill[s] : 3;
+    char4 v;
+    v.x = (char)rhe_code_value(b & 3u, f);
+    v.y = (char)rhe_code_value((b >> 2) & 3u, f);
+    v.z = (char)rhe_code_value((b >> 4) & 3u, f);
+    v.w = (char)rhe_code_value((b >> 6) & 3u, f);
+    reinterpret_cast<char4*>(out + (size_t)s * Np)[byte] = v;
+  }
+}
+
+// Pass A (SIMT): t_raw[s][c] += sum_i val(g_is) * R[c][i]   for a 32-SNP x chunk tile and 16 columns.
+// MODE 0: val = imputed A2 count; MODE 1: val = [count == 2] (dominance operand, rhe_dom.py:36-39).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_pass_a(const uint8_t* __restrict__ bed, int pitch, int m, const float* __restrict__ rhs, int Np,
+         int R1, const uint8_t* __restrict__ fill, double* __restrict__ t_raw, int chunk) {
+  __shared__ float Rt[16][512];
+  __shared__ uint32_t gw[32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int snp0 = blockIdx.x * 32, col0 = blockIdx.z * 16;
+  const int i_begin = blockIdx.y * chunk, i_end = min(Np, i_begin + chunk);
+  float acc[4][16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[q][c] = 0.f;
+  int fl[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int s = snp0 + warp * 4 + q;
+    fl[q] = s < m ? fill[s] : 0;
+  }
+  for (int base = i_begin; base < i_end; base += 512) {
+    for (int idx = threadIdx.x; idx < 16 * 512; idx += 256) {
+      int c = idx >> 9, i = idx & 511;
+      Rt[c][i] = (col0 + c < R1) ? __ldg(rhs + (size_t)(col0 + c) * Np + base + i) : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < 32 * 32; idx += 256) {
+      int r = idx >> 5, w = idx & 31;
+      int s = snp0 + r;
+      gw[r][w] = s < m ? __ldg(reinterpret_cast<const uint32_t*>(bed + (size_t)s * pitch) + (base >> 4) + w) : 0u;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int t = 0; t < 16; ++t) {
+      const int ind = 32 * t + lane;
+      const int word = ind >> 4, sh = (ind & 15) * 2;
+      float r[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) r[c] = Rt[c][ind];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t code = (gw[warp * 4 + q][word] >> sh) & 3u;
+        int g = rhe_code_value(code, fl[q]);
+        float v = MODE == 0 ? (float)g : (g == 2 ? 1.f : 0.f);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[q][c] = fmaf(v, r[c], acc[q][c]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float v = acc[q][c];
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      int s = snp0 + warp * 4 + q;
+      if (lane == 0 && s < m && col0 + c < R1) atomicAdd(t_raw + (size_t)s * R1 + col0 + c, (double)v);
+    }
+}
+
+// Standardisation as a rank-1 fix-up of the raw products:
+//   additive  t = r (G^T R - mu 1^T R),                      r  = 1/sqrt(mu (1 - mu/2))   base.py:291-296
+//   dominance t = r'(mu G^T R - 2 [G==2]^T R - eta 1^T R),   r' = 1/(mu (1 - mu/2)),
+//             eta = mu^2 - 2 f2 (mean of the encoded column)                                rhe_dom.py:15-41
+// plus the pass-B weights of [g==1], [g==2] and the per-SNP mean term.
+__global__ void k_standardize(int m, int Rs, int R1, int B, int n_ops, int n_sets,
+                              const double* __restrict__ t_raw, const double* __restrict__ colsum,
+                              const double* __restrict__ mu, const double* __restrict__ f2,
+                              double* __restrict__ t_std, float* __restrict__ w1, float* __restrict__ w2,
+                              double* __restrict__ shiftv) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int n_groups = n_ops * n_sets;
+  if (idx >= n_groups * m * Rs) return;
+  int c = idx % Rs, s = (idx / Rs) % m, grp = idx / (Rs * m);
+  int op = n_ops == 2 ? grp : 0, st = n_ops == 2 ? 0 : grp;
+  int col = st * Rs + c;
+  double mean = mu[s], var = mean * (1.0 - 0.5 * mean);
+  double ta = t_raw[(size_t)s * R1 + col], cs = colsum[col];
+  double t, u, a1, a2, sh;
+  if (op == 0) {
+    double r = 1.0 / sqrt(var);
+    t = r * (ta - mean * cs);
+    u = r * t;
+    a1 = u;
+    a2 = 2.0 * u;
+    sh = mean * u;
+  } else {
+    double r = 1.0 / var, eta = mean * mean - 2.0 * f2[s];
+    double t2 = t_raw[(size_t)m * R1 + (size_t)s * R1 + col];
+    t = r * (mean * ta - 2.0 * t2 - eta * cs);
+    u = r * t;
+    a1 = mean * u;
+    a2 = 2.0 * mean * u - 2.0 * u;
+    sh = eta * u;
+  }
+  t_std[((size_t)grp * m + s) * Rs + c] = t;
+  if (c < B) {
+    size_t o = ((size_t)grp * m + s) * B + c;
+    w1[o] = (float)a1;
+    w2[o] = (float)a2;
+    shiftv[o] = sh;
+  }
+}
+
+// Per-(group, bin) Gram of the standardised products and the pass-B mean term.
+//   gram[e][c1][c2] += sum_{s in bin} t[s][c1] t[s][c2];   cs[e][b] += sum_{s in bin} shiftv[s][b]
+__global__ void __launch_bounds__(256)
+k_bin_gram(int m, int Rs, int B, int K, const int32_t* __restrict__ bin_rows,
+           const int32_t* __restrict__ bin_off, const double* __restrict__ t_std,
+           const double* __restrict__ shiftv, double* __restrict__ gram, double* __restrict__ cs) {
+  const int e = blockIdx.x, k = e % K, grp = e / K;
+  const int begin = bin_off[k], end = bin_off[k + 1];
+  const int per = (end - begin + gridDim.y - 1) / gridDim.y;
+  const int lo = begin + blockIdx.y * per, hi = min(end, lo + per);
+  const double* T = t_std + (size_t)grp * m * Rs;
+  const double* SH = shiftv + (size_t)grp * m * B;
+  for (int p = threadIdx.x; p < Rs * Rs + B; p += blockDim.x) {
+    double acc = 0.0;
+    if (p < Rs * Rs) {
+      int c1 = p / Rs, c2 = p % Rs;
+      if (c2 < c1) continue;
+      for (int i = lo; i < hi; ++i) {
+        const double* row = T + (size_t)bin_rows[i] * Rs;
+        acc += row[c1] * row[c2];
+      }
+      if (lo < hi) {
+        atomicAdd(gram + ((size_t)e * Rs + c1) * Rs + c2, acc);
+        if (c1 != c2) atomicAdd(gram + ((size_t)e * Rs + c2) * Rs + c1, acc);
+      }
+    } else {
+      int b = p - Rs * Rs;
+      for (int i = lo; i < hi; ++i) acc += SH[(size_t)bin_rows[i] * B + b];
+      if (lo < hi) atomicAdd(cs + (size_t)e * B + b, acc);
+    }
+  }
+}
+
+// Pass B (SIMT): P[e][b][i] = rowscale[i] * ( sum_{s in bin} [g_is==1] w1[s][b] + [g_is==2] w2[s][b] - cs[e][b] )
+// One thread per individual, BG columns per thread, 32-SNP tiles staged in shared memory.
+template <int BG>
+__global__ void __launch_bounds__(512)
+k_pass_b(const uint8_t* __restrict__ bed, int pitch, int m, int Np, int B, int K, int n_ops,
+         const int32_t* __restrict__ bin_rows, const int32_t* __restrict__ bin_off,
+         const uint8_t* __restrict__ fill, const float* __restrict__ w1, const float* __restrict__ w2,
+         const double* __restrict__ cs, const float* __restrict__ rowscale,
+         float* __restrict__ P_out, float* __restrict__ S_accum) {
+  __shared__ uint32_t gw[32][33];
+  __shared__ float s1[32][BG], s2[32][BG];
+  __shared__ int sfill[32];
+  const int e = blockIdx.y, k = e % K, grp = e / K;
+  const int st = n_ops == 2 ? 0 : grp;
+  const int b0 = blockIdx.z * BG;
+  const int ibase = blockIdx.x * 512, i = ibase + threadIdx.x;
+  const int begin = bin_off[k], end = bin_off[k + 1];
+  const float* W1 = w1 + (size_t)grp * m * B;
+  const float* W2 = w2 + (size_t)grp * m * B;
+  double acc[BG];
+#pragma unroll
+  for (int b = 0; b < BG; ++b) acc[b] = 0.0;
+  const int word = threadIdx.x >> 4, sh = (threadIdx.x & 15) * 2;
+  for (int base = begin; base < end; base += 32) {
+    const int nrow = min(32, end - base);
+    for (int idx = threadIdx.x; idx < 32 * 32; idx += 512) {
+      int r = idx >> 5, w = idx & 31;
+      gw[r][w] = r < nrow ? __ldg(reinterpret_cast<const uint32_t*>(bed + (size_t)bin_rows[base + r] * pitch) + (ibase >> 4) + w) : 0u;
+    }
+    for (int idx = threadIdx.x; idx < 32 * BG; idx += 512) {
+      int r = idx / BG, b = idx % BG;
+      bool ok = r < nrow && b0 + b < B;
+      size_t o = ok ? (size_t)bin_rows[base + r] * B + b0 + b : 0;
+      s1[r][b] = ok ? W1[o] : 0.f;
+      s2[r][b] = ok ? W2[o] : 0.f;
+    }
+    if (threadIdx.x < 32) sfill[threadIdx.x] = threadIdx.x < nrow ? fill[bin_rows[base + threadIdx.x]] : 0;
+    __syncthreads();
+    float part[BG];
+#pragma unroll
+    for (int b = 0; b < BG; ++b) part[b] = 0.f;
+    for (int r = 0; r < nrow; ++r) {
+      int g = rhe_code_value((gw[r][word] >> sh) & 3u, sfill[r]);
+      float i1 = g == 1 ? 1.f : 0.f, i2 = g == 2 ? 1.f : 0.f;
+#pragma unroll
+      for (int b = 0; b < BG; ++b) part[b] = fmaf(i1, s1[r][b], fmaf(i2, s2[r][b], part[b]));
+    }
+#pragma unroll
+    for (int b = 0; b < BG; ++b) acc[b] += (double)part[b];
+    __syncthreads();
+  }
+  if (i < Np) {
+    const double rs = (double)rowscale[(size_t)st * Np + i];
+#pragma unroll
+    for (int b = 0; b < BG; ++b) {
+      if (b0 + b >= B) break;
+      float v = (float)(rs * (acc[b] - cs[(size_t)e * B + b0 + b]));
+      size_t o = ((size_t)e * B + b0 + b) * Np + i;
+      if (P_out) P_out[o] = v;
+      if (S_accum) S_accum[o] += v;
+    }
+  }
+}
+
+// Gram of the leave-one-out vectors: out[a][c] += sum_p (S_a[p] - P_a[p]) (S_c[p] - P_c[p]).
+// (base.py:483-486 forms S - P in fp64; base.py:578-581 sums the products in fp64.)
+#define GRAM_CHUNK 128
+#define GRAM_MAX_E 32
+__global__ void __launch_bounds__(256)
+k_loo_gram(const float* __restrict__ S, const float* __restrict__ P, int E, int64_t len,
+           double* __restrict__ out) {
+  __shared__ double d[GRAM_MAX_E][GRAM_CHUNK + 1];
+  const int npairs = E * (E + 1) / 2;
+  const int nseg = max(1, min(8, 256 / npairs));
+  // a thread owns up to 3 (pair, segment) work items: 528 pairs max for E = 32
+  double acc[3] = {0.0, 0.0, 0.0};
+  int pa[3], pc[3], seg[3];
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    int item = threadIdx.x + w * 256;
+    int pair = item % npairs;
+    seg[w] = item / npairs;
+    if (seg[w] >= nseg || (npairs > 256 && item >= npairs)) { pa[w] = -1; pc[w] = 0; continue; }
+    if (npairs > 256) seg[w] = 0;
+    // unrank pair -> (a <= c)
+    int a = 0, rem = pair;
+    while (rem >= E - a) { rem -= E - a; ++a; }
+    pa[w] = a;
+    pc[w] = a + rem;
+  }
+  const int nseg_eff = npairs > 256 ? 1 : nseg;
+  const int64_t nchunks = (len + GRAM_CHUNK - 1) / GRAM_CHUNK;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t p0 = ch * GRAM_CHUNK;
+    for (int idx = threadIdx.x; idx < E * GRAM_CHUNK; idx += 256) {
+      int a = idx / GRAM_CHUNK, p = idx % GRAM_CHUNK;
+      int64_t g = p0 + p;
+      double v = 0.0;
+      if (g < len) {
+        v = (double)S[(size_t)a * len + g];
+        if (P) v -= (double)P[(size_t)a * len + g];
+      }
+      d[a][p] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      if (pa[w] < 0) continue;
+      double s = 0.0;
+      for (int p = seg[w]; p < GRAM_CHUNK; p += nseg_eff) s += d[pa[w]][p] * d[pc[w]][p];
+      acc[w] += s;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    if (pa[w] < 0) continue;
+    atomicAdd(out + (size_t)pa[w] * E + pc[w], acc[w]);
+    if (pa[w] != pc[w]) atomicAdd(out + (size_t)pc[w] * E + pa[w], acc[w]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+
+static int validate(const rhe_config* c) {
+  if (!c) { rhe_set_error("config is NULL"); return RHE_ERR_INVALID; }
+  if (c->n_indv <= 0 || c->n_kept <= 0 || c->n_kept > c->n_indv) { rhe_set_error("bad n_indv / n_kept"); return RHE_ERR_INVALID; }
+  if (c->pitch_bytes % 128 != 0 || (int64_t)c->pitch_bytes * 4 < c->n_indv) { rhe_set_error("pitch_bytes must be a multiple of 128 and cover n_indv"); return RHE_ERR_INVALID; }
+  if (c->n_sets < 1 || c->n_sets > 2 || c->n_ops < 1 || c->n_ops > 2 || (c->n_sets == 2 && c->n_ops == 2)) { rhe_set_error("bad n_sets / n_ops"); return RHE_ERR_INVALID; }
+  if (c->n_vec < 1 || c->n_vec >= c->n_cols_set) { rhe_set_error("need 1 <= n_vec < n_cols_set"); return RHE_ERR_INVALID; }
+  if (c->n_bins < 1 || c->max_block_snps < 1) { rhe_set_error("bad n_bins / max_block_snps"); return RHE_ERR_INVALID; }
+  if (c->kernel_path != RHE_PATH_SIMT && c->kernel_path != RHE_PATH_TCGEN05) { rhe_set_error("unknown kernel_path"); return RHE_ERR_INVALID; }
+  return RHE_OK;
+}
+
+extern "C" int rhe_ctx_create(rhe_ctx** out, const rhe_config* cfg) {
+  if (!out) { rhe_set_error("out is NULL"); return RHE_ERR_INVALID; }
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc) return rc;
+  RHE_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  RHE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    rhe_set_error("pyrhe_b200 targets sm_100a (B200); device %d is sm_%d%d", cfg->device, prop.major, prop.minor);
+    return RHE_ERR_UNSUPPORTED;
+  }
+  rhe_ctx* c = new (std::nothrow) rhe_ctx();
+  if (!c) { rhe_set_error("out of host memory"); return RHE_ERR_INVALID; }
+  c->cfg = *cfg;
+  c->Np = cfg->pitch_bytes * 4;
+  c->R1 = cfg->n_sets * cfg->n_cols_set;
+  c->n_groups = cfg->n_ops * cfg->n_sets;
+  c->E_reg = c->n_groups * cfg->n_bins;
+  const size_t m = cfg->max_block_snps, Rs = cfg->n_cols_set, B = cfg->n_vec;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  alloc((void**)&c->colsum, sizeof(double) * c->R1);
+  alloc((void**)&c->counts, sizeof(int32_t) * 4 * m);
+  alloc((void**)&c->fill, m);
+  alloc((void**)&c->mu, sizeof(double) * m);
+  alloc((void**)&c->f2, sizeof(double) * m);
+  alloc((void**)&c->t_raw, sizeof(double) * cfg->n_ops * m * c->R1);
+  alloc((void**)&c->t_std, sizeof(double) * c->n_groups * m * Rs);
+  alloc((void**)&c->w1, sizeof(float) * c->n_groups * m * B);
+  alloc((void**)&c->w2, sizeof(float) * c->n_groups * m * B);
+  alloc((void**)&c->shiftv, sizeof(double) * c->n_groups * m * B);
+  alloc((void**)&c->cs, sizeof(double) * c->E_reg * B);
+  alloc((void**)&c->bin_off, sizeof(int32_t) * (cfg->n_bins + 1));
+  if (e != cudaSuccess) {
+    rhe_set_error("workspace allocation failed: %s", cudaGetErrorString(e));
+    rhe_ctx_destroy(c);
+    return RHE_ERR_CUDA;
+  }
+  if (cfg->kernel_path == RHE_PATH_TCGEN05) {
+    rc = rhe_tc_create(c);
+    if (rc) { rhe_ctx_destroy(c); return rc; }
+  }
+  *out = c;
+  return RHE_OK;
+}
+
+extern "C" int rhe_ctx_destroy(rhe_ctx* c) {
+  if (!c) return RHE_OK;
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  if (c->tc) rhe_tc_destroy(c);
+  void* ptrs[] = {c->colsum, c->counts, c->fill, c->mu, c->f2, c->t_raw, c->t_std, c->w1, c->w2, c->shiftv, c->cs, c->bin_off};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete c;
+  return RHE_OK;
+}
+
+extern "C" int rhe_set_rhs(rhe_ctx* c, const float* rhs, const float* rowscale, const uint32_t* keep2, void* stream) {
+  if (!c || !rhs || !rowscale || !keep2) { rhe_set_error("rhe_set_rhs: NULL argument"); return RHE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  c->rhs = rhs;
+  c->rowscale = rowscale;
+  c->keep2 = keep2;
+  k_colsum<<<c->R1, 256, 0, st>>>(rhs, c->Np, c->colsum);
+  RHE_LAUNCH_CHECK(c);
+  if (c->tc) return rhe_tc_set_rhs(c, st);
+  return RHE_OK;
+}
+
+extern "C" int rhe_set_uniforms(rhe_ctx* c, const double* u, int32_t count) {
+  if (!c) { rhe_set_error("ctx is NULL"); return RHE_ERR_INVALID; }
+  c->uniforms = u;
+  c->n_uniforms = count;
+  return RHE_OK;
+}
+
+extern "C" int rhe_upload_rows(const void* host_src, int64_t row_bytes, int64_t n_rows, void* dev_dst,
+                               int64_t pitch_bytes, void* stream) {
+  if (!host_src || !dev_dst || row_bytes <= 0 || n_rows < 0 || pitch_bytes < row_bytes) {
+    rhe_set_error("rhe_upload_rows: bad argument");
+    return RHE_ERR_INVALID;
+  }
+  if (n_rows == 0) return RHE_OK;
+  RHE_CUDA(cudaMemcpy2DAsync(dev_dst, (size_t)pitch_bytes, host_src, (size_t)row_bytes, (size_t)row_bytes,
+                             (size_t)n_rows, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return RHE_OK;
+}
+
+static int check_block(rhe_ctx* c, const void* bed, int m, const char* who) {
+  if (!c || !bed) { rhe_set_error("%s: NULL argument", who); return RHE_ERR_INVALID; }
+  if (m < 1 || m > c->cfg.max_block_snps) { rhe_set_error("%s: n_snps %d outside [1, %d]", who, m, c->cfg.max_block_snps); return RHE_ERR_INVALID; }
+  if (!c->keep2) { rhe_set_error("%s: rhe_set_rhs has not been called", who); return RHE_ERR_STATE; }
+  return RHE_OK;
+}
+
+static int run_stats(rhe_ctx* c, const uint8_t* bed, int m, int32_t* counts, cudaStream_t st) {
+  k_stats<<<rhe_div_up(m, 8), 256, 0, st>>>(bed, c->cfg.pitch_bytes, m, c->keep2, c->cfg.n_kept, counts);
+  RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
+static int run_params(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
+  int rc = run_stats(c, bed, m, c->counts, st);
+  if (rc) return rc;
+  if (c->cfg.impute_binary && (!c->uniforms || c->n_uniforms < m)) {
+    rhe_set_error("binary imputation needs rhe_set_uniforms with >= %d values", m);
+    return RHE_ERR_STATE;
+  }
+  k_snp_params<<<rhe_div_up(m, 256), 256, 0, st>>>(c->counts, m, c->cfg.n_kept, c->cfg.impute_binary,
+                                                    c->uniforms, c->fill, c->mu, c->f2);
+  RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
+extern "C" int rhe_block_stats(rhe_ctx* c, const uint8_t* bed, int32_t m, int32_t* counts, void* stream) {
+  int rc = check_block(c, bed, m, "rhe_block_stats");
+  if (rc) return rc;
+  if (!counts) { rhe_set_error("rhe_block_stats: counts is NULL"); return RHE_ERR_INVALID; }
+  return run_stats(c, bed, m, counts, (cudaStream_t)stream);
+}
+
+extern "C" int rhe_decode_block(rhe_ctx* c, const uint8_t* bed, int32_t m, int32_t apply_impute, int8_t* out, void* stream) {
+  int rc = check_block(c, bed, m, "rhe_decode_block");
+  if (rc) return rc;
+  if (!out) { rhe_set_error("rhe_decode_block: out is NULL"); return RHE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (apply_impute) { rc = run_params(c, bed, m, st); if (rc) return rc; }
+  k_decode<<<296, 256, 0, st>>>(bed, c->cfg.pitch_bytes, m, c->fill, apply_impute, out);
+  RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
+template <int BG>
+static void launch_pass_b(rhe_ctx* c, dim3 grid, cudaStream_t st, const uint8_t* bed, int m, const int32_t* rows,
+                          const int32_t* off, float* P_out, float* S_accum) {
+  k_pass_b<BG><<<grid, 512, 0, st>>>(bed, c->cfg.pitch_bytes, m, c->Np, c->cfg.n_vec, c->cfg.n_bins, c->cfg.n_ops,
+                                     rows, off, c->fill, c->w1, c->w2, c->cs, c->rowscale, P_out, S_accum);
+}
+
+extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, const int32_t* bin_rows,
+                                    const int32_t* bin_off_host, float* P_out, float* S_accum, double* gram_out,
+                                    void* stream) {
+  int rc = check_block(c, bed, m, "rhe_block_accumulate");
+  if (rc) return rc;
+  if (!bin_rows || !bin_off_host || !gram_out) { rhe_set_error("rhe_block_accumulate: NULL argument"); return RHE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const rhe_config& g = c->cfg;
+  const int K = g.n_bins, Rs = g.n_cols_set, B = g.n_vec;
+  rc = run_params(c, bed, m, st);
+  if (rc) return rc;
+
+  // ---- pass A
+  RHE_CUDA(cudaMemsetAsync(c->t_raw, 0, sizeof(double) * g.n_ops * (size_t)m * c->R1, st));
+  if (g.kernel_path == RHE_PATH_TCGEN05) {
+    rc = rhe_tc_pass_a(c, bed, m, st);
+    if (rc) return rc;
+  } else {
+    int chunk = 8192;
+    const int tiles = rhe_div_up(m, 32), cgroups = rhe_div_up(c->R1, 16);
+    while (chunk > 512 && (int64_t)tiles * cgroups * rhe_div_up(c->Np, chunk) < 592) chunk >>= 1;
+    dim3 grid(tiles, rhe_div_up(c->Np, chunk), cgroups);
+    k_pass_a<0><<<grid, 256, 0, st>>>(bed, g.pitch_bytes, m, c->rhs, c->Np, c->R1, c->fill, c->t_raw, chunk);
+    RHE_LAUNCH_CHECK(c);
+    if (g.n_ops == 2) {
+      k_pass_a<1><<<grid, 256, 0, st>>>(bed, g.pitch_bytes, m, c->rhs, c->Np, c->R1, c->fill,
+                                         c->t_raw + (size_t)m * c->R1, chunk);
+      RHE_LAUNCH_CHECK(c);
+    }
+  }
+  // ---- standardise, per-bin Gram, pass-B weights
+  {
+    int total = c->n_groups * m * Rs;
+    k_standardize<<<rhe_div_up(total, 256), 256, 0, st>>>(m, Rs, c->R1, B, g.n_ops, g.n_sets, c->t_raw, c->colsum,
+                                                           c->mu, c->f2, c->t_std, c->w1, c->w2, c->shiftv);
+    RHE_LAUNCH_CHECK(c);
+  }
+  int32_t* s_off_dev = c->bin_off;
+  RHE_CUDA(cudaMemcpyAsync(s_off_dev, bin_off_host, sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st));
+  RHE_CUDA(cudaMemsetAsync(gram_out, 0, sizeof(double) * (size_t)c->E_reg * Rs * Rs, st));
+  RHE_CUDA(cudaMemsetAsync(c->cs, 0, sizeof(double) * (size_t)c->E_reg * B, st));
+  k_bin_gram<<<dim3(c->E_reg, 8), 256, 0, st>>>(m, Rs, B, K, bin_rows, s_off_dev, c->t_std, c->shiftv, gram_out, c->cs);
+  RHE_LAUNCH_CHECK(c);
+  // ---- pass B
+  if (P_out || S_accum) {
+    if (g.kernel_path == RHE_PATH_TCGEN05) {
+      rc = rhe_tc_pass_b(c, bed, m, bin_rows, s_off_dev, P_out, S_accum, st);
+      if (rc) return rc;
+    } else {
+      int BG = B <= 4 ? 4 : B <= 8 ? 8 : B <= 12 ? 12 : 16;
+      dim3 grid(rhe_div_up(c->Np, 512), c->E_reg, rhe_div_up(B, BG));
+      switch (BG) {
+        case 4: launch_pass_b<4>(c, grid, st, bed, m, bin_rows, s_off_dev, P_out, S_accum); break;
+        case 8: launch_pass_b<8>(c, grid, st, bed, m, bin_rows, s_off_dev, P_out, S_accum); break;
+        case 12: launch_pass_b<12>(c, grid, st, bed, m, bin_rows, s_off_dev, P_out, S_accum); break;
+        default: launch_pass_b<16>(c, grid, st, bed, m, bin_rows, s_off_dev, P_out, S_accum); break;
+      }
+      RHE_LAUNCH_CHECK(c);
+    }
+  }
+  return RHE_OK;
+}
+
+extern "C" int rhe_loo_gram(rhe_ctx* c, const float* S, const float* P, int32_t n_est, int64_t len, double* out, void* stream) {
+  if (!c || !S || !out) { rhe_set_error("rhe_loo_gram: NULL argument"); return RHE_ERR_INVALID; }
+  if (n_est < 1 || n_est > GRAM_MAX_E) { rhe_set_error("rhe_loo_gram: n_est %d outside [1, %d]", n_est, GRAM_MAX_E); return RHE_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  RHE_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_est * n_est, st));
+  int64_t nchunks = (len + GRAM_CHUNK - 1) / GRAM_CHUNK;
+  int grid = (int)(nchunks < 148 * 4 ? nchunks : 148 * 4);
+  k_loo_gram<<<grid, 256, 0, st>>>(S, P, n_est, len, out);
+  RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}

@@ -1,0 +1,73 @@
+// Shared definitions for the pyrhe_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pyrhe_b200.h"
+
+struct rhe_ctx {
+  rhe_config cfg;
+  int Np;        // individuals incl. padding = 4 * pitch_bytes
+  int R1;        // total right-hand-side columns = n_sets * Rs
+  int n_groups;  // n_ops * n_sets
+  int E_reg;     // n_groups * K
+  // caller-owned inputs
+  const float* rhs = nullptr;
+  const float* rowscale = nullptr;
+  const uint32_t* keep2 = nullptr;
+  const double* uniforms = nullptr;
+  int n_uniforms = 0;
+  // context-owned workspaces (sized for max_block_snps)
+  double* colsum = nullptr;    // [R1]               sum over individuals of every RHS column
+  int32_t* counts = nullptr;   // [m][4]             n0 n1 n2 nmiss (kept individuals)
+  uint8_t* fill = nullptr;     // [m]                imputation fill value 0/1/2
+  double* mu = nullptr;        // [m]                mean A2 count after imputation
+  double* f2 = nullptr;        // [m]                fraction of individuals with count 2 (DOM)
+  double* t_raw = nullptr;     // [n_ops][m][R1]     G^T R and [G==2]^T R
+  double* t_std = nullptr;     // [n_groups][m][Rs]  standardised X^T R
+  float* w1 = nullptr;         // [n_groups][m][B]   pass-B weight of [g == 1]
+  float* w2 = nullptr;         // [n_groups][m][B]   pass-B weight of [g == 2]
+  double* shiftv = nullptr;    // [n_groups][m][B]   per-SNP mean term of pass B
+  double* cs = nullptr;        // [E_reg][B]         per-(bin) sum of shiftv
+  int32_t* bin_off = nullptr;  // [K + 1]            device copy of the block's bin offsets
+  void* tc = nullptr;          // tensor-core path state (rhe_tc.cu)
+  int64_t launches = 0;
+};
+
+void rhe_set_error(const char* fmt, ...);
+
+#define RHE_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      rhe_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,   \
+                    __LINE__);                                                          \
+      return RHE_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define RHE_LAUNCH_CHECK(ctx)                                                           \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess) {                                                            \
+      rhe_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_),         \
+                    __FILE__, __LINE__);                                                \
+      return RHE_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+// 2-bit PLINK code -> A2 count with the per-SNP fill for the missing code (01).
+__device__ __forceinline__ int rhe_code_value(uint32_t code, int fill) {
+  // 00 -> 0, 01 -> fill, 10 -> 1, 11 -> 2
+  return code == 1u ? fill : (int)(code >> 1) + (int)(code == 3u);
+}
+
+static inline int rhe_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// tensor-core path entry points (rhe_tc.cu)
+int rhe_tc_create(rhe_ctx* ctx);
+void rhe_tc_destroy(rhe_ctx* ctx);
+int rhe_tc_set_rhs(rhe_ctx* ctx, cudaStream_t st);
+int rhe_tc_pass_a(rhe_ctx* ctx, const uint8_t* bed, int m, cudaStream_t st);
+int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, int m, const int32_t* bin_rows,
+                  const int32_t* bin_off, float* P_out, float* S_accum, cudaStream_t st);
