@@ -116,6 +116,19 @@ int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
 int rhe_loo_gram(rhe_ctx* ctx, const float* S_dev, const float* P_dev, int32_t n_est,
                  int64_t len, double* out_dev, void* stream);
 
+/* Synthetic PLINK rows generated on the device: SNP s has A2 frequency
+ * p_s ~ U(0.05, 0.5), genotypes ~ Binomial(2, p_s) i.i.d., code 01 (missing) with probability
+ * missing_rate; counter-based hash of (seed, first_snp + row, byte) so any row range can be
+ * regenerated.  Bench / test utility: 125 GB of genotypes never has to cross PCIe. */
+int rhe_synth_genotypes(uint8_t* bed_dev, int64_t n_rows, int64_t pitch_bytes, int32_t n_indv,
+                        int64_t first_snp, uint64_t seed, float missing_rate, void* stream);
+
+/* Per-phase device timing of rhe_block_accumulate (CUDA events on the launch stream).
+ * phases_ms double[4] = {stats + imputation parameters, pass A, standardise + Gram, pass B},
+ * summed over the calls since the last collect; the call synchronises the events. */
+int rhe_timing_enable(rhe_ctx* ctx, int32_t enable);
+int rhe_timing_collect(rhe_ctx* ctx, double* phases_ms, int32_t* n_calls);
+
 /* Number of kernels this library has launched on behalf of `ctx` (bench.py gpu_launches). */
 int64_t rhe_launch_count(const rhe_ctx* ctx);
 

@@ -41,6 +41,10 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rhe_loo_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "rhe_launch_count": (C.c_int64, [C.c_void_p]),
+    "rhe_synth_genotypes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_float,
+                                      C.c_void_p]),
+    "rhe_timing_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "rhe_timing_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

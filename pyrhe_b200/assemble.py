@@ -157,3 +157,57 @@ def trace_sums_row(T: np.ndarray, M_row: np.ndarray, N: int, E: int) -> np.ndarr
     out = (T[:E, :E] - N) * MM / float(N) ** 2
     out[MM == 0] = 0
     return out
+
+
+def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo: np.ndarray, M_tab: np.ndarray,
+                           trait: int = 0, nxe_quirk: bool = True):
+    """Vectorised `normal_equations` over all jackknife samples (the production path).
+
+    XX [S, E, E], G_loo [S, E_reg, Rs, Rs], M_tab [S, E]  ->  T [S, E+1, E+1], q [S, E+1]."""
+    E, E_reg, B, C, N = plan.E, plan.E_reg, plan.B, plan.C, ht.N
+    S = XX.shape[0]
+    zs, ws, yc = plan.cols_Z(), plan.cols_W(), plan.col_y(trait)
+    Mf = np.asarray(M_tab, dtype=np.float64)
+    MM = Mf[:, :, None] * Mf[:, None, :]
+    V = XX.astype(np.float64).copy()
+    T = np.zeros((S, E + 1, E + 1))
+    q = np.zeros((S, E + 1))
+    if C > 0:
+        QWtZ = ht.Q @ ht.WtZ
+        H = np.empty((S, E, C, B))
+        WtLU = np.empty((S, E, C, B))
+        H[:, :E_reg] = G_loo[:, :, ws, zs]
+        WtLU[:, :E_reg] = G_loo[:, :, ws, ws] @ QWtZ
+        Hq = H
+        if plan.has_nxe:
+            H[:, E_reg] = ht.nxe_H
+            WtLU[:, E_reg] = ht.nxe_WtLU
+            if nxe_quirk:
+                Hq = H.copy()
+                Hq[:, E_reg, :, :-1] = 0
+                WtLU[:, E_reg, :, :-1] = 0
+        QH = np.einsum("cd,sedb->secb", ht.Q, H)
+        QHq = QH if Hq is H else np.einsum("cd,sedb->secb", ht.Q, Hq)
+        r1 = np.einsum("sacb,secb->sae", H, QH)
+        r2 = np.einsum("sacb,secb->sae", WtLU, QHq)
+        V += r2 - 2 * r1
+    V /= B
+    np.divide(V, MM, out=T[:, :E, :E], where=MM != 0)
+    tr = np.full((S, E), float(N))
+    if plan.model == "genie" and E > plan.K:
+        zz = np.einsum("sebb->se", G_loo[:, plan.K:E_reg, zs, zs])
+        tr[:, plan.K:E_reg] = zz / (B * Mf[:, plan.K:E_reg])
+        if plan.has_nxe:
+            tr[:, E_reg] = ht.nxe_tr / (B * Mf[:, E_reg])
+    if C > 0:
+        tr = tr - np.einsum("secb,cb->se", H, QWtZ) / (B * Mf)
+    T[:, :E, E] = tr
+    T[:, E, :E] = tr
+    T[:, E, E] = N - C
+    yxxy = np.empty((S, E))
+    yxxy[:, :E_reg] = G_loo[:, :, yc, yc]
+    if plan.has_nxe:
+        yxxy[:, E_reg] = ht.nxe_yxxy[trait]
+    np.divide(yxxy, Mf, out=q[:, :E], where=Mf != 0)
+    q[:, E] = ht.yy_res[trait]
+    return T, q

@@ -374,6 +374,43 @@ k_loo_gram(const float* __restrict__ S, const float* __restrict__ P, int E, int6
   }
 }
 
+// Synthetic genotypes: one thread per packed byte (4 genotypes).
+__device__ __forceinline__ uint64_t rhe_mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void k_synth(uint8_t* __restrict__ bed, int64_t n_rows, int64_t pitch, int n_indv, int64_t first_snp,
+                        uint64_t seed, float missing_rate) {
+  const int64_t total = n_rows * pitch;
+  const int row_bytes = (n_indv + 3) / 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / pitch;
+    const int byte = (int)(idx % pitch);
+    uint32_t out = 0;
+    if (byte < row_bytes) {
+      const uint64_t snp = (uint64_t)(first_snp + r);
+      const float p = 0.05f + 0.45f * (float)(rhe_mix64(seed ^ (snp * 0xD1342543DE82EF95ull)) >> 40) * (1.0f / 16777216.0f);
+      const uint32_t thr = (uint32_t)(p * 65536.0f), mthr = (uint32_t)(missing_rate * 65536.0f);
+      const uint64_t h = rhe_mix64(rhe_mix64(seed + snp) ^ ((uint64_t)byte * 0x2545F4914F6CDD1Dull));
+      const uint64_t h2 = rhe_mix64(h);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (byte * 4 + t >= n_indv) break;
+        const uint32_t a = (uint32_t)(h >> (16 * t)) & 0xFFFFu, b = (uint32_t)(h2 >> (16 * t)) & 0xFFFFu;
+        const uint32_t c = (uint32_t)(rhe_mix64(h2 + t) & 0xFFFFu);
+        const int g = (a < thr) + (b < thr);
+        uint32_t code = g == 0 ? 0u : (g == 1 ? 2u : 3u);
+        if (c < mthr) code = 1u;
+        out |= code << (2 * t);
+      }
+    }
+    bed[idx] = (uint8_t)out;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 
@@ -440,6 +477,7 @@ extern "C" int rhe_ctx_destroy(rhe_ctx* c) {
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
   if (c->tc) rhe_tc_destroy(c);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   void* ptrs[] = {c->colsum, c->counts, c->fill, c->mu, c->f2, c->t_raw, c->t_std, c->w1, c->w2, c->shiftv, c->cs, c->bin_off};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete c;
@@ -537,8 +575,14 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
   cudaStream_t st = (cudaStream_t)stream;
   const rhe_config& g = c->cfg;
   const int K = g.n_bins, Rs = g.n_cols_set, B = g.n_vec;
+  cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (c->timing) {
+    for (auto& e : tev) { RHE_CUDA(cudaEventCreate(&e)); c->ev.push_back(e); }
+    RHE_CUDA(cudaEventRecord(tev[0], st));
+  }
   rc = run_params(c, bed, m, st);
   if (rc) return rc;
+  if (c->timing) RHE_CUDA(cudaEventRecord(tev[1], st));
 
   // ---- pass A
   RHE_CUDA(cudaMemsetAsync(c->t_raw, 0, sizeof(double) * g.n_ops * (size_t)m * c->R1, st));
@@ -558,6 +602,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
       RHE_LAUNCH_CHECK(c);
     }
   }
+  if (c->timing) RHE_CUDA(cudaEventRecord(tev[2], st));
   // ---- standardise, per-bin Gram, pass-B weights
   {
     int total = c->n_groups * m * Rs;
@@ -571,6 +616,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
   RHE_CUDA(cudaMemsetAsync(c->cs, 0, sizeof(double) * (size_t)c->E_reg * B, st));
   k_bin_gram<<<dim3(c->E_reg, 8), 256, 0, st>>>(m, Rs, B, K, bin_rows, s_off_dev, c->t_std, c->shiftv, gram_out, c->cs);
   RHE_LAUNCH_CHECK(c);
+  if (c->timing) RHE_CUDA(cudaEventRecord(tev[3], st));
   // ---- pass B
   if (P_out || S_accum) {
     if (g.kernel_path == RHE_PATH_TCGEN05) {
@@ -588,6 +634,43 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
       RHE_LAUNCH_CHECK(c);
     }
   }
+  if (c->timing) RHE_CUDA(cudaEventRecord(tev[4], st));
+  return RHE_OK;
+}
+
+extern "C" int rhe_synth_genotypes(uint8_t* bed, int64_t n_rows, int64_t pitch, int32_t n_indv, int64_t first_snp,
+                                   uint64_t seed, float missing_rate, void* stream) {
+  if (!bed || n_rows < 0 || pitch <= 0 || n_indv <= 0 || (int64_t)(n_indv + 3) / 4 > pitch) {
+    rhe_set_error("rhe_synth_genotypes: bad argument");
+    return RHE_ERR_INVALID;
+  }
+  if (n_rows == 0) return RHE_OK;
+  k_synth<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(bed, n_rows, pitch, n_indv, first_snp, seed, missing_rate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { rhe_set_error("k_synth launch failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
+  return RHE_OK;
+}
+
+extern "C" int rhe_timing_enable(rhe_ctx* c, int32_t enable) {
+  if (!c) { rhe_set_error("ctx is NULL"); return RHE_ERR_INVALID; }
+  c->timing = enable != 0;
+  return RHE_OK;
+}
+
+extern "C" int rhe_timing_collect(rhe_ctx* c, double* phases_ms, int32_t* n_calls) {
+  if (!c || !phases_ms || !n_calls) { rhe_set_error("rhe_timing_collect: NULL argument"); return RHE_ERR_INVALID; }
+  for (int i = 0; i < 4; ++i) phases_ms[i] = 0.0;
+  *n_calls = (int32_t)(c->ev.size() / 5);
+  for (size_t k = 0; k + 4 < c->ev.size(); k += 5) {
+    RHE_CUDA(cudaEventSynchronize(c->ev[k + 4]));
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0.f;
+      RHE_CUDA(cudaEventElapsedTime(&ms, c->ev[k + i], c->ev[k + i + 1]));
+      phases_ms[i] += (double)ms;
+    }
+  }
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  c->ev.clear();
   return RHE_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/pyrhe_b200.h"
 
 struct rhe_ctx {
@@ -31,6 +32,8 @@ struct rhe_ctx {
   int32_t* bin_off = nullptr;  // [K + 1]            device copy of the block's bin offsets
   void* tc = nullptr;          // tensor-core path state (rhe_tc.cu)
   int64_t launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // 5 events per timed rhe_block_accumulate call
 };
 
 void rhe_set_error(const char* fmt, ...);

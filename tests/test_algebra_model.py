@@ -64,3 +64,22 @@ def test_binary_fill_rule_matches_reference_decisions():
         has_missing = (r == 3).any(0)
         ref_fill = np.where(has_missing, np.max(np.where(r == 3, imp[:, a:b], 0), axis=0), fill)
         np.testing.assert_array_equal(fill[has_missing], ref_fill[has_missing])
+
+
+@pytest.mark.parametrize("name", ["rhe_cov_binary", "dom_cov", "genie_full_cov", "genie_full_nocov", "rhe_overlap"])
+def test_batched_assembly_equals_scalar_specification(name):
+    from pyrhe_b200.assemble import normal_equations_batch
+    p = oracle_problem(name)
+    plan = plan_for(p)
+    ht, Y_res = host_terms(plan, p.Z, p.W, p.y, p.env)
+    pieces = run_model(p.packed, p.n_indv_original, p.annot, p.Z, Y_res, p.W, p.env, p.missing_indv,
+                       p.num_jack, p.impute, p.seed, plan)
+    J = p.num_jack
+    if J == 1:
+        return
+    T, q = assemble_all(plan, ht, pieces, J)
+    G_tot = pieces["G_blk"].sum(0)
+    G_loo = np.concatenate([G_tot[None] - pieces["G_blk"], G_tot[None]], axis=0)
+    Tb, qb = normal_equations_batch(plan, ht, pieces["XX"], G_loo, pieces["M"])
+    np.testing.assert_allclose(Tb, T, rtol=1e-12, atol=1e-12 * np.abs(T).max())
+    np.testing.assert_allclose(qb, q, rtol=1e-12, atol=1e-12 * np.abs(q).max())
