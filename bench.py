@@ -32,6 +32,8 @@ WORKLOADS = {
     # BASELINE.json configs[4]: the configuration the metric is quoted on
     "config5": dict(N=500_000, M=1_000_000, J=100, K=8, C=5, B=10, model="rhe"),
     "config2": dict(N=200_000, M=500_000, J=100, K=8, C=5, B=10, model="rhe"),
+    # a few config2-sized blocks: short enough to run under ncu
+    "profile": dict(N=200_000, M=20_000, J=4, K=8, C=5, B=10, model="rhe"),
     "small": dict(N=20_000, M=40_000, J=20, K=8, C=5, B=10, model="rhe"),
 }
 METRIC = "rhe_genotype_throughput"
