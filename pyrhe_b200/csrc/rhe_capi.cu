@@ -620,7 +620,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
   // ---- pass B
   if (P_out || S_accum) {
     if (g.kernel_path == RHE_PATH_TCGEN05) {
-      rc = rhe_tc_pass_b(c, bed, m, bin_rows, s_off_dev, P_out, S_accum, st);
+      rc = rhe_tc_pass_b(c, bed, m, bin_rows, s_off_dev, bin_off_host, P_out, S_accum, st);
       if (rc) return rc;
     } else {
       int BG = B <= 4 ? 4 : B <= 8 ? 8 : B <= 12 ? 12 : 16;

@@ -73,4 +73,5 @@ void rhe_tc_destroy(rhe_ctx* ctx);
 int rhe_tc_set_rhs(rhe_ctx* ctx, cudaStream_t st);
 int rhe_tc_pass_a(rhe_ctx* ctx, const uint8_t* bed, int m, cudaStream_t st);
 int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, int m, const int32_t* bin_rows,
-                  const int32_t* bin_off, float* P_out, float* S_accum, cudaStream_t st);
+                  const int32_t* bin_off, const int32_t* bin_off_host, float* P_out, float* S_accum,
+                  cudaStream_t st);

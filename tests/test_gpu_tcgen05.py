@@ -1,0 +1,79 @@
+"""GPU: the int8 tcgen05 / TMEM / TMA kernel path (RHE_PATH_TCGEN05) against the golden vectors, the
+CUDA-core path and a size-independent property at a larger shape."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, oracle_problem
+from device_model import assemble_all
+from test_gpu_parity import make_engine, plan_for, solve_all
+
+pytestmark = pytest.mark.gpu
+TC = 1
+RHE_CASES = ["rhe_cov_binary", "rhe_nocov_mean", "rhe_overlap", "rhe_one_block", "rhe_example_shape"]
+
+
+@pytest.mark.parametrize("name", RHE_CASES)
+def test_tcgen05_T_q_sigma_match_reference(name):
+    g = load_golden(name)
+    for t in range(g["T"].shape[0]):
+        p = oracle_problem(name, trait=t)
+        plan = plan_for(p)
+        eng, ht, _ = make_engine(p, plan, kernel_path=TC)
+        pieces = eng.run()
+        eng.close()
+        T, q = assemble_all(plan, ht, pieces, p.num_jack)
+        np.testing.assert_allclose(T, g["T"][t], rtol=1e-5, atol=1e-6 * np.abs(g["T"][t]).max())
+        np.testing.assert_allclose(q, g["q"][t], rtol=1e-5, atol=1e-6 * np.abs(g["q"][t]).max())
+        sig = solve_all(T, q)
+        np.testing.assert_allclose(sig[-1], g["res_sigma_ests_total"][t], rtol=1e-5, atol=2e-5 * float(np.var(p.y)))
+
+
+def test_tcgen05_vectors_match_simt_path():
+    """XXz partials and totals of the two kernel paths agree to fixed-point resolution."""
+    p = oracle_problem("rhe_cov_binary")
+    plan = plan_for(p)
+    out = {}
+    for path in (0, TC):
+        eng, _, _ = make_engine(p, plan, kernel_path=path)
+        pieces = eng.run()
+        out[path] = (eng.S.cpu().numpy().astype(np.float64), eng.P_all.cpu().numpy().astype(np.float64), pieces)
+        eng.close()
+    scale = np.abs(out[0][0]).max()
+    np.testing.assert_allclose(out[TC][0], out[0][0], rtol=0, atol=2e-6 * scale)
+    np.testing.assert_allclose(out[TC][1], out[0][1], rtol=0, atol=2e-6 * scale)
+    np.testing.assert_allclose(out[TC][2]["G_blk"], out[0][2]["G_blk"], rtol=1e-6, atol=1e-6 * np.abs(out[0][2]["G_blk"]).max())
+
+
+def test_tcgen05_larger_shape_against_simt_and_split_invariance():
+    """N = 20k, M = 4k, several CTAs per dimension: tensor path == CUDA-core path, and the exact
+    integer accumulation makes pass A independent of the jackknife partition (J = 2 vs J = 4 totals)."""
+    from pyrhe_b200 import synth
+    from pyrhe_b200.assemble import PathPlan
+    from pyrhe_b200.engine import RheEngine
+    from pyrhe_b200.hostmath import host_terms
+    rng = np.random.default_rng(5)
+    N, M, K, B = 20_000, 4_096, 4, 10
+    packed = synth.pack_counts(synth.random_counts(N, M, rng, missing_rate=0.002))
+    annot = synth.random_annot(M, K, rng)
+    Z = rng.standard_normal((N, B))
+    W = rng.standard_normal((N, 3))
+    y = rng.standard_normal((N, 1))
+    y -= y.mean()
+    plan = PathPlan(model="rhe", K=K, B=B, C=3)
+    ht, Y_res = host_terms(plan, Z, W, y, None)
+    res = {}
+    for path, J in ((0, 4), (TC, 4), (TC, 2)):
+        eng = RheEngine(plan, n_indv=N, keep=np.ones(N, bool), annot=annot, num_jack=J, impute="binary", seed=3,
+                        kernel_path=path)
+        eng.set_rhs(Z, W, Y_res)
+        eng.load_genotypes(packed)
+        pieces = eng.run()
+        res[(path, J)] = (pieces, eng.S.cpu().numpy().astype(np.float64))
+        eng.close()
+    a, b = res[(0, 4)], res[(TC, 4)]
+    np.testing.assert_allclose(b[0]["XX"], a[0]["XX"], rtol=2e-6)
+    np.testing.assert_allclose(b[0]["G_blk"], a[0]["G_blk"], rtol=1e-5, atol=1e-6 * np.abs(a[0]["G_blk"]).max())
+    np.testing.assert_allclose(b[1], a[1], rtol=0, atol=2e-6 * np.abs(a[1]).max())
+    # totals do not depend on how SNPs are grouped into blocks
+    Gt4, Gt2 = b[0]["G_blk"].sum(0), res[(TC, 2)][0]["G_blk"].sum(0)
+    np.testing.assert_allclose(Gt2, Gt4, rtol=1e-9, atol=1e-9 * np.abs(Gt4).max())
