@@ -16,7 +16,6 @@
 #include <cstdio>
 #include "rhe_common.cuh"
 
-#define TC_STAGES 4
 #define TC_TILE_A 16384          // 128 rows x 128 bytes
 #define TC_THREADS 192
 
@@ -34,8 +33,7 @@ struct TcState {
   int8_t* rq = nullptr;       // [NBa][Np]   limb l of column c at row l * R1p + c, permuted individual order
   double* col_dq = nullptr;   // [R1]        power-of-two dequantisation factor of every RHS column
   int32_t* pos_rows = nullptr;  // [cap_pos]   block-local SNP row of every bin-sorted position (-1 = padding)
-  uint8_t* pos32_bin = nullptr; // [cap_pos/32] bin of every 32-position group (255 = padding)
-  int32_t* pstart = nullptr;    // [K + 1]     first position of every bin (multiples of 32)
+  int32_t* pstart = nullptr;    // [K + 1]     first position of every bin (multiples of 128)
   int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights
   unsigned int* wmax = nullptr; // [B]         max |weight| per column (float bits)
   int cap_pos = 0;
@@ -153,10 +151,46 @@ __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
   return r;
 }
 
+// Ring depths.  A "super-stage" is 128 rows x 128 packed bytes (512 individuals): every decode thread
+// owns one row and streams its own 128-byte lines with cp.async (thread-private, so no block barrier
+// is needed to consume them), TC_PK super-stages deep.  Each super-stage is decoded into four int8
+// A tiles (128 individuals each) that cycle through a ring of TC_AS slots.
+#define TC_PK 3
+#define TC_AS 2
+#define TC_PACKED (128 * 128)
+
 struct TcSmem {
-  uint64_t full_a[TC_STAGES], full_b[TC_STAGES], empty[TC_STAGES], acc_full;
+  uint64_t full_a[TC_AS], empty_a[TC_AS], full_b[TC_AS], empty_b[TC_AS], acc_full;
   uint32_t tmem_base;
 };
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Thread t streams 128 bytes of its row into slot layout [chunk 0..7][thread][16 B] (conflict-free reads).
+__device__ __forceinline__ void tc_issue_row(uint8_t* slot, int t, const uint8_t* src) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) cp_async16(slot + c * 2048 + t * 16, src + c * 16);
+}
+
+__device__ __forceinline__ void tc_setup(TcSmem* sm, int warp, uint32_t tmem_cols) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_AS; ++s) {
+      mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1);
+      mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1);
+    }
+    mbar_init(&sm->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&sm->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
 
 // ------------------------------------------------------------------------------------------ pass A
 // grid = (SNP tiles of 128, splits over individuals).  t_raw[s][c] += dq[c] * sum_i g_is * q_ic  (exact).
@@ -167,43 +201,47 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileA = smem;
-  uint8_t* tileB = smem + TC_STAGES * TC_TILE_A;
+  uint8_t* tileB = tileA + TC_AS * TC_TILE_A;
   const int tileB_bytes = NB * 128;
-  TcSmem* sm = reinterpret_cast<TcSmem*>(tileB + TC_STAGES * tileB_bytes);
+  uint8_t* packed = tileB + TC_AS * tileB_bytes;
+  TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int snp0 = blockIdx.x * 128;
   const int i_begin = blockIdx.y * chunk, i_end = min(Np, i_begin + chunk);
-  const int n_stage = (i_end - i_begin) >> 7;
-  if (n_stage <= 0) return;
+  const int n_ss = (i_end - i_begin) >> 9;          // super-stages of 512 individuals
+  if (n_ss <= 0) return;
+  const int n_sub = n_ss * 4;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty[s], 1); }
-    mbar_init(&sm->acc_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(&sm->tmem_base, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  tc_setup(sm, warp, tmem_cols);
   const uint32_t tmem = sm->tmem_base;
 
   if (warp < 4) {
-    // ---- decode producers: thread t owns SNP row snp0 + t
     const int t = threadIdx.x;
     const int s = min(snp0 + t, m - 1);
     const uint32_t tab = ((uint32_t)fill[s] << 8) | (1u << 16) | (2u << 24);
-    const uint4* src = reinterpret_cast<const uint4*>(bed + (size_t)s * pitch + (i_begin >> 2));
-    uint4 lo = ldg_nc(src), hi = ldg_nc(src + 1);
-    for (int k = 0; k < n_stage; ++k) {
-      const int st = k % TC_STAGES, use = k / TC_STAGES;
-      uint4 nlo = lo, nhi = hi;
-      if (k + 1 < n_stage) { nlo = ldg_nc(src + 2 * (k + 1)); nhi = ldg_nc(src + 2 * (k + 1) + 1); }
-      mbar_wait(&sm->empty[st], (use & 1) ^ 1);
-      tc_store_row(tileA + st * TC_TILE_A, t, lo, hi, tab);
-      fence_proxy_async();
-      mbar_arrive(&sm->full_a[st]);
-      lo = nlo; hi = nhi;
+    const uint8_t* src = bed + (size_t)s * pitch + (i_begin >> 2);
+#pragma unroll
+    for (int pre = 0; pre < TC_PK - 1; ++pre) {
+      if (pre < n_ss) tc_issue_row(packed + pre * TC_PACKED, t, src + pre * 128);
+      cp_async_commit();
+    }
+    for (int ss = 0; ss < n_ss; ++ss) {
+      const int nxt = ss + TC_PK - 1;
+      if (nxt < n_ss) tc_issue_row(packed + (nxt % TC_PK) * TC_PACKED, t, src + (size_t)nxt * 128);
+      cp_async_commit();
+      cp_async_wait<TC_PK - 1>();
+      const uint8_t* slot = packed + (ss % TC_PK) * TC_PACKED + t * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int sub = ss * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
+        const uint4 lo = *reinterpret_cast<const uint4*>(slot + (2 * q) * 2048);
+        const uint4 hi = *reinterpret_cast<const uint4*>(slot + (2 * q + 1) * 2048);
+        mbar_wait(&sm->empty_a[a], (use & 1) ^ 1);
+        tc_store_row(tileA + a * TC_TILE_A, t, lo, hi, tab);
+        fence_proxy_async();
+        mbar_arrive(&sm->full_a[a]);
+      }
     }
     // ---- epilogue: lane quadrant `warp` of TMEM, row = SNP
     mbar_wait(&sm->acc_full, 0);
@@ -229,27 +267,28 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     tc_fence_before();
   } else if (warp == 4) {
     if (lane == 0) {
-      for (int k = 0; k < n_stage; ++k) {
-        const int st = k % TC_STAGES, use = k / TC_STAGES;
-        mbar_wait(&sm->empty[st], (use & 1) ^ 1);
-        mbar_expect_tx(&sm->full_b[st], (uint32_t)tileB_bytes);
-        tma_load_2d(tileB + st * tileB_bytes, &tm_rq, &sm->full_b[st], i_begin + k * 128, 0);
+      for (int sub = 0; sub < n_sub; ++sub) {
+        const int a = sub % TC_AS, use = sub / TC_AS;
+        mbar_wait(&sm->empty_b[a], (use & 1) ^ 1);
+        mbar_expect_tx(&sm->full_b[a], (uint32_t)tileB_bytes);
+        tma_load_2d(tileB + a * tileB_bytes, &tm_rq, &sm->full_b[a], i_begin + sub * 128, 0);
       }
     }
   } else {
     if (lane == 0) {
       const uint32_t idesc = idesc_i8(128, NB, 0);
-      for (int k = 0; k < n_stage; ++k) {
-        const int st = k % TC_STAGES, use = k / TC_STAGES;
-        mbar_wait(&sm->full_a[st], use & 1);
-        mbar_wait(&sm->full_b[st], use & 1);
+      for (int sub = 0; sub < n_sub; ++sub) {
+        const int a = sub % TC_AS, use = sub / TC_AS;
+        mbar_wait(&sm->full_a[a], use & 1);
+        mbar_wait(&sm->full_b[a], use & 1);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(tileA + st * TC_TILE_A), b0 = smem_u32(tileB + st * tileB_bytes);
+        const uint32_t a0 = smem_u32(tileA + a * TC_TILE_A), b0 = smem_u32(tileB + a * tileB_bytes);
 #pragma unroll
         for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: advance 32 bytes inside the swizzle atom
           umma_i8(tmem, smem_desc_sw128(a0 + j * 32, 16, 1024), smem_desc_sw128(b0 + j * 32, 16, 1024), idesc,
-                  (uint32_t)((k | j) != 0));
-        umma_commit(&sm->empty[st]);
+                  (uint32_t)((sub | j) != 0));
+        umma_commit(&sm->empty_a[a]);
+        umma_commit(&sm->empty_b[a]);
       }
       umma_commit(&sm->acc_full);
     }
@@ -259,94 +298,103 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------ pass B
-// grid = individual tiles of 128.  Positions = SNP rows sorted by bin, every bin padded to a multiple of 32
-// (one MMA K-step never mixes bins); bin k accumulates in TMEM columns [k * NC, (k + 1) * NC).
+// grid = (tiles of 512 individuals, bins).  Positions = the bin's SNP rows, padded to a multiple of 128
+// with zero-weight rows.  Each stage gathers 128 rows x 128 packed bytes (a full DRAM line per row), decodes
+// them into four MN-major A tiles (128 individuals each) that share one Uq tile, and accumulates four
+// 128 x NC int32 tiles in TMEM.
 __global__ void __launch_bounds__(TC_THREADS)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np,
-            int n_stage, const int32_t* __restrict__ pos_rows, const uint8_t* __restrict__ pos32_bin,
-            const uint8_t* __restrict__ fill, int K, int B, int Bp, int L, int NC, int F,
-            const unsigned int* __restrict__ wmax, const int32_t* __restrict__ pstart, const double* __restrict__ cs,
-            const float* __restrict__ rowscale, float* __restrict__ P_out, float* __restrict__ S_accum,
-            uint32_t tmem_cols) {
+            const int32_t* __restrict__ pos_rows, const uint8_t* __restrict__ fill, int B, int Bp, int L, int NC, int F,
+            const unsigned int* __restrict__ wmax, const int32_t* __restrict__ pstart, const int32_t* __restrict__ bin_off,
+            const double* __restrict__ cs, const float* __restrict__ rowscale, float* __restrict__ P_out,
+            float* __restrict__ S_accum, uint32_t tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileA = smem;
-  uint8_t* tileB = smem + TC_STAGES * TC_TILE_A;
+  uint8_t* tileB = tileA + TC_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
-  TcSmem* sm = reinterpret_cast<TcSmem*>(tileB + TC_STAGES * tileB_bytes);
+  uint8_t* packed = tileB + TC_AS * tileB_bytes;
+  TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * 128;
+  const int k = blockIdx.y;
+  const int i0 = blockIdx.x * 512;
+  const int p0 = pstart[k];
+  const int n_st = (pstart[k + 1] - p0) >> 7;
+  const int n_real = bin_off[k + 1] - bin_off[k];
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty[s], 1); }
-    mbar_init(&sm->acc_full, 1);
-    fence_barrier_init();
+  if (n_st == 0) {   // empty bin in this block: X_k = 0, so P = 0 (S unchanged)
+    if (P_out)
+      for (int idx = threadIdx.x; idx < B * 512; idx += TC_THREADS) {
+        const int b = idx >> 9, i = i0 + (idx & 511);
+        if (i < Np) P_out[((size_t)k * B + b) * Np + i] = 0.f;
+      }
+    return;
   }
-  if (warp == 5) tmem_alloc(&sm->tmem_base, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+
+  tc_setup(sm, warp, tmem_cols);
   const uint32_t tmem = sm->tmem_base;
 
   if (warp < 4) {
     const int t = threadIdx.x;
     const uint8_t* base = bed + (i0 >> 2);
-    int row = pos_rows[t];
-    uint32_t tab = 0x02010000u;
-    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-    if (row >= 0) {
-      tab |= (uint32_t)fill[row] << 8;
-      const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)row * pitch);
-      lo = ldg_nc(src); hi = ldg_nc(src + 1);
-    }
-    for (int k = 0; k < n_stage; ++k) {
-      const int st = k % TC_STAGES, use = k / TC_STAGES;
-      uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo;
-      uint32_t ntab = 0x02010000u;
-      if (k + 1 < n_stage) {
-        const int nrow = pos_rows[(k + 1) * 128 + t];
-        if (nrow >= 0) {
-          ntab |= (uint32_t)fill[nrow] << 8;
-          const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)nrow * pitch);
-          nlo = ldg_nc(src); nhi = ldg_nc(src + 1);
-        }
+    const int32_t* rows = pos_rows + p0 + t;
+#pragma unroll
+    for (int pre = 0; pre < TC_PK - 1; ++pre) {
+      if (pre < n_st) {
+        const int row = rows[pre * 128];
+        if (row >= 0) tc_issue_row(packed + pre * TC_PACKED, t, base + (size_t)row * pitch);
       }
-      mbar_wait(&sm->empty[st], (use & 1) ^ 1);
-      tc_store_row(tileA + st * TC_TILE_A, t, lo, hi, tab);
-      fence_proxy_async();
-      mbar_arrive(&sm->full_a[st]);
-      lo = nlo; hi = nhi; tab = ntab;
+      cp_async_commit();
     }
-    // ---- epilogue: TMEM lane = position inside the 128-individual tile
+    for (int st = 0; st < n_st; ++st) {
+      const int nxt = st + TC_PK - 1;
+      if (nxt < n_st) {
+        const int row = rows[nxt * 128];
+        if (row >= 0) tc_issue_row(packed + (nxt % TC_PK) * TC_PACKED, t, base + (size_t)row * pitch);
+      }
+      cp_async_commit();
+      cp_async_wait<TC_PK - 1>();
+      const int row = rows[st * 128];
+      const uint32_t tab = 0x02010000u | (row >= 0 ? (uint32_t)fill[row] << 8 : 0u);
+      const uint8_t* slot = packed + (st % TC_PK) * TC_PACKED + t * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int sub = st * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
+        const uint4 lo = *reinterpret_cast<const uint4*>(slot + (2 * q) * 2048);
+        const uint4 hi = *reinterpret_cast<const uint4*>(slot + (2 * q + 1) * 2048);
+        mbar_wait(&sm->empty_a[a], (use & 1) ^ 1);
+        tc_store_row(tileA + a * TC_TILE_A, t, lo, hi, tab);
+        fence_proxy_async();
+        mbar_arrive(&sm->full_a[a]);
+      }
+    }
+    // ---- epilogue: TMEM lane = position inside the 128-individual tile q
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
-    const int i = i0 + (t & ~15) + tc_perm16(t & 15);
-    const double rs = (double)rowscale[i];
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int k = 0; k < K; ++k) {
-      const bool has = pstart[k + 1] > pstart[k];
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
+      const bool in_range = i < Np;
+      const double rs = in_range ? (double)rowscale[i] : 0.0;
       for (int c0 = 0; c0 < Bp; c0 += 4) {
         double val[4] = {0.0, 0.0, 0.0, 0.0};
-        if (has) {
-          double wgt = 1.0;
-          for (int l = 0; l < L; ++l) {
-            int32_t v[4];
-            tmem_ld4(trow + (uint32_t)(k * NC + l * Bp + c0), v);
+        double wgt = 1.0;
+        for (int l = 0; l < L; ++l) {
+          int32_t v[4];
+          tmem_ld4(trow + (uint32_t)(q * NC + l * Bp + c0), v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) val[j] += wgt * (double)v[j];
-            wgt *= 256.0;
-          }
+          for (int j = 0; j < 4; ++j) val[j] += wgt * (double)v[j];
+          wgt *= 256.0;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int b = c0 + j;
-          if (b < B) {
+          if (b < B && in_range) {
             // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
             const int e = (int)((wmax[b] >> 23) & 255u) - 126;
-            const double x = rs * (ldexp(val[j], e - F) - cs[(size_t)k * B + b]);
+            const float xf = (float)(rs * (ldexp(val[j], e - F) - cs[(size_t)k * B + b]));
             const size_t o = ((size_t)k * B + b) * Np + i;
-            const float xf = (float)x;
             if (P_out) P_out[o] = xf;
             if (S_accum) S_accum[o] += xf;
           }
@@ -356,31 +404,32 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     tc_fence_before();
   } else if (warp == 4) {
     if (lane == 0) {
-      for (int k = 0; k < n_stage; ++k) {
-        const int st = k % TC_STAGES, use = k / TC_STAGES;
-        mbar_wait(&sm->empty[st], (use & 1) ^ 1);
-        mbar_expect_tx(&sm->full_b[st], (uint32_t)tileB_bytes);
-        tma_load_2d(tileB + st * tileB_bytes, &tm_uq, &sm->full_b[st], k * 128, 0);
+      for (int st = 0; st < n_st; ++st) {
+        const int b = st % TC_AS, use = st / TC_AS;
+        mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
+        mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
+        tma_load_2d(tileB + b * tileB_bytes, &tm_uq, &sm->full_b[b], p0 + st * 128, 0);
       }
     }
   } else {
     if (lane == 0) {
       const uint32_t idesc = idesc_i8(128, NC, 1);   // A is MN-major: 128 individuals contiguous per SNP row
-      unsigned long long started = 0ull;
-      for (int k = 0; k < n_stage; ++k) {
-        const int st = k % TC_STAGES, use = k / TC_STAGES;
-        mbar_wait(&sm->full_a[st], use & 1);
-        mbar_wait(&sm->full_b[st], use & 1);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(tileA + st * TC_TILE_A), b0 = smem_u32(tileB + st * tileB_bytes);
-        for (int j = 0; j < 4; ++j) {   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
-          const uint32_t bin = pos32_bin[k * 4 + j];
-          if (bin == 255u) continue;
-          umma_i8(tmem + bin * NC, smem_desc_sw128(a0 + j * 4096, TC_TILE_A, 1024), smem_desc_sw128(b0 + j * 32, 16, 1024),
-                  idesc, (uint32_t)((started >> bin) & 1ull));
-          started |= 1ull << bin;
+      for (int st = 0; st < n_st; ++st) {
+        const int b = st % TC_AS, useb = st / TC_AS;
+        mbar_wait(&sm->full_b[b], useb & 1);
+        const uint32_t b0 = smem_u32(tileB + b * tileB_bytes);
+        const int ksteps = min(4, (n_real - st * 128 + 31) >> 5);   // all-padding K-steps are skipped
+        for (int q = 0; q < 4; ++q) {
+          const int sub = st * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
+          mbar_wait(&sm->full_a[a], use & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(tileA + a * TC_TILE_A);
+          for (int j = 0; j < ksteps; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
+            umma_i8(tmem + q * NC, smem_desc_sw128(a0 + j * 4096, TC_TILE_A, 1024), smem_desc_sw128(b0 + j * 32, 16, 1024),
+                    idesc, (uint32_t)((st | j) != 0));
+          umma_commit(&sm->empty_a[a]);
         }
-        umma_commit(&sm->empty[st]);
+        umma_commit(&sm->empty_b[b]);
       }
       umma_commit(&sm->acc_full);
     }
@@ -427,14 +476,11 @@ k_tc_quant_rhs(const float* __restrict__ rhs, int Np, int R1p, int L, int F, int
 }
 
 __global__ void k_tc_positions(const int32_t* __restrict__ bin_rows, const int32_t* __restrict__ bin_off,
-                               const int32_t* __restrict__ pstart, int32_t* __restrict__ pos_rows,
-                               uint8_t* __restrict__ pos32_bin) {
+                               const int32_t* __restrict__ pstart, int32_t* __restrict__ pos_rows) {
   const int k = blockIdx.y;
   const int n = bin_off[k + 1] - bin_off[k], p0 = pstart[k], span = pstart[k + 1] - p0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < span; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < span; i += gridDim.x * blockDim.x)
     pos_rows[p0 + i] = i < n ? bin_rows[bin_off[k] + i] : -1;
-    if ((i & 31) == 0) pos32_bin[(p0 + i) >> 5] = (uint8_t)k;
-  }
 }
 
 __global__ void k_tc_wmax(const float* __restrict__ w1, int m, int B, unsigned int* __restrict__ wmax) {
@@ -467,6 +513,9 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int tc_smem_bytes(int n_cols) {
+  return TC_AS * (TC_TILE_A + n_cols * 128) + TC_PK * TC_PACKED + (int)sizeof(TcSmem) + 1024;
+}
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
 int rhe_tc_create(rhe_ctx* c) {
@@ -481,7 +530,7 @@ int rhe_tc_create(rhe_ctx* c) {
   s->NBa = round_up(s->L * s->R1p, 16);
   s->Bp = round_up(g.n_vec, 4);
   s->NCb = round_up(s->L * s->Bp, 16);
-  if (s->NBa > 256 || g.n_bins * s->NCb > 512 || g.n_bins > 64) {
+  if (s->NBa > 256 || 4 * s->NCb > 512 || g.n_bins > 64) {
     delete s;
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     return RHE_ERR_UNSUPPORTED;
@@ -504,8 +553,7 @@ int rhe_tc_create(rhe_ctx* c) {
   if (e != cudaSuccess) { rhe_set_error("tensor-core workspace allocation failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
-  const int smem_a = TC_STAGES * (TC_TILE_A + s->NBa * 128) + (int)sizeof(TcSmem) + 1024;
-  const int smem_b = TC_STAGES * (TC_TILE_A + s->NCb * 128) + (int)sizeof(TcSmem) + 1024;
+  const int smem_a = tc_smem_bytes(s->NBa), smem_b = tc_smem_bytes(s->NCb);
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
   return RHE_OK;
@@ -514,7 +562,7 @@ int rhe_tc_create(rhe_ctx* c) {
 void rhe_tc_destroy(rhe_ctx* c) {
   TcState* s = (TcState*)c->tc;
   if (!s) return;
-  void* ptrs[] = {s->rq, s->col_dq, s->pos_rows, s->pos32_bin, s->pstart, s->uq, s->wmax};
+  void* ptrs[] = {s->rq, s->col_dq, s->pos_rows, s->pstart, s->uq, s->wmax};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete s;
   c->tc = nullptr;
@@ -530,15 +578,15 @@ int rhe_tc_set_rhs(rhe_ctx* c, cudaStream_t st) {
 int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
   const int tiles = rhe_div_up(m, 128);
-  // enough CTAs for two waves of 2 CTAs/SM, but at least 16 stages (2048 individuals) per CTA
+  // about four CTAs per SM in total (two resident), at least 8 super-stages (4096 individuals) per CTA
   int splits = rhe_div_up(148 * 4, tiles);
-  int chunk = round_up(rhe_div_up(c->Np, splits), 128);
-  if (chunk < 2048) chunk = 2048;
+  int chunk = round_up(rhe_div_up(c->Np, splits), 512);
+  if (chunk < 4096) chunk = 4096;
   if (chunk > c->Np) chunk = c->Np;
   splits = rhe_div_up(c->Np, chunk);
-  const int smem = TC_STAGES * (TC_TILE_A + s->NBa * 128) + (int)sizeof(TcSmem) + 1024;
-  k_tc_pass_a<<<dim3(tiles, splits), TC_THREADS, smem, st>>>(s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p,
-                                                            s->L, c->fill, s->col_dq, c->t_raw, chunk, pow2_cols(s->NBa));
+  k_tc_pass_a<<<dim3(tiles, splits), TC_THREADS, tc_smem_bytes(s->NBa), st>>>(
+      s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw, chunk,
+      pow2_cols(s->NBa));
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
@@ -548,19 +596,17 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   TcState* s = (TcState*)c->tc;
   const rhe_config& g = c->cfg;
   const int K = g.n_bins, B = g.n_vec;
-  // bin-sorted positions: every bin padded to a multiple of 32 rows, the total to a multiple of 128
+  // bin-sorted positions: every bin padded to a multiple of 128 rows (one stage never mixes bins)
   int32_t pstart[65];
   pstart[0] = 0;
-  for (int k = 0; k < K; ++k) pstart[k + 1] = pstart[k] + round_up(bin_off_host[k + 1] - bin_off_host[k], 32);
+  for (int k = 0; k < K; ++k) pstart[k + 1] = pstart[k] + round_up(bin_off_host[k + 1] - bin_off_host[k], 128);
   const int n_pos = round_up(pstart[K] > 0 ? pstart[K] : 1, 128);
   if (n_pos > s->cap_pos) {
     RHE_CUDA(cudaStreamSynchronize(st));
     if (s->pos_rows) cudaFree(s->pos_rows);
-    if (s->pos32_bin) cudaFree(s->pos32_bin);
     if (s->uq) cudaFree(s->uq);
     s->cap_pos = round_up(n_pos + n_pos / 8, 128);
     RHE_CUDA(cudaMalloc((void**)&s->pos_rows, sizeof(int32_t) * s->cap_pos));
-    RHE_CUDA(cudaMalloc((void**)&s->pos32_bin, s->cap_pos / 32));
     RHE_CUDA(cudaMalloc((void**)&s->uq, (size_t)s->NCb * s->cap_pos));
     RHE_CUDA(cudaMemset(s->uq, 0, (size_t)s->NCb * s->cap_pos));
     int rc = tc_encode_2d(s, &s->tm_uq, s->uq, (uint64_t)s->cap_pos, (uint64_t)s->NCb, (uint32_t)s->NCb);
@@ -568,19 +614,17 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   }
   RHE_CUDA(cudaMemcpyAsync(s->pstart, pstart, sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st));
   RHE_CUDA(cudaMemsetAsync(s->pos_rows, 0xFF, sizeof(int32_t) * n_pos, st));
-  RHE_CUDA(cudaMemsetAsync(s->pos32_bin, 0xFF, n_pos / 32, st));
   RHE_CUDA(cudaMemsetAsync(s->wmax, 0, sizeof(unsigned int) * B, st));
-  k_tc_positions<<<dim3(rhe_div_up(m, 256), K), 256, 0, st>>>(bin_rows, bin_off, s->pstart, s->pos_rows, s->pos32_bin);
+  k_tc_positions<<<dim3(rhe_div_up(m, 256), K), 256, 0, st>>>(bin_rows, bin_off, s->pstart, s->pos_rows);
   RHE_LAUNCH_CHECK(c);
   k_tc_wmax<<<rhe_div_up(m * B, 256), 256, 0, st>>>(c->w1, m, B, s->wmax);
   RHE_LAUNCH_CHECK(c);
   k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B, 256), 256, 0, st>>>(c->w1, s->pos_rows, n_pos, s->cap_pos, B, s->Bp, s->L, s->F,
                                                                     s->wmax, s->uq);
   RHE_LAUNCH_CHECK(c);
-  const int smem = TC_STAGES * (TC_TILE_A + s->NCb * 128) + (int)sizeof(TcSmem) + 1024;
-  k_tc_pass_b<<<c->Np / 128, TC_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, s->pos_rows, s->pos32_bin,
-                                                     c->fill, K, B, s->Bp, s->L, s->NCb, s->F, s->wmax, s->pstart, c->cs,
-                                                     c->rowscale, P_out, S_accum, pow2_cols(K * s->NCb));
+  k_tc_pass_b<<<dim3(rhe_div_up(c->Np, 512), K), TC_THREADS, tc_smem_bytes(s->NCb), st>>>(
+      s->tm_uq, bed, g.pitch_bytes, c->Np, s->pos_rows, c->fill, B, s->Bp, s->L, s->NCb, s->F, s->wmax, s->pstart, bin_off,
+      c->cs, c->rowscale, P_out, S_accum, pow2_cols(4 * s->NCb));
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }

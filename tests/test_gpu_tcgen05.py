@@ -62,18 +62,19 @@ def test_tcgen05_larger_shape_against_simt_and_split_invariance():
     plan = PathPlan(model="rhe", K=K, B=B, C=3)
     ht, Y_res = host_terms(plan, Z, W, y, None)
     res = {}
-    for path, J in ((0, 4), (TC, 4), (TC, 2)):
-        eng = RheEngine(plan, n_indv=N, keep=np.ones(N, bool), annot=annot, num_jack=J, impute="binary", seed=3,
+    for path, J, impute in ((0, 4, "binary"), (TC, 4, "binary"), (TC, 4, "mean"), (TC, 2, "mean")):
+        eng = RheEngine(plan, n_indv=N, keep=np.ones(N, bool), annot=annot, num_jack=J, impute=impute, seed=3,
                         kernel_path=path)
         eng.set_rhs(Z, W, Y_res)
         eng.load_genotypes(packed)
         pieces = eng.run()
-        res[(path, J)] = (pieces, eng.S.cpu().numpy().astype(np.float64))
+        res[(path, J, impute)] = (pieces, eng.S.cpu().numpy().astype(np.float64))
         eng.close()
-    a, b = res[(0, 4)], res[(TC, 4)]
+    a, b = res[(0, 4, "binary")], res[(TC, 4, "binary")]
     np.testing.assert_allclose(b[0]["XX"], a[0]["XX"], rtol=2e-6)
     np.testing.assert_allclose(b[0]["G_blk"], a[0]["G_blk"], rtol=1e-5, atol=1e-6 * np.abs(a[0]["G_blk"]).max())
     np.testing.assert_allclose(b[1], a[1], rtol=0, atol=2e-6 * np.abs(a[1]).max())
-    # totals do not depend on how SNPs are grouped into blocks
-    Gt4, Gt2 = b[0]["G_blk"].sum(0), res[(TC, 2)][0]["G_blk"].sum(0)
+    # totals do not depend on how SNPs are grouped into blocks ("mean" imputation: the binary rule
+    # indexes its uniforms by block-local SNP, base.py:510, so it legitimately depends on J)
+    Gt4, Gt2 = res[(TC, 4, "mean")][0]["G_blk"].sum(0), res[(TC, 2, "mean")][0]["G_blk"].sum(0)
     np.testing.assert_allclose(Gt2, Gt4, rtol=1e-9, atol=1e-9 * np.abs(Gt4).max())
