@@ -24,8 +24,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct TcState {
-  int L = 4;            // limbs per fixed-point value
-  int F = 30;           // fixed-point magnitude bits: |q| <= 2^F, F = 8 L - 2
+  int L = 3;            // limbs per fixed-point value (PYRHE_B200_LIMBS)
+  int F = 22;           // fixed-point magnitude bits: |q| <= 2^F, F = 8 L - 2
   int R1p = 0;          // RHS columns rounded up to 4
   int NBa = 0;          // pass A MMA N  = round16(L * R1p)
   int Bp = 0;           // pass-B columns rounded up to 4
@@ -99,7 +99,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, int32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// value[j] = sum_l 256^l * limb_l[j] for four adjacent columns; limb l sits `stride` columns further on
+__device__ __forceinline__ void tmem_combine4(uint32_t taddr, int L, int stride, double (&val)[4]) {
+  int32_t v[4][4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l)
+    if (l < L) tmem_ld4(taddr + (uint32_t)(l * stride), v[l]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double acc = 0.0;
+#pragma unroll
+    for (int l = 3; l >= 0; --l)
+      if (l < L) acc = acc * 256.0 + (double)v[l][j];
+    val[j] = acc;
+  }
 }
 
 // Shared-memory matrix descriptor, 128B swizzle, version 1 (cute::UMMA::SmemDescriptor).
@@ -157,10 +173,11 @@ __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
 // A tiles (128 individuals each) that cycle through a ring of TC_AS slots.
 #define TC_PK 3
 #define TC_AS 2
+#define TC_BS 4          // B-operand (TMA) ring: deep enough to hide the L2 -> smem latency
 #define TC_PACKED (128 * 128)
 
 struct TcSmem {
-  uint64_t full_a[TC_AS], empty_a[TC_AS], full_b[TC_AS], empty_b[TC_AS], acc_full;
+  uint64_t full_a[TC_AS], empty_a[TC_AS], full_b[TC_BS], empty_b[TC_BS], acc_full;
   uint32_t tmem_base;
 };
 
@@ -179,10 +196,8 @@ __device__ __forceinline__ void tc_issue_row(uint8_t* slot, int t, const uint8_t
 
 __device__ __forceinline__ void tc_setup(TcSmem* sm, int warp, uint32_t tmem_cols) {
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_AS; ++s) {
-      mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1);
-      mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1);
-    }
+    for (int s = 0; s < TC_AS; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
+    for (int s = 0; s < TC_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
     mbar_init(&sm->acc_full, 1);
     fence_barrier_init();
   }
@@ -203,7 +218,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   uint8_t* tileA = smem;
   uint8_t* tileB = tileA + TC_AS * TC_TILE_A;
   const int tileB_bytes = NB * 128;
-  uint8_t* packed = tileB + TC_AS * tileB_bytes;
+  uint8_t* packed = tileB + TC_BS * tileB_bytes;
   TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,15 +264,8 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     const int snp = snp0 + t;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < R1p; c0 += 4) {
-      double val[4] = {0.0, 0.0, 0.0, 0.0};
-      double wgt = 1.0;
-      for (int l = 0; l < L; ++l) {
-        int32_t v[4];
-        tmem_ld4(trow + (uint32_t)(l * R1p + c0), v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) val[j] += wgt * (double)v[j];
-        wgt *= 256.0;
-      }
+      double val[4];
+      tmem_combine4(trow + (uint32_t)c0, L, R1p, val);
       if (snp < m) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -268,27 +276,27 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   } else if (warp == 4) {
     if (lane == 0) {
       for (int sub = 0; sub < n_sub; ++sub) {
-        const int a = sub % TC_AS, use = sub / TC_AS;
-        mbar_wait(&sm->empty_b[a], (use & 1) ^ 1);
-        mbar_expect_tx(&sm->full_b[a], (uint32_t)tileB_bytes);
-        tma_load_2d(tileB + a * tileB_bytes, &tm_rq, &sm->full_b[a], i_begin + sub * 128, 0);
+        const int b = sub % TC_BS, use = sub / TC_BS;
+        mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
+        mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
+        tma_load_2d(tileB + b * tileB_bytes, &tm_rq, &sm->full_b[b], i_begin + sub * 128, 0);
       }
     }
   } else {
     if (lane == 0) {
       const uint32_t idesc = idesc_i8(128, NB, 0);
       for (int sub = 0; sub < n_sub; ++sub) {
-        const int a = sub % TC_AS, use = sub / TC_AS;
+        const int a = sub % TC_AS, use = sub / TC_AS, b = sub % TC_BS, useb = sub / TC_BS;
+        mbar_wait(&sm->full_b[b], useb & 1);
         mbar_wait(&sm->full_a[a], use & 1);
-        mbar_wait(&sm->full_b[a], use & 1);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(tileA + a * TC_TILE_A), b0 = smem_u32(tileB + a * tileB_bytes);
+        const uint32_t a0 = smem_u32(tileA + a * TC_TILE_A), b0 = smem_u32(tileB + b * tileB_bytes);
 #pragma unroll
         for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: advance 32 bytes inside the swizzle atom
           umma_i8(tmem, smem_desc_sw128(a0 + j * 32, 16, 1024), smem_desc_sw128(b0 + j * 32, 16, 1024), idesc,
                   (uint32_t)((sub | j) != 0));
         umma_commit(&sm->empty_a[a]);
-        umma_commit(&sm->empty_b[a]);
+        umma_commit(&sm->empty_b[b]);
       }
       umma_commit(&sm->acc_full);
     }
@@ -313,7 +321,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   uint8_t* tileA = smem;
   uint8_t* tileB = tileA + TC_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
-  uint8_t* packed = tileB + TC_AS * tileB_bytes;
+  uint8_t* packed = tileB + TC_BS * tileB_bytes;
   TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -378,15 +386,8 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       const bool in_range = i < Np;
       const double rs = in_range ? (double)rowscale[i] : 0.0;
       for (int c0 = 0; c0 < Bp; c0 += 4) {
-        double val[4] = {0.0, 0.0, 0.0, 0.0};
-        double wgt = 1.0;
-        for (int l = 0; l < L; ++l) {
-          int32_t v[4];
-          tmem_ld4(trow + (uint32_t)(q * NC + l * Bp + c0), v);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) val[j] += wgt * (double)v[j];
-          wgt *= 256.0;
-        }
+        double val[4];
+        tmem_combine4(trow + (uint32_t)(q * NC + c0), L, Bp, val);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int b = c0 + j;
@@ -396,7 +397,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
             const float xf = (float)(rs * (ldexp(val[j], e - F) - cs[(size_t)k * B + b]));
             const size_t o = ((size_t)k * B + b) * Np + i;
             if (P_out) P_out[o] = xf;
-            if (S_accum) S_accum[o] += xf;
+            if (S_accum) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
           }
         }
       }
@@ -405,7 +406,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   } else if (warp == 4) {
     if (lane == 0) {
       for (int st = 0; st < n_st; ++st) {
-        const int b = st % TC_AS, use = st / TC_AS;
+        const int b = st % TC_BS, use = st / TC_BS;
         mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
         mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
         tma_load_2d(tileB + b * tileB_bytes, &tm_uq, &sm->full_b[b], p0 + st * 128, 0);
@@ -415,7 +416,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     if (lane == 0) {
       const uint32_t idesc = idesc_i8(128, NC, 1);   // A is MN-major: 128 individuals contiguous per SNP row
       for (int st = 0; st < n_st; ++st) {
-        const int b = st % TC_AS, useb = st / TC_AS;
+        const int b = st % TC_BS, useb = st / TC_BS;
         mbar_wait(&sm->full_b[b], useb & 1);
         const uint32_t b0 = smem_u32(tileB + b * tileB_bytes);
         const int ksteps = min(4, (n_real - st * 128 + 31) >> 5);   // all-padding K-steps are skipped
@@ -514,7 +515,7 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int tc_smem_bytes(int n_cols) {
-  return TC_AS * (TC_TILE_A + n_cols * 128) + TC_PK * TC_PACKED + (int)sizeof(TcSmem) + 1024;
+  return TC_AS * TC_TILE_A + TC_BS * n_cols * 128 + TC_PK * TC_PACKED + (int)sizeof(TcSmem) + 1024;
 }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
@@ -523,7 +524,7 @@ int rhe_tc_create(rhe_ctx* c) {
   if (g.n_ops != 1 || g.n_sets != 1) { rhe_set_error("RHE_PATH_TCGEN05 currently covers the RHE model (one operand, one RHS set)"); return RHE_ERR_UNSUPPORTED; }
   TcState* s = new TcState();
   const char* envL = getenv("PYRHE_B200_LIMBS");
-  s->L = envL ? atoi(envL) : 4;
+  s->L = envL ? atoi(envL) : 3;
   if (s->L < 2 || s->L > 4) { delete s; rhe_set_error("PYRHE_B200_LIMBS must be 2..4"); return RHE_ERR_INVALID; }
   s->F = 8 * s->L - 2;
   s->R1p = round_up(c->R1, 4);
