@@ -152,13 +152,25 @@ __device__ __forceinline__ uint4 tc_expand(uint32_t w, uint32_t tab) {
   return r;
 }
 
-// Decode 32 packed bytes (128 individuals of one SNP row) into row `r` of a swizzled 128 x 128B tile.
-__device__ __forceinline__ void tc_store_row(uint8_t* tile, int r, const uint4& lo, const uint4& hi, uint32_t tab) {
-  uint8_t* row = tile + r * 128;
+// Explicit shared-state-space accesses (32-bit addresses): the dynamic-smem base is re-aligned with integer
+// arithmetic, after which the compiler can no longer prove the address space and would emit generic LD/ST.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Decode 32 packed bytes (128 individuals of one SNP row) into row `r` of a swizzled 128 x 128B tile
+// (`tile` is a shared-space address).
+__device__ __forceinline__ void tc_store_row(uint32_t tile, int r, const uint4& lo, const uint4& hi, uint32_t tab) {
+  const uint32_t row = tile + r * 128;
   const int x = r & 7;
   const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-  for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ x) << 4)) = tc_expand(w[c], tab);
+  for (int c = 0; c < 8; ++c) sts128(row + ((c ^ x) << 4), tc_expand(w[c], tab));
 }
 
 __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
@@ -181,15 +193,15 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Thread t streams 128 bytes of its row into slot layout [chunk 0..7][thread][16 B] (conflict-free reads).
-__device__ __forceinline__ void tc_issue_row(uint8_t* slot, int t, const uint8_t* src) {
+__device__ __forceinline__ void tc_issue_row(uint32_t slot, int t, const uint8_t* src) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) cp_async16(slot + c * 2048 + t * 16, src + c * 16);
 }
@@ -220,6 +232,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   const int tileB_bytes = NB * 128;
   uint8_t* packed = tileB + TC_BS * tileB_bytes;
   TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
+  const uint32_t tileA_s = smem_u32(tileA), packed_s = smem_u32(packed);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int snp0 = blockIdx.x * 128;
@@ -238,22 +251,22 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     const uint8_t* src = bed + (size_t)s * pitch + (i_begin >> 2);
 #pragma unroll
     for (int pre = 0; pre < TC_PK - 1; ++pre) {
-      if (pre < n_ss) tc_issue_row(packed + pre * TC_PACKED, t, src + pre * 128);
+      if (pre < n_ss) tc_issue_row(packed_s + pre * TC_PACKED, t, src + pre * 128);
       cp_async_commit();
     }
     for (int ss = 0; ss < n_ss; ++ss) {
       const int nxt = ss + TC_PK - 1;
-      if (nxt < n_ss) tc_issue_row(packed + (nxt % TC_PK) * TC_PACKED, t, src + (size_t)nxt * 128);
+      if (nxt < n_ss) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, src + (size_t)nxt * 128);
       cp_async_commit();
       cp_async_wait<TC_PK - 1>();
-      const uint8_t* slot = packed + (ss % TC_PK) * TC_PACKED + t * 16;
+      const uint32_t slot = packed_s + (ss % TC_PK) * TC_PACKED + t * 16;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int sub = ss * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
-        const uint4 lo = *reinterpret_cast<const uint4*>(slot + (2 * q) * 2048);
-        const uint4 hi = *reinterpret_cast<const uint4*>(slot + (2 * q + 1) * 2048);
+        const uint4 lo = lds128(slot + (2 * q) * 2048);
+        const uint4 hi = lds128(slot + (2 * q + 1) * 2048);
         mbar_wait(&sm->empty_a[a], (use & 1) ^ 1);
-        tc_store_row(tileA + a * TC_TILE_A, t, lo, hi, tab);
+        tc_store_row(tileA_s + a * TC_TILE_A, t, lo, hi, tab);
         fence_proxy_async();
         mbar_arrive(&sm->full_a[a]);
       }
@@ -323,6 +336,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   const int tileB_bytes = NC * 128;
   uint8_t* packed = tileB + TC_BS * tileB_bytes;
   TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
+  const uint32_t tileA_s = smem_u32(tileA), packed_s = smem_u32(packed);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.y;
@@ -351,7 +365,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     for (int pre = 0; pre < TC_PK - 1; ++pre) {
       if (pre < n_st) {
         const int row = rows[pre * 128];
-        if (row >= 0) tc_issue_row(packed + pre * TC_PACKED, t, base + (size_t)row * pitch);
+        if (row >= 0) tc_issue_row(packed_s + pre * TC_PACKED, t, base + (size_t)row * pitch);
       }
       cp_async_commit();
     }
@@ -359,20 +373,20 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       const int nxt = st + TC_PK - 1;
       if (nxt < n_st) {
         const int row = rows[nxt * 128];
-        if (row >= 0) tc_issue_row(packed + (nxt % TC_PK) * TC_PACKED, t, base + (size_t)row * pitch);
+        if (row >= 0) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, base + (size_t)row * pitch);
       }
       cp_async_commit();
       cp_async_wait<TC_PK - 1>();
       const int row = rows[st * 128];
       const uint32_t tab = 0x02010000u | (row >= 0 ? (uint32_t)fill[row] << 8 : 0u);
-      const uint8_t* slot = packed + (st % TC_PK) * TC_PACKED + t * 16;
+      const uint32_t slot = packed_s + (st % TC_PK) * TC_PACKED + t * 16;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int sub = st * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
-        const uint4 lo = *reinterpret_cast<const uint4*>(slot + (2 * q) * 2048);
-        const uint4 hi = *reinterpret_cast<const uint4*>(slot + (2 * q + 1) * 2048);
+        const uint4 lo = lds128(slot + (2 * q) * 2048);
+        const uint4 hi = lds128(slot + (2 * q + 1) * 2048);
         mbar_wait(&sm->empty_a[a], (use & 1) ^ 1);
-        tc_store_row(tileA + a * TC_TILE_A, t, lo, hi, tab);
+        tc_store_row(tileA_s + a * TC_TILE_A, t, lo, hi, tab);
         fence_proxy_async();
         mbar_arrive(&sm->full_a[a]);
       }
