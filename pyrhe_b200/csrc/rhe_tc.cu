@@ -10,14 +10,17 @@
 // MN-major A operand (instruction-descriptor bit 15).  The small B operands (Rq / Uq tiles) arrive by
 // TMA; accumulators live in TMEM and are read back with tcgen05.ld in the epilogue.
 //
-// Warp roles (192 threads): warps 0-3 decode packed bytes -> int8 tile (then run the epilogue, one TMEM
-// lane quadrant each), warp 4 lane 0 issues TMA, warp 5 allocates TMEM and lane 0 issues tcgen05.mma.
+// Warp roles: TC_G groups of four decode warps (group g expands sub-tiles q = g mod TC_G of every super-stage into
+// A slot g, so the groups overlap each other's load / fence / barrier latencies; afterwards they run the epilogue,
+// one TMEM lane quadrant per warp), then one TMA warp and one warp that allocates TMEM and issues tcgen05.mma.
 #include <cuda.h>
 #include <cstdio>
 #include "rhe_common.cuh"
 
 #define TC_TILE_A 16384          // 128 rows x 128 bytes
-#define TC_THREADS 192
+#define TC_G 2                                  // decode groups of 4 warps; group g owns A slot g
+#define TC_DECODE_WARPS (4 * TC_G)
+#define TC_THREADS (32 * (TC_DECODE_WARPS + 2))
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -184,7 +187,7 @@ __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
 // is needed to consume them), TC_PK super-stages deep.  Each super-stage is decoded into four int8
 // A tiles (128 individuals each) that cycle through a ring of TC_AS slots.
 #define TC_PK 3
-#define TC_AS 2
+#define TC_AS TC_G
 #define TC_BS 4          // B-operand (TMA) ring: deep enough to hide the L2 -> smem latency
 #define TC_PACKED (128 * 128)
 
@@ -201,9 +204,14 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Thread t streams 128 bytes of its row into slot layout [chunk 0..7][thread][16 B] (conflict-free reads).
-__device__ __forceinline__ void tc_issue_row(uint32_t slot, int t, const uint8_t* src) {
+// Group g fetches only the chunks of the sub-tiles it decodes (q = g, g + TC_G, ...: chunks 2q, 2q + 1).
+__device__ __forceinline__ void tc_issue_row(uint32_t slot, int t, int g, const uint8_t* src) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) cp_async16(slot + c * 2048 + t * 16, src + c * 16);
+  for (int q = 0; q < 4; q += TC_G) {
+    const int c = 2 * (q + g);
+    cp_async16(slot + c * 2048 + t * 16, src + c * 16);
+    cp_async16(slot + (c + 1) * 2048 + t * 16, src + (c + 1) * 16);
+  }
 }
 
 __device__ __forceinline__ void tc_setup(TcSmem* sm, int warp, uint32_t tmem_cols) {
@@ -213,7 +221,7 @@ __device__ __forceinline__ void tc_setup(TcSmem* sm, int warp, uint32_t tmem_col
     mbar_init(&sm->acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&sm->tmem_base, tmem_cols);
+  if (warp == TC_DECODE_WARPS + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -221,7 +229,7 @@ __device__ __forceinline__ void tc_setup(TcSmem* sm, int warp, uint32_t tmem_col
 
 // ------------------------------------------------------------------------------------------ pass A
 // grid = (SNP tiles of 128, splits over individuals).  t_raw[s][c] += dq[c] * sum_i g_is * q_ic  (exact).
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict__ bed, int pitch, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
             double* __restrict__ t_raw, int chunk, uint32_t tmem_cols) {
@@ -244,24 +252,25 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   tc_setup(sm, warp, tmem_cols);
   const uint32_t tmem = sm->tmem_base;
 
-  if (warp < 4) {
-    const int t = threadIdx.x;
+  if (warp < TC_DECODE_WARPS) {
+    const int t = threadIdx.x & 127, g = warp >> 2;
     const int s = min(snp0 + t, m - 1);
     const uint32_t tab = ((uint32_t)fill[s] << 8) | (1u << 16) | (2u << 24);
     const uint8_t* src = bed + (size_t)s * pitch + (i_begin >> 2);
 #pragma unroll
     for (int pre = 0; pre < TC_PK - 1; ++pre) {
-      if (pre < n_ss) tc_issue_row(packed_s + pre * TC_PACKED, t, src + pre * 128);
+      if (pre < n_ss) tc_issue_row(packed_s + pre * TC_PACKED, t, g, src + pre * 128);
       cp_async_commit();
     }
     for (int ss = 0; ss < n_ss; ++ss) {
       const int nxt = ss + TC_PK - 1;
-      if (nxt < n_ss) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, src + (size_t)nxt * 128);
+      if (nxt < n_ss) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, g, src + (size_t)nxt * 128);
       cp_async_commit();
       cp_async_wait<TC_PK - 1>();
       const uint32_t slot = packed_s + (ss % TC_PK) * TC_PACKED + t * 16;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q0 = 0; q0 < 4; q0 += TC_G) {
+        const int q = q0 + g;
         const int sub = ss * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
         const uint4 lo = lds128(slot + (2 * q) * 2048);
         const uint4 hi = lds128(slot + (2 * q + 1) * 2048);
@@ -275,8 +284,8 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
     const int snp = snp0 + t;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < R1p; c0 += 4) {
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = 4 * g; c0 < R1p; c0 += 4 * TC_G) {
       double val[4];
       tmem_combine4(trow + (uint32_t)c0, L, R1p, val);
       if (snp < m) {
@@ -286,7 +295,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == TC_DECODE_WARPS) {
     if (lane == 0) {
       for (int sub = 0; sub < n_sub; ++sub) {
         const int b = sub % TC_BS, use = sub / TC_BS;
@@ -315,7 +324,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     }
   }
   __syncthreads();
-  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
+  if (warp == TC_DECODE_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------ pass B
@@ -323,7 +332,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 // with zero-weight rows.  Each stage gathers 128 rows x 128 packed bytes (a full DRAM line per row), decodes
 // them into four MN-major A tiles (128 individuals each) that share one Uq tile, and accumulates four
 // 128 x NC int32 tiles in TMEM.
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np,
             const int32_t* __restrict__ pos_rows, const uint8_t* __restrict__ fill, int B, int Bp, int L, int NC, int F,
             const unsigned int* __restrict__ wmax, const int32_t* __restrict__ pstart, const int32_t* __restrict__ bin_off,
@@ -357,15 +366,15 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   tc_setup(sm, warp, tmem_cols);
   const uint32_t tmem = sm->tmem_base;
 
-  if (warp < 4) {
-    const int t = threadIdx.x;
+  if (warp < TC_DECODE_WARPS) {
+    const int t = threadIdx.x & 127, g = warp >> 2;
     const uint8_t* base = bed + (i0 >> 2);
     const int32_t* rows = pos_rows + p0 + t;
 #pragma unroll
     for (int pre = 0; pre < TC_PK - 1; ++pre) {
       if (pre < n_st) {
         const int row = rows[pre * 128];
-        if (row >= 0) tc_issue_row(packed_s + pre * TC_PACKED, t, base + (size_t)row * pitch);
+        if (row >= 0) tc_issue_row(packed_s + pre * TC_PACKED, t, g, base + (size_t)row * pitch);
       }
       cp_async_commit();
     }
@@ -373,7 +382,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       const int nxt = st + TC_PK - 1;
       if (nxt < n_st) {
         const int row = rows[nxt * 128];
-        if (row >= 0) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, base + (size_t)row * pitch);
+        if (row >= 0) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, g, base + (size_t)row * pitch);
       }
       cp_async_commit();
       cp_async_wait<TC_PK - 1>();
@@ -381,7 +390,8 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       const uint32_t tab = 0x02010000u | (row >= 0 ? (uint32_t)fill[row] << 8 : 0u);
       const uint32_t slot = packed_s + (st % TC_PK) * TC_PACKED + t * 16;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q0 = 0; q0 < 4; q0 += TC_G) {
+        const int q = q0 + g;
         const int sub = st * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
         const uint4 lo = lds128(slot + (2 * q) * 2048);
         const uint4 hi = lds128(slot + (2 * q + 1) * 2048);
@@ -394,8 +404,8 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     // ---- epilogue: TMEM lane = position inside the 128-individual tile q
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int q = 0; q < 4; ++q) {
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int q = g; q < 4; q += TC_G) {
       const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
       const bool in_range = i < Np;
       const double rs = in_range ? (double)rowscale[i] : 0.0;
@@ -417,7 +427,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == TC_DECODE_WARPS) {
     if (lane == 0) {
       for (int st = 0; st < n_st; ++st) {
         const int b = st % TC_BS, use = st / TC_BS;
@@ -450,7 +460,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     }
   }
   __syncthreads();
-  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
+  if (warp == TC_DECODE_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------ quantisation kernels
@@ -593,8 +603,11 @@ int rhe_tc_set_rhs(rhe_ctx* c, cudaStream_t st) {
 int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
   const int tiles = rhe_div_up(m, 128);
-  // about four CTAs per SM in total (two resident), at least 8 super-stages (4096 individuals) per CTA
-  int splits = rhe_div_up(148 * 4, tiles);
+  // whole waves of 2 resident CTAs per SM (a nearly empty last wave costs a full CTA time); at least
+  // 8 super-stages (4096 individuals) per CTA so that prologue / epilogue stay amortised
+  const int slots = 148 * 2;
+  int splits = tiles >= slots ? 1 : slots / tiles;
+  if (tiles * splits < slots / 2 + slots / 4 && tiles < slots) splits = (2 * slots) / tiles;   // poor fill: use two waves
   int chunk = round_up(rhe_div_up(c->Np, splits), 512);
   if (chunk < 4096) chunk = 4096;
   if (chunk > c->Np) chunk = c->Np;
