@@ -120,7 +120,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config5", choices=list(WORKLOADS))
-    ap.add_argument("--kernel_path", type=int, default=int(os.environ.get("PYRHE_B200_PATH", "0")))
+    ap.add_argument("--kernel_path", type=int, default=int(os.environ.get("PYRHE_B200_PATH", "1")),
+                    help="1 = int8 tcgen05 kernels (default), 0 = CUDA-core validation kernels")
     ap.add_argument("--cpu_snps", type=int, default=200, help="SNPs per block of the CPU sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")

@@ -26,6 +26,21 @@ def _round_up(a, b):
     return (a + b - 1) // b * b
 
 
+def shard_blocks(num_jack: int, world: int, rank: int):
+    """Contiguous range [j0, j1) of jackknife blocks owned by `rank`: ceil(J / world) per rank, exactly
+    how the reference hands block ranges to its worker processes (base.py:530-533)."""
+    per = -(-num_jack // world)
+    return min(rank * per, num_jack), min((rank + 1) * per, num_jack)
+
+
+def allreduce_sum(tensors, group=None):
+    """The path's one exchange step: sum the rank-local totals (and small Gram pieces) over all ranks.
+    NCCL over NVLink for CUDA tensors; gloo in the CPU tests of the sharding logic."""
+    import torch.distributed as dist
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
 class RheEngine:
     def __init__(self, plan: PathPlan, *, n_indv: int, keep: np.ndarray, annot: np.ndarray, num_jack: int,
                  impute: str = "binary", seed: int = 0, device: Optional[torch.device] = None,
@@ -48,8 +63,7 @@ class RheEngine:
         self.pitch = _round_up(self.row_bytes, 128)
         self.Np = 4 * self.pitch
         self.ranges = block_ranges(self.M_snps, self.J)
-        per = -(-self.J // world)                                   # ceil, as base.py:531
-        self.j0, self.j1 = min(rank * per, self.J), min((rank + 1) * per, self.J)
+        self.j0, self.j1 = shard_blocks(self.J, world, rank)
         self.own = list(range(self.j0, self.j1))
         self.max_m = max(b - a for a, b in self.ranges)
 
@@ -196,9 +210,7 @@ class RheEngine:
                     cur.wait_event(upload_events[j])
                 self._accumulate(j, P_all[jl] if self.store_partials else None, S, G_blk[j])
             if self.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(S, group=self.pg)
-                dist.all_reduce(G_blk, group=self.pg)
+                allreduce_sum([S, G_blk], self.pg)
             if plan.has_nxe:
                 S[E_reg].copy_(self.nxe_S)
             length = B * Np
@@ -218,7 +230,7 @@ class RheEngine:
                 _lib.check(self.lib.rhe_loo_gram(self._ctx, _lib.ptr(S), None, E, length, _lib.ptr(XX[J]),
                                                  self._stream()))
             if self.world > 1:
-                dist.all_reduce(XX, group=self.pg)
+                allreduce_sum([XX], self.pg)
             self.S, self.P_all = S, P_all
             out = dict(XX=XX.cpu().numpy(), G_blk=G_blk.cpu().numpy(), M=self.Mjk)
         return out
