@@ -94,6 +94,58 @@ __global__ void k_snp_params(const int32_t* __restrict__ counts, int m, int n_ke
   f2[s] = (double)n2 / (double)n_kept;
 }
 
+// Fused front end of rhe_block_accumulate: masked popcounts (one warp per SNP row), the imputation fill and
+// moments of the SNP, and the zeroing of everything this block accumulates into (t_raw rows, cs, gram, wmax).
+__global__ void __launch_bounds__(256)
+k_stats_params(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t* __restrict__ keep2, int n_kept,
+               int binary, const double* __restrict__ uniforms, int32_t* __restrict__ counts,
+               uint8_t* __restrict__ fill, double* __restrict__ mu, double* __restrict__ f2,
+               double* __restrict__ t_raw, int t_cols, int n_ops, double* __restrict__ cs, int n_cs,
+               double* __restrict__ gram, int n_gram, unsigned int* __restrict__ wmax, int n_wmax) {
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < n_cs; i += 256) cs[i] = 0.0;
+    for (int i = threadIdx.x; i < n_wmax; i += 256) wmax[i] = 0u;
+  }
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n_gram; i += gridDim.x * 256) gram[i] = 0.0;
+  const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (s >= m) return;
+  const int lane = threadIdx.x & 31;
+  for (int op = 0; op < n_ops; ++op)
+    for (int c = lane; c < t_cols; c += 32) t_raw[((size_t)op * m + s) * t_cols + c] = 0.0;
+  const uint32_t* row = reinterpret_cast<const uint32_t*>(bed + (size_t)s * pitch);
+  int n1 = 0, n2 = 0, nm = 0;
+  for (int w = lane; w < pitch / 4; w += 32) {
+    uint32_t x = __ldg(row + w), k = __ldg(keep2 + w) & 0x55555555u;
+    uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+    n2 += __popc(hi & lo & k);
+    n1 += __popc(hi & ~lo & k);
+    nm += __popc(~hi & lo & k);
+  }
+  for (int o = 16; o; o >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    nm += __shfl_xor_sync(0xffffffffu, nm, o);
+  }
+  if (lane == 0) {
+    reinterpret_cast<int4*>(counts)[s] = make_int4(n_kept - n1 - n2 - nm, n1, n2, nm);
+    int f = 0;
+    if (binary) {   // same float32 replay as k_snp_params
+      float mean32 = (float)((double)(n1 + 2 * n2) / (double)(n_kept - nm));
+      float p = __fmul_rn(mean32, 0.5f);
+      float om = __fsub_rn(1.0f, p);
+      float d0 = __fmul_rn(om, om);
+      float d1 = __fmul_rn(__fmul_rn(2.0f, p), om);
+      float u = (float)uniforms[s];
+      f = (u < d0) ? 0 : ((u < __fadd_rn(d0, d1)) ? 1 : 2);
+    }
+    if (f == 1) n1 += nm;
+    if (f == 2) n2 += nm;
+    fill[s] = (uint8_t)f;
+    mu[s] = (double)(n1 + 2 * n2) / (double)n_kept;
+    f2[s] = (double)n2 / (double)n_kept;
+  }
+}
+
 // Test hook: decoded (optionally imputed) A2 counts, one byte per genotype.
 __global__ void k_decode(const uint8_t* __restrict__ bed, int pitch, int m,
                          const uint8_t* __restrict__ fill, int apply_impute, int8_t* __restrict__ out) {
@@ -184,7 +236,7 @@ __global__ void k_standardize(int m, int Rs, int R1, int B, int n_ops, int n_set
                               const double* __restrict__ t_raw, const double* __restrict__ colsum,
                               const double* __restrict__ mu, const double* __restrict__ f2,
                               double* __restrict__ t_std, float* __restrict__ w1, float* __restrict__ w2,
-                              double* __restrict__ shiftv) {
+                              double* __restrict__ shiftv, unsigned int* __restrict__ wmax) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int n_groups = n_ops * n_sets;
   if (idx >= n_groups * m * Rs) return;
@@ -216,6 +268,7 @@ __global__ void k_standardize(int m, int Rs, int R1, int B, int n_ops, int n_set
     w1[o] = (float)a1;
     w2[o] = (float)a2;
     shiftv[o] = sh;
+    if (wmax) atomicMax(wmax + c, __float_as_uint(fabsf((float)a1)));   // tensor path: per-column quantisation range
   }
 }
 
@@ -478,6 +531,7 @@ extern "C" int rhe_ctx_destroy(rhe_ctx* c) {
   cudaDeviceSynchronize();
   if (c->tc) rhe_tc_destroy(c);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  for (auto& e : c->off_cache) cudaFree(e.dev);
   void* ptrs[] = {c->colsum, c->counts, c->fill, c->mu, c->f2, c->t_raw, c->t_std, c->w1, c->w2, c->shiftv, c->cs, c->bin_off};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete c;
@@ -580,12 +634,31 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
     for (auto& e : tev) { RHE_CUDA(cudaEventCreate(&e)); c->ev.push_back(e); }
     RHE_CUDA(cudaEventRecord(tev[0], st));
   }
-  rc = run_params(c, bed, m, st);
-  if (rc) return rc;
+  if (g.impute_binary && (!c->uniforms || c->n_uniforms < m)) {
+    rhe_set_error("binary imputation needs rhe_set_uniforms with >= %d values", m);
+    return RHE_ERR_STATE;
+  }
+  // bin offsets on the device: annotation metadata, copied the first time this block is seen
+  int32_t* s_off_dev = nullptr;
+  for (auto& e : c->off_cache)
+    if (e.key == bin_rows && (int)e.host.size() == K + 1 && memcmp(e.host.data(), bin_off_host, sizeof(int32_t) * (K + 1)) == 0) s_off_dev = e.dev;
+  if (!s_off_dev) {
+    rhe_ctx::OffEntry e;
+    e.key = bin_rows;
+    e.host.assign(bin_off_host, bin_off_host + K + 1);
+    RHE_CUDA(cudaMalloc((void**)&e.dev, sizeof(int32_t) * (K + 1)));
+    RHE_CUDA(cudaMemcpy(e.dev, bin_off_host, sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice));
+    c->off_cache.push_back(e);
+    s_off_dev = e.dev;
+  }
+  unsigned int* wmax = g.kernel_path == RHE_PATH_TCGEN05 ? rhe_tc_wmax(c) : nullptr;
+  k_stats_params<<<rhe_div_up(m, 8), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
+                                                   c->counts, c->fill, c->mu, c->f2, c->t_raw, c->R1, g.n_ops, c->cs,
+                                                   c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? B : 0);
+  RHE_LAUNCH_CHECK(c);
   if (c->timing) RHE_CUDA(cudaEventRecord(tev[1], st));
 
   // ---- pass A
-  RHE_CUDA(cudaMemsetAsync(c->t_raw, 0, sizeof(double) * g.n_ops * (size_t)m * c->R1, st));
   if (g.kernel_path == RHE_PATH_TCGEN05) {
     rc = rhe_tc_pass_a(c, bed, m, st);
     if (rc) return rc;
@@ -607,13 +680,9 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
   {
     int total = c->n_groups * m * Rs;
     k_standardize<<<rhe_div_up(total, 256), 256, 0, st>>>(m, Rs, c->R1, B, g.n_ops, g.n_sets, c->t_raw, c->colsum,
-                                                           c->mu, c->f2, c->t_std, c->w1, c->w2, c->shiftv);
+                                                           c->mu, c->f2, c->t_std, c->w1, c->w2, c->shiftv, wmax);
     RHE_LAUNCH_CHECK(c);
   }
-  int32_t* s_off_dev = c->bin_off;
-  RHE_CUDA(cudaMemcpyAsync(s_off_dev, bin_off_host, sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st));
-  RHE_CUDA(cudaMemsetAsync(gram_out, 0, sizeof(double) * (size_t)c->E_reg * Rs * Rs, st));
-  RHE_CUDA(cudaMemsetAsync(c->cs, 0, sizeof(double) * (size_t)c->E_reg * B, st));
   k_bin_gram<<<dim3(c->E_reg, 8), 256, 0, st>>>(m, Rs, B, K, bin_rows, s_off_dev, c->t_std, c->shiftv, gram_out, c->cs);
   RHE_LAUNCH_CHECK(c);
   if (c->timing) RHE_CUDA(cudaEventRecord(tev[3], st));

@@ -34,6 +34,9 @@ struct rhe_ctx {
   int64_t launches = 0;
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // 5 events per timed rhe_block_accumulate call
+  // device copies of the per-block bin offsets, keyed by the caller's bin_rows pointer (annotation metadata)
+  struct OffEntry { const int32_t* key; std::vector<int32_t> host; int32_t* dev; };
+  std::vector<OffEntry> off_cache;
 };
 
 void rhe_set_error(const char* fmt, ...);
@@ -72,6 +75,7 @@ int rhe_tc_create(rhe_ctx* ctx);
 void rhe_tc_destroy(rhe_ctx* ctx);
 int rhe_tc_set_rhs(rhe_ctx* ctx, cudaStream_t st);
 int rhe_tc_pass_a(rhe_ctx* ctx, const uint8_t* bed, int m, cudaStream_t st);
+unsigned int* rhe_tc_wmax(rhe_ctx* ctx);   // per-column max |pass-B weight| (float bits), or NULL
 int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, int m, const int32_t* bin_rows,
                   const int32_t* bin_off, const int32_t* bin_off_host, float* P_out, float* S_accum,
                   cudaStream_t st);

@@ -5,41 +5,55 @@
 //   pass B   D[i, n] = sum_s G[i, s] * Uq[s, n]      M = 128 individuals, K = SNPs,        N = limb columns
 // G is exact in int8 ({0,1,2}); the fp32 right-hand sides are fixed-point numbers split into L signed
 // 8-bit limbs stacked along N, so the int32 accumulation is EXACT and the result is independent of how
-// the work is split.  One decoded shared-memory tile serves both passes: rows = SNPs,
-// 128 bytes = 128 individuals, 128B-swizzled.  Pass A reads it as a K-major A operand, pass B as an
-// MN-major A operand (instruction-descriptor bit 15).  The small B operands (Rq / Uq tiles) arrive by
-// TMA; accumulators live in TMEM and are read back with tcgen05.ld in the epilogue.
+// the work is split.
 //
-// Warp roles: TC_G groups of four decode warps (group g expands sub-tiles q = g mod TC_G of every super-stage into
-// A slot g, so the groups overlap each other's load / fence / barrier latencies; afterwards they run the epilogue,
-// one TMEM lane quadrant per warp), then one TMA warp and one warp that allocates TMEM and issues tcgen05.mma.
+// Packed rows are streamed with thread-private cp.async rings (a decode thread owns one SNP row and only
+// ever reads back what it fetched itself, so no block-level barrier guards the ring).  A 32-bit packed word
+// expands to sixteen int8 values with 3 logic ops and 4 byte-permutes.
+//   pass A: the expanded A operand goes straight from registers into TENSOR MEMORY (tcgen05.st) and the MMA
+//           reads A from TMEM (K-major), so the big operand never touches shared memory; only the small Rq
+//           tile (TMA, 128B swizzle) does.
+//   pass B: needs the same bytes as an MN-major operand (128 individuals contiguous per SNP row), which TMEM
+//           cannot provide, so the tile is written to shared memory (128B swizzle) and read by the MMA through an
+//           MN-major descriptor.  One CTA owns MT x 128 individuals and ALL bins: bin k accumulates in its
+//           own TMEM columns, rows are gathered by bin, and the mainloop runs over the whole block.
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "rhe_common.cuh"
 
 #define TC_TILE_A 16384          // 128 rows x 128 bytes
-#define TC_G 2                                  // decode groups of 4 warps; group g owns A slot g
-#define TC_DECODE_WARPS (4 * TC_G)
-#define TC_THREADS (32 * (TC_DECODE_WARPS + 2))
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Annotation-derived metadata of one jackknife block (depends only on the bin row lists, so it is built the
+// first time a block is seen and reused by later traits / steps).
+struct TcBlockMeta {
+  const int32_t* key = nullptr;   // the caller's bin_rows pointer identifies the block
+  int m = 0;
+  int n_pos = 0;                  // bin-sorted positions, every bin padded to a multiple of 128 rows
+  int32_t* pos_rows = nullptr;    // [n_pos]       block-local SNP row (-1 = padding)
+  int32_t* stage_info = nullptr;  // [n_pos / 128] bin | first-stage-of-bin << 8 | K-steps << 16
+  int32_t* bin_count = nullptr;   // [K]           rows per bin
+};
 
 struct TcState {
   int L = 3;            // limbs per fixed-point value (PYRHE_B200_LIMBS)
   int F = 22;           // fixed-point magnitude bits: |q| <= 2^F, F = 8 L - 2
   int R1p = 0;          // RHS columns rounded up to 4
   int NBa = 0;          // pass A MMA N  = round16(L * R1p)
-  int Bp = 0;           // pass-B columns rounded up to 4
-  int NCb = 0;          // pass B MMA N per bin = round16(L * Bp)
+  int Bp = 0;           // pass-B columns rounded up to 2
+  int NCb = 0;          // pass B MMA N per (bin, M-tile) = round16(L * Bp)
+  int MT = 2;           // 128-individual M-tiles per pass-B CTA
   int8_t* rq = nullptr;       // [NBa][Np]   limb l of column c at row l * R1p + c, permuted individual order
   double* col_dq = nullptr;   // [R1]        power-of-two dequantisation factor of every RHS column
-  int32_t* pos_rows = nullptr;  // [cap_pos]   block-local SNP row of every bin-sorted position (-1 = padding)
-  int32_t* pstart = nullptr;    // [K + 1]     first position of every bin (multiples of 128)
-  int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights
+  int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights of the current block
   unsigned int* wmax = nullptr; // [B]         max |weight| per column (float bits)
   int cap_pos = 0;
+  std::vector<TcBlockMeta> blocks;
   CUtensorMap tm_rq, tm_uq;
   PFN_encodeTiled encode = nullptr;
 };
@@ -182,20 +196,6 @@ __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
   return r;
 }
 
-// Ring depths.  A "super-stage" is 128 rows x 128 packed bytes (512 individuals): every decode thread
-// owns one row and streams its own 128-byte lines with cp.async (thread-private, so no block barrier
-// is needed to consume them), TC_PK super-stages deep.  Each super-stage is decoded into four int8
-// A tiles (128 individuals each) that cycle through a ring of TC_AS slots.
-#define TC_PK 3
-#define TC_AS TC_G
-#define TC_BS 4          // B-operand (TMA) ring: deep enough to hide the L2 -> smem latency
-#define TC_PACKED (128 * 128)
-
-struct TcSmem {
-  uint64_t full_a[TC_AS], empty_a[TC_AS], full_b[TC_BS], empty_b[TC_BS], acc_full;
-  uint32_t tmem_base;
-};
-
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -203,91 +203,143 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Thread t streams 128 bytes of its row into slot layout [chunk 0..7][thread][16 B] (conflict-free reads).
-// Group g fetches only the chunks of the sub-tiles it decodes (q = g, g + TC_G, ...: chunks 2q, 2q + 1).
-__device__ __forceinline__ void tc_issue_row(uint32_t slot, int t, int g, const uint8_t* src) {
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, int32_t (&v)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+// value[j] = sum_l 256^l * limb_l[j] for two adjacent columns; limb l sits `stride` columns further on
+__device__ __forceinline__ void tmem_combine2(uint32_t taddr, int L, int stride, double (&val)[2]) {
+  int32_t v[4][2];
 #pragma unroll
-  for (int q = 0; q < 4; q += TC_G) {
-    const int c = 2 * (q + g);
-    cp_async16(slot + c * 2048 + t * 16, src + c * 16);
-    cp_async16(slot + (c + 1) * 2048 + t * 16, src + (c + 1) * 16);
+  for (int l = 0; l < 4; ++l)
+    if (l < L) tmem_ld2(taddr + (uint32_t)(l * stride), v[l]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    double acc = 0.0;
+#pragma unroll
+    for (int l = 3; l >= 0; --l)
+      if (l < L) acc = acc * 256.0 + (double)v[l][j];
+    val[j] = acc;
   }
 }
-
-__device__ __forceinline__ void tc_setup(TcSmem* sm, int warp, uint32_t tmem_cols) {
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_AS; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
-    for (int s = 0; s < TC_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
-    mbar_init(&sm->acc_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == TC_DECODE_WARPS + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+// 32 registers (one 128-byte operand row) -> 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint4 (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0].x), "r"(r[0].y), "r"(r[0].z), "r"(r[0].w), "r"(r[1].x), "r"(r[1].y), "r"(r[1].z), "r"(r[1].w),
+        "r"(r[2].x), "r"(r[2].y), "r"(r[2].z), "r"(r[2].w), "r"(r[3].x), "r"(r[3].y), "r"(r[3].z), "r"(r[3].w),
+        "r"(r[4].x), "r"(r[4].y), "r"(r[4].z), "r"(r[4].w), "r"(r[5].x), "r"(r[5].y), "r"(r[5].z), "r"(r[5].w),
+        "r"(r[6].x), "r"(r[6].y), "r"(r[6].z), "r"(r[6].w), "r"(r[7].x), "r"(r[7].y), "r"(r[7].z), "r"(r[7].w)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], int8 x int8 -> int32 (A operand from tensor memory, K-major)
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  uint32_t zero = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(zero) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------ pass A
 // grid = (SNP tiles of 128, splits over individuals).  t_raw[s][c] += dq[c] * sum_i g_is * q_ic  (exact).
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// Two groups of four decode warps; group g expands sub-tiles q = g, g + 2 of every 512-individual super-stage
+// into TMEM A slot q.
+#define PA_G 2
+#define PA_DW (4 * PA_G)
+#define PA_THREADS (32 * (PA_DW + 2))
+#define PA_AS 4                   // TMEM A slots (32 columns each) = sub-tiles of one super-stage
+#define PA_BS 4                   // smem ring of Rq tiles (TMA)
+#define PA_PK 4                   // cp.async ring of packed super-stages (128 rows x 128 B)
+#define PA_PACKED (128 * 128)
+
+struct PaSmem {
+  uint64_t full_a[PA_AS], empty_a[PA_AS], full_b[PA_BS], empty_b[PA_BS], acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(PA_THREADS, 2)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict__ bed, int pitch, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
-            double* __restrict__ t_raw, int chunk, uint32_t tmem_cols) {
+            double* __restrict__ t_raw, int chunk, uint32_t tmem_cols, uint32_t col_a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* tileA = smem;
-  uint8_t* tileB = tileA + TC_AS * TC_TILE_A;
+  uint8_t* tileB = smem;
   const int tileB_bytes = NB * 128;
-  uint8_t* packed = tileB + TC_BS * tileB_bytes;
-  TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
-  const uint32_t tileA_s = smem_u32(tileA), packed_s = smem_u32(packed);
+  uint8_t* packed = tileB + PA_BS * tileB_bytes;
+  PaSmem* sm = reinterpret_cast<PaSmem*>(packed + PA_PK * PA_PACKED);
+  const uint32_t packed_s = smem_u32(packed);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int snp0 = blockIdx.x * 128;
   const int i_begin = blockIdx.y * chunk, i_end = min(Np, i_begin + chunk);
   const int n_ss = (i_end - i_begin) >> 9;          // super-stages of 512 individuals
   if (n_ss <= 0) return;
-  const int n_sub = n_ss * 4;
 
-  tc_setup(sm, warp, tmem_cols);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PA_AS; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
+    for (int s = 0; s < PA_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
+    mbar_init(&sm->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == PA_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
 
-  if (warp < TC_DECODE_WARPS) {
+  if (warp < PA_DW) {
     const int t = threadIdx.x & 127, g = warp >> 2;
     const int s = min(snp0 + t, m - 1);
     const uint32_t tab = ((uint32_t)fill[s] << 8) | (1u << 16) | (2u << 24);
     const uint8_t* src = bed + (size_t)s * pitch + (i_begin >> 2);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    // group g fetches only the chunks of its own sub-tiles (q = g, g + 2 -> chunks 2q, 2q + 1)
+    auto issue = [&](int ss) {
+      const uint32_t slot = packed_s + (ss % PA_PK) * PA_PACKED + t * 16;
+      const uint8_t* p = src + (size_t)ss * 128;
 #pragma unroll
-    for (int pre = 0; pre < TC_PK - 1; ++pre) {
-      if (pre < n_ss) tc_issue_row(packed_s + pre * TC_PACKED, t, g, src + pre * 128);
+      for (int q = 0; q < 4; q += PA_G) {
+        const int c = 2 * (q + g);
+        cp_async16(slot + c * 2048, p + c * 16);
+        cp_async16(slot + (c + 1) * 2048, p + (c + 1) * 16);
+      }
+    };
+#pragma unroll
+    for (int pre = 0; pre < PA_PK - 1; ++pre) {
+      if (pre < n_ss) issue(pre);
       cp_async_commit();
     }
     for (int ss = 0; ss < n_ss; ++ss) {
-      const int nxt = ss + TC_PK - 1;
-      if (nxt < n_ss) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, g, src + (size_t)nxt * 128);
+      if (ss + PA_PK - 1 < n_ss) issue(ss + PA_PK - 1);
       cp_async_commit();
-      cp_async_wait<TC_PK - 1>();
-      const uint32_t slot = packed_s + (ss % TC_PK) * TC_PACKED + t * 16;
+      cp_async_wait<PA_PK - 1>();
+      const uint32_t slot = packed_s + (ss % PA_PK) * PA_PACKED + t * 16;
 #pragma unroll
-      for (int q0 = 0; q0 < 4; q0 += TC_G) {
-        const int q = q0 + g;
-        const int sub = ss * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
+      for (int q0 = 0; q0 < 4; q0 += PA_G) {
+        const int q = q0 + g;                        // TMEM A slot q, used once per super-stage
         const uint4 lo = lds128(slot + (2 * q) * 2048);
         const uint4 hi = lds128(slot + (2 * q + 1) * 2048);
-        mbar_wait(&sm->empty_a[a], (use & 1) ^ 1);
-        tc_store_row(tileA_s + a * TC_TILE_A, t, lo, hi, tab);
-        fence_proxy_async();
-        mbar_arrive(&sm->full_a[a]);
+        uint4 r[8];
+        r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
+        r[4] = tc_expand(hi.x, tab); r[5] = tc_expand(hi.y, tab); r[6] = tc_expand(hi.z, tab); r[7] = tc_expand(hi.w, tab);
+        mbar_wait(&sm->empty_a[q], (ss & 1) ^ 1);
+        tc_fence_after();
+        tmem_st32(lane_base + col_a + 32 * q, r);
+        tc_fence_before();
+        mbar_arrive(&sm->full_a[q]);
       }
     }
-    // ---- epilogue: lane quadrant `warp` of TMEM, row = SNP
+    // ---- epilogue: lane quadrant (warp & 3) of TMEM, row = SNP; the two groups split the columns
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
     const int snp = snp0 + t;
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int c0 = 4 * g; c0 < R1p; c0 += 4 * TC_G) {
+    for (int c0 = 4 * g; c0 < R1p; c0 += 4 * PA_G) {
       double val[4];
-      tmem_combine4(trow + (uint32_t)c0, L, R1p, val);
+      tmem_combine4(lane_base + (uint32_t)c0, L, R1p, val);
       if (snp < m) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -295,10 +347,11 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
       }
     }
     tc_fence_before();
-  } else if (warp == TC_DECODE_WARPS) {
+  } else if (warp == PA_DW) {
     if (lane == 0) {
+      const int n_sub = n_ss * 4;
       for (int sub = 0; sub < n_sub; ++sub) {
-        const int b = sub % TC_BS, use = sub / TC_BS;
+        const int b = sub % PA_BS, use = sub / PA_BS;
         mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
         mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
         tma_load_2d(tileB + b * tileB_bytes, &tm_rq, &sm->full_b[b], i_begin + sub * 128, 0);
@@ -307,152 +360,168 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   } else {
     if (lane == 0) {
       const uint32_t idesc = idesc_i8(128, NB, 0);
-      for (int sub = 0; sub < n_sub; ++sub) {
-        const int a = sub % TC_AS, use = sub / TC_AS, b = sub % TC_BS, useb = sub / TC_BS;
-        mbar_wait(&sm->full_b[b], useb & 1);
-        mbar_wait(&sm->full_a[a], use & 1);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(tileA + a * TC_TILE_A), b0 = smem_u32(tileB + b * tileB_bytes);
+      for (int ss = 0; ss < n_ss; ++ss) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: advance 32 bytes inside the swizzle atom
-          umma_i8(tmem, smem_desc_sw128(a0 + j * 32, 16, 1024), smem_desc_sw128(b0 + j * 32, 16, 1024), idesc,
-                  (uint32_t)((sub | j) != 0));
-        umma_commit(&sm->empty_a[a]);
-        umma_commit(&sm->empty_b[b]);
+        for (int q = 0; q < 4; ++q) {
+          const int sub = ss * 4 + q, b = sub % PA_BS, useb = sub / PA_BS;
+          mbar_wait(&sm->full_b[b], useb & 1);
+          mbar_wait(&sm->full_a[q], ss & 1);
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(tileB + b * tileB_bytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
+            umma_i8_ts(tmem, tmem + col_a + 32 * q + 8 * j, smem_desc_sw128(b0 + j * 32, 16, 1024), idesc,
+                       (uint32_t)((sub | j) != 0));
+          umma_commit(&sm->empty_a[q]);
+          umma_commit(&sm->empty_b[b]);
+        }
       }
       umma_commit(&sm->acc_full);
     }
   }
   __syncthreads();
-  if (warp == TC_DECODE_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
+  if (warp == PA_DW + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------ pass B
-// grid = (tiles of 512 individuals, bins).  Positions = the bin's SNP rows, padded to a multiple of 128
-// with zero-weight rows.  Each stage gathers 128 rows x 128 packed bytes (a full DRAM line per row), decodes
-// them into four MN-major A tiles (128 individuals each) that share one Uq tile, and accumulates four
-// 128 x NC int32 tiles in TMEM.
-__global__ void __launch_bounds__(TC_THREADS, 2)
-k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np,
-            const int32_t* __restrict__ pos_rows, const uint8_t* __restrict__ fill, int B, int Bp, int L, int NC, int F,
-            const unsigned int* __restrict__ wmax, const int32_t* __restrict__ pstart, const int32_t* __restrict__ bin_off,
-            const double* __restrict__ cs, const float* __restrict__ rowscale, float* __restrict__ P_out,
-            float* __restrict__ S_accum, uint32_t tmem_cols) {
+// grid = tiles of MT x 128 individuals; one CTA runs over ALL bin-sorted positions of the block.
+// Four groups of four decode warps: group g = (par, q) expands M-tile q of the stages st = par (mod 4 / MT)
+// into shared-memory A slot g.  Stage st belongs to one bin (bins are padded to 128 rows); bin k, M-tile q
+// accumulates in TMEM columns [(k * MT + q) * NC, +NC).
+#define PB_G 4
+#define PB_DW (4 * PB_G)
+#define PB_THREADS (32 * (PB_DW + 2))
+#define PB_BS 4                   // smem ring of Uq tiles (TMA)
+#define PB_PKG 4                  // per-group cp.async ring depth (in the group's own stages)
+
+struct PbSmem {
+  uint64_t full_a[PB_G], empty_a[PB_G], full_b[PB_BS], empty_b[PB_BS], acc_full;
+  uint32_t tmem_base;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(PB_THREADS, 1)
+k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
+            const int32_t* __restrict__ pos_rows, const int32_t* __restrict__ stage_info,
+            const int32_t* __restrict__ bin_count, const uint8_t* __restrict__ fill, int K, int B, int Bp, int L, int NC,
+            int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
+            const float* __restrict__ rowscale, float* __restrict__ P_out, float* __restrict__ S_accum,
+            uint32_t tmem_cols) {
+  constexpr int SI = PB_G / MT;                      // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileA = smem;
-  uint8_t* tileB = tileA + TC_AS * TC_TILE_A;
+  uint8_t* tileB = tileA + PB_G * TC_TILE_A;
   const int tileB_bytes = NC * 128;
-  uint8_t* packed = tileB + TC_BS * tileB_bytes;
-  TcSmem* sm = reinterpret_cast<TcSmem*>(packed + TC_PK * TC_PACKED);
+  uint8_t* packed = tileB + PB_BS * tileB_bytes;     // [group][PB_PKG][2 chunks][128 threads][16 B]
+  PbSmem* sm = reinterpret_cast<PbSmem*>(packed + PB_G * PB_PKG * 4096);
   const uint32_t tileA_s = smem_u32(tileA), packed_s = smem_u32(packed);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.y;
-  const int i0 = blockIdx.x * 512;
-  const int p0 = pstart[k];
-  const int n_st = (pstart[k + 1] - p0) >> 7;
-  const int n_real = bin_off[k + 1] - bin_off[k];
+  const int i0 = blockIdx.x * (MT * 128);
 
-  if (n_st == 0) {   // empty bin in this block: X_k = 0, so P = 0 (S unchanged)
-    if (P_out)
-      for (int idx = threadIdx.x; idx < B * 512; idx += TC_THREADS) {
-        const int b = idx >> 9, i = i0 + (idx & 511);
-        if (i < Np) P_out[((size_t)k * B + b) * Np + i] = 0.f;
-      }
-    return;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PB_G; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
+    for (int s = 0; s < PB_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
+    mbar_init(&sm->acc_full, 1);
+    fence_barrier_init();
   }
-
-  tc_setup(sm, warp, tmem_cols);
+  if (warp == PB_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
 
-  if (warp < TC_DECODE_WARPS) {
+  if (warp < PB_DW) {
     const int t = threadIdx.x & 127, g = warp >> 2;
-    const uint8_t* base = bed + (i0 >> 2);
-    const int32_t* rows = pos_rows + p0 + t;
-#pragma unroll
-    for (int pre = 0; pre < TC_PK - 1; ++pre) {
-      if (pre < n_st) {
-        const int row = rows[pre * 128];
-        if (row >= 0) tc_issue_row(packed_s + pre * TC_PACKED, t, g, base + (size_t)row * pitch);
+    const int par = g / MT, q = g % MT;
+    const uint8_t* base = bed + (i0 >> 2) + q * 32;
+    const uint32_t ring = packed_s + g * (PB_PKG * 4096) + t * 16;
+    const uint32_t tile = tileA_s + g * TC_TILE_A;
+    const int n_own = n_stage > par ? (n_stage - par + SI - 1) / SI : 0;   // stages st = par + SI * u
+    auto issue = [&](int u) {
+      const int row = pos_rows[(par + SI * u) * 128 + t];
+      if (row >= 0) {
+        const uint8_t* p = base + (size_t)row * pitch;
+        const uint32_t slot = ring + (u % PB_PKG) * 4096;
+        cp_async16(slot, p);
+        cp_async16(slot + 2048, p + 16);
       }
+    };
+#pragma unroll
+    for (int pre = 0; pre < PB_PKG - 1; ++pre) {
+      if (pre < n_own) issue(pre);
       cp_async_commit();
     }
-    for (int st = 0; st < n_st; ++st) {
-      const int nxt = st + TC_PK - 1;
-      if (nxt < n_st) {
-        const int row = rows[nxt * 128];
-        if (row >= 0) tc_issue_row(packed_s + (nxt % TC_PK) * TC_PACKED, t, g, base + (size_t)row * pitch);
-      }
+    for (int u = 0; u < n_own; ++u) {
+      if (u + PB_PKG - 1 < n_own) issue(u + PB_PKG - 1);
       cp_async_commit();
-      cp_async_wait<TC_PK - 1>();
-      const int row = rows[st * 128];
+      cp_async_wait<PB_PKG - 1>();
+      const int row = pos_rows[(par + SI * u) * 128 + t];
       const uint32_t tab = 0x02010000u | (row >= 0 ? (uint32_t)fill[row] << 8 : 0u);
-      const uint32_t slot = packed_s + (st % TC_PK) * TC_PACKED + t * 16;
-#pragma unroll
-      for (int q0 = 0; q0 < 4; q0 += TC_G) {
-        const int q = q0 + g;
-        const int sub = st * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
-        const uint4 lo = lds128(slot + (2 * q) * 2048);
-        const uint4 hi = lds128(slot + (2 * q + 1) * 2048);
-        mbar_wait(&sm->empty_a[a], (use & 1) ^ 1);
-        tc_store_row(tileA_s + a * TC_TILE_A, t, lo, hi, tab);
-        fence_proxy_async();
-        mbar_arrive(&sm->full_a[a]);
-      }
+      const uint32_t slot = ring + (u % PB_PKG) * 4096;
+      const uint4 lo = lds128(slot), hi = lds128(slot + 2048);
+      mbar_wait(&sm->empty_a[g], (u & 1) ^ 1);
+      tc_store_row(tile, t, lo, hi, tab);
+      fence_proxy_async();
+      mbar_arrive(&sm->full_a[g]);
     }
-    // ---- epilogue: TMEM lane = position inside the 128-individual tile q
+    // ---- epilogue: TMEM lane = position inside M-tile q; group (par, q) takes the bins k = par (mod SI)
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int q = g; q < 4; q += TC_G) {
-      const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
-      const bool in_range = i < Np;
-      const double rs = in_range ? (double)rowscale[i] : 0.0;
-      for (int c0 = 0; c0 < Bp; c0 += 4) {
-        double val[4];
-        tmem_combine4(trow + (uint32_t)(q * NC + c0), L, Bp, val);
+    const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
+    const double rs = (double)rowscale[i];
+    for (int k = par; k < K; k += SI) {
+      const bool has = bin_count[k] > 0;
+      const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
+      for (int c0 = 0; c0 < Bp; c0 += 2) {
+        double val[2] = {0.0, 0.0};
+        if (has) tmem_combine2(tcol + (uint32_t)c0, L, Bp, val);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           const int b = c0 + j;
-          if (b < B && in_range) {
+          if (b < B) {
             // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
             const int e = (int)((wmax[b] >> 23) & 255u) - 126;
-            const float xf = (float)(rs * (ldexp(val[j], e - F) - cs[(size_t)k * B + b]));
+            const float xf = has ? (float)(rs * (ldexp(val[j], e - F) - cs[(size_t)k * B + b])) : 0.f;
             const size_t o = ((size_t)k * B + b) * Np + i;
             if (P_out) P_out[o] = xf;
-            if (S_accum) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
+            if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
           }
         }
       }
     }
     tc_fence_before();
-  } else if (warp == TC_DECODE_WARPS) {
+  } else if (warp == PB_DW) {
     if (lane == 0) {
-      for (int st = 0; st < n_st; ++st) {
-        const int b = st % TC_BS, use = st / TC_BS;
+      for (int st = 0; st < n_stage; ++st) {
+        const int b = st % PB_BS, use = st / PB_BS;
         mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
         mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
-        tma_load_2d(tileB + b * tileB_bytes, &tm_uq, &sm->full_b[b], p0 + st * 128, 0);
+        tma_load_2d(tileB + b * tileB_bytes, &tm_uq, &sm->full_b[b], st * 128, 0);
       }
     }
   } else {
     if (lane == 0) {
       const uint32_t idesc = idesc_i8(128, NC, 1);   // A is MN-major: 128 individuals contiguous per SNP row
-      for (int st = 0; st < n_st; ++st) {
-        const int b = st % TC_BS, useb = st / TC_BS;
+      for (int st = 0; st < n_stage; ++st) {
+        const int b = st % PB_BS, useb = st / PB_BS;
+        const int info = stage_info[st];
+        const int k = info & 255, first = (info >> 8) & 1, ksteps = info >> 16;
         mbar_wait(&sm->full_b[b], useb & 1);
         const uint32_t b0 = smem_u32(tileB + b * tileB_bytes);
-        const int ksteps = min(4, (n_real - st * 128 + 31) >> 5);   // all-padding K-steps are skipped
-        for (int q = 0; q < 4; ++q) {
-          const int sub = st * 4 + q, a = sub % TC_AS, use = sub / TC_AS;
-          mbar_wait(&sm->full_a[a], use & 1);
+        const int par = st % SI, u = st / SI;
+#pragma unroll
+        for (int q = 0; q < MT; ++q) {
+          const int g = par * MT + q;
+          mbar_wait(&sm->full_a[g], u & 1);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(tileA + a * TC_TILE_A);
+          const uint32_t a0 = tileA_s + g * TC_TILE_A;
           for (int j = 0; j < ksteps; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
-            umma_i8(tmem + q * NC, smem_desc_sw128(a0 + j * 4096, TC_TILE_A, 1024), smem_desc_sw128(b0 + j * 32, 16, 1024),
-                    idesc, (uint32_t)((st | j) != 0));
-          umma_commit(&sm->empty_a[a]);
+            umma_i8(tmem + (uint32_t)((k * MT + q) * NC), smem_desc_sw128(a0 + j * 4096, TC_TILE_A, 1024),
+                    smem_desc_sw128(b0 + j * 32, 16, 1024), idesc, (uint32_t)(!first || j > 0));
+          umma_commit(&sm->empty_a[g]);
         }
         umma_commit(&sm->empty_b[b]);
       }
@@ -460,7 +529,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     }
   }
   __syncthreads();
-  if (warp == TC_DECODE_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
+  if (warp == PB_DW + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------ quantisation kernels
@@ -538,10 +607,9 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-static inline int tc_smem_bytes(int n_cols) {
-  return TC_AS * TC_TILE_A + TC_BS * n_cols * 128 + TC_PK * TC_PACKED + (int)sizeof(TcSmem) + 1024;
-}
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
+static inline int pa_smem_bytes(int nb) { return PA_BS * nb * 128 + PA_PK * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
+static inline int pb_smem_bytes(int nc) { return PB_G * TC_TILE_A + PB_BS * nc * 128 + PB_G * PB_PKG * 4096 + (int)sizeof(PbSmem) + 1024; }
 
 int rhe_tc_create(rhe_ctx* c) {
   const rhe_config& g = c->cfg;
@@ -553,11 +621,12 @@ int rhe_tc_create(rhe_ctx* c) {
   s->F = 8 * s->L - 2;
   s->R1p = round_up(c->R1, 4);
   s->NBa = round_up(s->L * s->R1p, 16);
-  s->Bp = round_up(g.n_vec, 4);
+  s->Bp = round_up(g.n_vec, 2);
   s->NCb = round_up(s->L * s->Bp, 16);
-  if (s->NBa > 256 || 4 * s->NCb > 512 || g.n_bins > 64) {
-    delete s;
+  s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
+  if (s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
+    delete s;
     return RHE_ERR_UNSUPPORTED;
   }
   void* fn = nullptr;
@@ -573,21 +642,25 @@ int rhe_tc_create(rhe_ctx* c) {
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
   alloc((void**)&s->rq, (size_t)s->NBa * c->Np);
   alloc((void**)&s->col_dq, sizeof(double) * c->R1);
-  alloc((void**)&s->pstart, sizeof(int32_t) * (g.n_bins + 1));
   alloc((void**)&s->wmax, sizeof(unsigned int) * g.n_vec);
   if (e != cudaSuccess) { rhe_set_error("tensor-core workspace allocation failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
-  const int smem_a = tc_smem_bytes(s->NBa), smem_b = tc_smem_bytes(s->NCb);
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa)));
+  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb)));
+  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb)));
   return RHE_OK;
 }
 
 void rhe_tc_destroy(rhe_ctx* c) {
   TcState* s = (TcState*)c->tc;
   if (!s) return;
-  void* ptrs[] = {s->rq, s->col_dq, s->pos_rows, s->pstart, s->uq, s->wmax};
+  for (TcBlockMeta& b : s->blocks) {
+    if (b.pos_rows) cudaFree(b.pos_rows);
+    if (b.stage_info) cudaFree(b.stage_info);
+    if (b.bin_count) cudaFree(b.bin_count);
+  }
+  void* ptrs[] = {s->rq, s->col_dq, s->uq, s->wmax};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete s;
   c->tc = nullptr;
@@ -599,6 +672,8 @@ int rhe_tc_set_rhs(rhe_ctx* c, cudaStream_t st) {
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
+
+unsigned int* rhe_tc_wmax(rhe_ctx* c) { return c->tc ? ((TcState*)c->tc)->wmax : nullptr; }
 
 int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
@@ -612,10 +687,49 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   if (chunk < 4096) chunk = 4096;
   if (chunk > c->Np) chunk = c->Np;
   splits = rhe_div_up(c->Np, chunk);
-  k_tc_pass_a<<<dim3(tiles, splits), TC_THREADS, tc_smem_bytes(s->NBa), st>>>(
+  const uint32_t col_a = (uint32_t)round_up(s->NBa, 32);
+  k_tc_pass_a<<<dim3(tiles, splits), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
       s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw, chunk,
-      pow2_cols(s->NBa));
+      pow2_cols((int)col_a + 32 * PA_AS), col_a);
   RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
+// Bin-sorted positions of a block: built once per block (keyed by the caller's bin_rows pointer).
+static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows, const int32_t* bin_off_dev,
+                         const int32_t* bin_off_host, cudaStream_t st, TcBlockMeta** out) {
+  for (TcBlockMeta& b : s->blocks)
+    if (b.key == bin_rows && b.m == m) { *out = &b; return RHE_OK; }
+  const int K = c->cfg.n_bins;
+  std::vector<int32_t> pstart(K + 1, 0), counts(K), info;
+  for (int k = 0; k < K; ++k) {
+    counts[k] = bin_off_host[k + 1] - bin_off_host[k];
+    pstart[k + 1] = pstart[k] + round_up(counts[k], 128);
+    for (int done = 0; done < counts[k]; done += 128) {
+      const int left = counts[k] - done;
+      info.push_back(k | ((done == 0) << 8) | (((left < 128 ? left : 128) + 31) / 32) << 16);
+    }
+  }
+  TcBlockMeta b;
+  b.key = bin_rows;
+  b.m = m;
+  b.n_pos = pstart[K];
+  const int n_alloc = b.n_pos > 0 ? b.n_pos : 128;
+  RHE_CUDA(cudaMalloc((void**)&b.pos_rows, sizeof(int32_t) * n_alloc));
+  RHE_CUDA(cudaMalloc((void**)&b.stage_info, sizeof(int32_t) * (n_alloc / 128)));
+  RHE_CUDA(cudaMalloc((void**)&b.bin_count, sizeof(int32_t) * K));
+  int32_t* d_pstart = nullptr;
+  RHE_CUDA(cudaMalloc((void**)&d_pstart, sizeof(int32_t) * (K + 1)));
+  RHE_CUDA(cudaMemcpyAsync(d_pstart, pstart.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st));
+  RHE_CUDA(cudaMemcpyAsync(b.bin_count, counts.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, st));
+  if (!info.empty())
+    RHE_CUDA(cudaMemcpyAsync(b.stage_info, info.data(), sizeof(int32_t) * info.size(), cudaMemcpyHostToDevice, st));
+  k_tc_positions<<<dim3(rhe_div_up(m, 256), K), 256, 0, st>>>(bin_rows, bin_off_dev, d_pstart, b.pos_rows);
+  RHE_LAUNCH_CHECK(c);
+  RHE_CUDA(cudaStreamSynchronize(st));     // the host staging vectors die here (first sight of the block only)
+  cudaFree(d_pstart);
+  s->blocks.push_back(b);
+  *out = &s->blocks.back();
   return RHE_OK;
 }
 
@@ -624,35 +738,34 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   TcState* s = (TcState*)c->tc;
   const rhe_config& g = c->cfg;
   const int K = g.n_bins, B = g.n_vec;
-  // bin-sorted positions: every bin padded to a multiple of 128 rows (one stage never mixes bins)
-  int32_t pstart[65];
-  pstart[0] = 0;
-  for (int k = 0; k < K; ++k) pstart[k + 1] = pstart[k] + round_up(bin_off_host[k + 1] - bin_off_host[k], 128);
-  const int n_pos = round_up(pstart[K] > 0 ? pstart[K] : 1, 128);
+  TcBlockMeta* meta = nullptr;
+  int rc = tc_block_meta(c, s, m, bin_rows, bin_off, bin_off_host, st, &meta);
+  if (rc) return rc;
+  const int n_pos = meta->n_pos;
   if (n_pos > s->cap_pos) {
     RHE_CUDA(cudaStreamSynchronize(st));
-    if (s->pos_rows) cudaFree(s->pos_rows);
     if (s->uq) cudaFree(s->uq);
     s->cap_pos = round_up(n_pos + n_pos / 8, 128);
-    RHE_CUDA(cudaMalloc((void**)&s->pos_rows, sizeof(int32_t) * s->cap_pos));
     RHE_CUDA(cudaMalloc((void**)&s->uq, (size_t)s->NCb * s->cap_pos));
     RHE_CUDA(cudaMemset(s->uq, 0, (size_t)s->NCb * s->cap_pos));
-    int rc = tc_encode_2d(s, &s->tm_uq, s->uq, (uint64_t)s->cap_pos, (uint64_t)s->NCb, (uint32_t)s->NCb);
+    rc = tc_encode_2d(s, &s->tm_uq, s->uq, (uint64_t)s->cap_pos, (uint64_t)s->NCb, (uint32_t)s->NCb);
     if (rc) return rc;
   }
-  RHE_CUDA(cudaMemcpyAsync(s->pstart, pstart, sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st));
-  RHE_CUDA(cudaMemsetAsync(s->pos_rows, 0xFF, sizeof(int32_t) * n_pos, st));
-  RHE_CUDA(cudaMemsetAsync(s->wmax, 0, sizeof(unsigned int) * B, st));
-  k_tc_positions<<<dim3(rhe_div_up(m, 256), K), 256, 0, st>>>(bin_rows, bin_off, s->pstart, s->pos_rows);
-  RHE_LAUNCH_CHECK(c);
-  k_tc_wmax<<<rhe_div_up(m * B, 256), 256, 0, st>>>(c->w1, m, B, s->wmax);
-  RHE_LAUNCH_CHECK(c);
-  k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B, 256), 256, 0, st>>>(c->w1, s->pos_rows, n_pos, s->cap_pos, B, s->Bp, s->L, s->F,
-                                                                    s->wmax, s->uq);
-  RHE_LAUNCH_CHECK(c);
-  k_tc_pass_b<<<dim3(rhe_div_up(c->Np, 512), K), TC_THREADS, tc_smem_bytes(s->NCb), st>>>(
-      s->tm_uq, bed, g.pitch_bytes, c->Np, s->pos_rows, c->fill, B, s->Bp, s->L, s->NCb, s->F, s->wmax, s->pstart, bin_off,
-      c->cs, c->rowscale, P_out, S_accum, pow2_cols(4 * s->NCb));
+  if (n_pos > 0) {
+    k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B, 256), 256, 0, st>>>(c->w1, meta->pos_rows, n_pos, s->cap_pos, B, s->Bp, s->L,
+                                                                      s->F, s->wmax, s->uq);
+    RHE_LAUNCH_CHECK(c);
+  }
+  const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
+  const int smem = pb_smem_bytes(s->NCb);
+  if (s->MT == 2)
+    k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, meta->pos_rows,
+                                                          meta->stage_info, meta->bin_count, c->fill, K, B, s->Bp, s->L, s->NCb,
+                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols);
+  else
+    k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, meta->pos_rows,
+                                                          meta->stage_info, meta->bin_count, c->fill, K, B, s->Bp, s->L, s->NCb,
+                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
