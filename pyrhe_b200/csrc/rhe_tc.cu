@@ -51,6 +51,7 @@ struct TcState {
   int8_t* rq = nullptr;       // [NBa][Np]   limb l of column c at row l * R1p + c, permuted individual order
   double* col_dq = nullptr;   // [R1]        power-of-two dequantisation factor of every RHS column
   int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights of the current block
+  int32_t* pos_meta = nullptr;  // [cap_pos]      SNP row | fill << 24 of the current block
   unsigned int* wmax = nullptr; // [B]         max |weight| per column (float bits)
   int cap_pos = 0;
   std::vector<TcBlockMeta> blocks;
@@ -145,6 +146,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
+// Loop-invariant form: the start address lives in the low 14 bits of the low word, so advancing the operand by
+// `bytes` is one 32-bit add on a precomputed descriptor (no carry: all shared addresses are < 256 KB).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // Instruction descriptor for kind::i8: S32 accumulator, signed 8-bit A and B (cute::UMMA::InstrDescriptor).
 __host__ __device__ constexpr uint32_t idesc_i8(int M, int N, int a_mn_major) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | (0u << 16) |
@@ -234,6 +239,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint4 (&r)[8]) {
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// Zero 32 consecutive TMEM columns of this thread's lane (accumulators start at 0 so that every MMA can
+// accumulate and the issuing threads need no ordering among themselves).
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  uint4 z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  tmem_st32(taddr, z);
+}
+
 // D[tmem] (+)= A[tmem] * B[smem], int8 x int8 -> int32 (A operand from tensor memory, K-major)
 __device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   uint32_t zero = 0;
@@ -244,13 +258,32 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(zero) : "memory");
 }
 
+// Optional cycle accounting (PYRHE_TC_PROF=1 at build time): where each role spends its time.
+#ifdef RHE_TC_PROF
+__device__ unsigned long long g_prof[32];
+#define PROF_T0() long long _t0 = clock64()
+#define PROF_ADD(slot) do { long long _t1 = clock64(); if ((threadIdx.x & 127) == 0 || threadIdx.x == 32 * (PB_DW + 1)) atomicAdd(&g_prof[slot], (unsigned long long)(_t1 - _t0)); _t0 = _t1; } while (0)
+extern "C" void rhe_tc_prof_dump() {
+  unsigned long long h[32];
+  cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+  const char* names[] = {"B.dec.cpwait", "B.dec.lds+meta", "B.dec.empty_wait", "B.dec.store", "B.dec.fence+arrive", "B.dec.epilogue",
+                         "B.mma.info", "B.mma.full_b", "B.mma.full_a", "B.mma.issue", "B.mma.total", "B.tma.empty_b", "B.dec.total", "B.dec.issue"};
+  for (int i = 0; i < 14; ++i) printf("  %-20s %12.3f Mcyc\n", names[i], h[i] / 1e6);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+}
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#endif
+
 // ------------------------------------------------------------------------------------------ pass A
 // grid = (SNP tiles of 128, splits over individuals).  t_raw[s][c] += dq[c] * sum_i g_is * q_ic  (exact).
 // Two groups of four decode warps; group g expands sub-tiles q = g, g + 2 of every 512-individual super-stage
 // into TMEM A slot q.
 #define PA_G 2
 #define PA_DW (4 * PA_G)
-#define PA_THREADS (32 * (PA_DW + 2))
+#define PA_THREADS (32 * (PA_DW + 1 + PA_G))   // decode warps, one TMA warp, one MMA-issue warp per group
 #define PA_AS 4                   // TMEM A slots (32 columns each) = sub-tiles of one super-stage
 #define PA_BS 4                   // smem ring of Rq tiles (TMA)
 #define PA_PK 4                   // cp.async ring of packed super-stages (128 rows x 128 B)
@@ -282,7 +315,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   if (threadIdx.x == 0) {
     for (int s = 0; s < PA_AS; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
     for (int s = 0; s < PA_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
-    mbar_init(&sm->acc_full, 1);
+    mbar_init(&sm->acc_full, PA_G);
     fence_barrier_init();
   }
   if (warp == PA_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
@@ -290,6 +323,11 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
+  if (warp < 4)                                        // zero the accumulator columns (lane quadrant per warp)
+    for (uint32_t c = 0; c < col_a; c += 32) tmem_zero32(tmem + ((uint32_t)(warp * 32) << 16) + c);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < PA_DW) {
     const int t = threadIdx.x & 127, g = warp >> 2;
@@ -358,22 +396,25 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
       }
     }
   } else {
+    // ---- MMA issue: one warp (one elected lane) per decode group, so no single thread serialises the block.
+    // Every MMA accumulates (the accumulator was zeroed), hence the issuers need no mutual ordering.
     if (lane == 0) {
+      const int g = warp - (PA_DW + 1);
       const uint32_t idesc = idesc_i8(128, NB, 0);
+      static_assert(PA_BS == 4, "sub-tile q of every super-stage uses Rq ring slot q");
       for (int ss = 0; ss < n_ss; ++ss) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int sub = ss * 4 + q, b = sub % PA_BS, useb = sub / PA_BS;
-          mbar_wait(&sm->full_b[b], useb & 1);
+        for (int q0 = 0; q0 < 4; q0 += PA_G) {         // sub = 4 ss + q: TMEM A slot q, Rq ring slot q, use ss
+          const int q = q0 + g;
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(tileB + q * tileB_bytes), 16, 1024);
+          mbar_wait(&sm->full_b[q], ss & 1);
           mbar_wait(&sm->full_a[q], ss & 1);
           tc_fence_after();
-          const uint32_t b0 = smem_u32(tileB + b * tileB_bytes);
 #pragma unroll
           for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
-            umma_i8_ts(tmem, tmem + col_a + 32 * q + 8 * j, smem_desc_sw128(b0 + j * 32, 16, 1024), idesc,
-                       (uint32_t)((sub | j) != 0));
+            umma_i8_ts(tmem, tmem + col_a + 32 * q + 8 * j, desc_advance(bdesc, j * 32), idesc, 1u);
           umma_commit(&sm->empty_a[q]);
-          umma_commit(&sm->empty_b[b]);
+          umma_commit(&sm->empty_b[q]);
         }
       }
       umma_commit(&sm->acc_full);
@@ -390,23 +431,29 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 // accumulates in TMEM columns [(k * MT + q) * NC, +NC).
 #define PB_G 4
 #define PB_DW (4 * PB_G)
-#define PB_THREADS (32 * (PB_DW + 2))
+#define PB_THREADS (32 * (PB_DW + 1 + PB_G))   // decode warps, one TMA warp, one MMA-issue warp per group
 #define PB_BS 4                   // smem ring of Uq tiles (TMA)
 #define PB_PKG 4                  // per-group cp.async ring depth (in the group's own stages)
 
+#define PB_MAX_STAGES 512
+#define PB_MAX_KB 1024            // K * B entries of the per-bin mean term staged in shared memory
 struct PbSmem {
   uint64_t full_a[PB_G], empty_a[PB_G], full_b[PB_BS], empty_b[PB_BS], acc_full;
   uint32_t tmem_base;
+  int32_t info[PB_MAX_STAGES];    // stage_info of the block
+  double cs[PB_MAX_KB];           // per-(bin, column) mean term
+  double dq[64];                  // per-column dequantisation factor 2^(e - F)
+  int32_t cnt[256];               // rows per bin
 };
 
 template <int MT>
 __global__ void __launch_bounds__(PB_THREADS, 1)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
-            const int32_t* __restrict__ pos_rows, const int32_t* __restrict__ stage_info,
-            const int32_t* __restrict__ bin_count, const uint8_t* __restrict__ fill, int K, int B, int Bp, int L, int NC,
+            const int32_t* __restrict__ pos_meta, const int32_t* __restrict__ stage_info,
+            const int32_t* __restrict__ bin_count, int K, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, float* __restrict__ P_out, float* __restrict__ S_accum,
-            uint32_t tmem_cols) {
+            uint32_t tmem_cols, int a_major, int kcap) {
   constexpr int SI = PB_G / MT;                      // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -422,15 +469,28 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PB_G; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
-    for (int s = 0; s < PB_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
-    mbar_init(&sm->acc_full, 1);
+    for (int s = 0; s < PB_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], MT); }
+    mbar_init(&sm->acc_full, PB_G);
     fence_barrier_init();
   }
   if (warp == PB_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
+  for (int i = threadIdx.x; i < n_stage; i += PB_THREADS) sm->info[i] = stage_info[i];
+  for (int i = threadIdx.x; i < K * B; i += PB_THREADS) sm->cs[i] = cs[i];
+  for (int i = threadIdx.x; i < K; i += PB_THREADS) sm->cnt[i] = bin_count[i];
+  // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
+  for (int i = threadIdx.x; i < B; i += PB_THREADS) sm->dq[i] = ldexp(1.0, (int)((wmax[i] >> 23) & 255u) - 126 - F);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
+  if (warp < PB_DW) {                                  // zero the accumulators: quadrant per warp, columns split by group
+    const uint32_t used = (uint32_t)(K * MT * NC);
+    for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < used; c += 32 * PB_G)
+      tmem_zero32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < PB_DW) {
     const int t = threadIdx.x & 127, g = warp >> 2;
@@ -439,33 +499,60 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const uint32_t ring = packed_s + g * (PB_PKG * 4096) + t * 16;
     const uint32_t tile = tileA_s + g * TC_TILE_A;
     const int n_own = n_stage > par ? (n_stage - par + SI - 1) / SI : 0;   // stages st = par + SI * u
-    auto issue = [&](int u) {
-      const int row = pos_rows[(par + SI * u) * 128 + t];
-      if (row >= 0) {
-        const uint8_t* p = base + (size_t)row * pitch;
+    // pos_meta[p] = SNP row | fill << 24 (or -1 for padding); loaded one iteration before it is needed so
+    // that the dependent address never stalls the (in-order) decode thread
+    auto meta_of = [&](int u) { return u < n_own ? __ldg(pos_meta + (par + SI * u) * 128 + t) : -1; };
+    auto issue = [&](int u, int meta) {
+      if (meta >= 0) {
+        const uint8_t* p = base + (size_t)(meta & 0xFFFFFF) * pitch;
         const uint32_t slot = ring + (u % PB_PKG) * 4096;
         cp_async16(slot, p);
         cp_async16(slot + 2048, p + 16);
       }
     };
+    int tabs[PB_PKG];                                  // value tables of the stages in flight (register ring)
 #pragma unroll
     for (int pre = 0; pre < PB_PKG - 1; ++pre) {
-      if (pre < n_own) issue(pre);
+      const int meta = meta_of(pre);
+      issue(pre, meta);
+      tabs[pre] = meta;
       cp_async_commit();
     }
-    for (int u = 0; u < n_own; ++u) {
-      if (u + PB_PKG - 1 < n_own) issue(u + PB_PKG - 1);
-      cp_async_commit();
-      cp_async_wait<PB_PKG - 1>();
-      const int row = pos_rows[(par + SI * u) * 128 + t];
-      const uint32_t tab = 0x02010000u | (row >= 0 ? (uint32_t)fill[row] << 8 : 0u);
-      const uint32_t slot = ring + (u % PB_PKG) * 4096;
-      const uint4 lo = lds128(slot), hi = lds128(slot + 2048);
-      mbar_wait(&sm->empty_a[g], (u & 1) ^ 1);
-      tc_store_row(tile, t, lo, hi, tab);
-      fence_proxy_async();
-      mbar_arrive(&sm->full_a[g]);
+    int meta_next = meta_of(PB_PKG - 1);
+    PROF_T0();
+#ifdef RHE_TC_PROF
+    const long long _tstart = clock64();
+#endif
+    for (int u0 = 0; u0 < n_own; u0 += PB_PKG) {
+#pragma unroll
+      for (int r = 0; r < PB_PKG; ++r) {               // unrolled so that the register ring is statically indexed
+        const int u = u0 + r;
+        if (u < n_own) {
+          issue(u + PB_PKG - 1, meta_next);
+          tabs[(r + PB_PKG - 1) % PB_PKG] = meta_next;
+          meta_next = meta_of(u + PB_PKG);
+          cp_async_commit();
+          PROF_ADD(13);
+          cp_async_wait<PB_PKG - 1>();
+          PROF_ADD(0);
+          const int meta = tabs[r];
+          const uint32_t tab = 0x02010000u | (meta >= 0 ? ((uint32_t)meta >> 24) << 8 : 0u);
+          const uint32_t slot = ring + (u % PB_PKG) * 4096;
+          const uint4 lo = lds128(slot), hi = lds128(slot + 2048);
+          PROF_ADD(1);
+          mbar_wait(&sm->empty_a[g], (u & 1) ^ 1);
+          PROF_ADD(2);
+          tc_store_row(tile, t, lo, hi, tab);
+          PROF_ADD(3);
+          fence_proxy_async();
+          mbar_arrive(&sm->full_a[g]);
+          PROF_ADD(4);
+        }
+      }
     }
+#ifdef RHE_TC_PROF
+    if ((threadIdx.x & 127) == 0) atomicAdd(&g_prof[12], (unsigned long long)(clock64() - _tstart));
+#endif
     // ---- epilogue: TMEM lane = position inside M-tile q; group (par, q) takes the bins k = par (mod SI)
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
@@ -473,7 +560,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
     const double rs = (double)rowscale[i];
     for (int k = par; k < K; k += SI) {
-      const bool has = bin_count[k] > 0;
+      const bool has = sm->cnt[k] > 0;
       const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
       for (int c0 = 0; c0 < Bp; c0 += 2) {
         double val[2] = {0.0, 0.0};
@@ -482,9 +569,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
         for (int j = 0; j < 2; ++j) {
           const int b = c0 + j;
           if (b < B) {
-            // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
-            const int e = (int)((wmax[b] >> 23) & 255u) - 126;
-            const float xf = has ? (float)(rs * (ldexp(val[j], e - F) - cs[(size_t)k * B + b])) : 0.f;
+            const float xf = has ? (float)(rs * (val[j] * sm->dq[b] - sm->cs[k * B + b])) : 0.f;
             const size_t o = ((size_t)k * B + b) * Np + i;
             if (P_out) P_out[o] = xf;
             if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
@@ -492,6 +577,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
         }
       }
     }
+    PROF_ADD(5);
     tc_fence_before();
   } else if (warp == PB_DW) {
     if (lane == 0) {
@@ -503,29 +589,40 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       }
     }
   } else {
+    // ---- MMA issue: one warp (one elected lane) per decode group (par, q); all MMAs accumulate into zeroed TMEM
     if (lane == 0) {
-      const uint32_t idesc = idesc_i8(128, NC, 1);   // A is MN-major: 128 individuals contiguous per SNP row
-      for (int st = 0; st < n_stage; ++st) {
-        const int b = st % PB_BS, useb = st / PB_BS;
-        const int info = stage_info[st];
-        const int k = info & 255, first = (info >> 8) & 1, ksteps = info >> 16;
-        mbar_wait(&sm->full_b[b], useb & 1);
-        const uint32_t b0 = smem_u32(tileB + b * tileB_bytes);
-        const int par = st % SI, u = st / SI;
-#pragma unroll
-        for (int q = 0; q < MT; ++q) {
-          const int g = par * MT + q;
-          mbar_wait(&sm->full_a[g], u & 1);
-          tc_fence_after();
-          const uint32_t a0 = tileA_s + g * TC_TILE_A;
-          for (int j = 0; j < ksteps; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
-            umma_i8(tmem + (uint32_t)((k * MT + q) * NC), smem_desc_sw128(a0 + j * 4096, TC_TILE_A, 1024),
-                    smem_desc_sw128(b0 + j * 32, 16, 1024), idesc, (uint32_t)(!first || j > 0));
-          umma_commit(&sm->empty_a[g]);
-        }
+      const int g = warp - (PB_DW + 1);
+      const int par = g / MT, q = g % MT;
+      const uint32_t idesc = idesc_i8(128, NC, a_major);   // A is MN-major: 128 individuals contiguous per SNP row
+      const uint64_t adesc = smem_desc_sw128(tileA_s + g * TC_TILE_A, TC_TILE_A, 1024);
+      const uint32_t tileB_s = smem_u32(tileB);
+      PROF_T0();
+#ifdef RHE_TC_PROF
+      const long long _tstart = clock64();
+#endif
+      int u = 0;
+      for (int st = par; st < n_stage; st += SI, ++u) {
+        const int b = st % PB_BS;
+        const int info = sm->info[st];
+        const int k = info & 255, ksteps = min(info >> 16, kcap);
+        const uint64_t bdesc = smem_desc_sw128(tileB_s + b * tileB_bytes, 16, 1024);
+        PROF_ADD(6);
+        mbar_wait(&sm->full_b[b], (st / PB_BS) & 1);
+        PROF_ADD(7);
+        mbar_wait(&sm->full_a[g], u & 1);
+        PROF_ADD(8);
+        tc_fence_after();
+        const uint32_t dcol = tmem + (uint32_t)((k * MT + q) * NC);
+        for (int j = 0; j < ksteps; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
+          umma_i8(dcol, desc_advance(adesc, j * 4096), desc_advance(bdesc, j * 32), idesc, 1u);
+        umma_commit(&sm->empty_a[g]);
         umma_commit(&sm->empty_b[b]);
+        PROF_ADD(9);
       }
       umma_commit(&sm->acc_full);
+#ifdef RHE_TC_PROF
+      atomicAdd(&g_prof[10], (unsigned long long)(clock64() - _tstart));
+#endif
     }
   }
   __syncthreads();
@@ -584,11 +681,13 @@ __global__ void k_tc_wmax(const float* __restrict__ w1, int m, int B, unsigned i
 }
 
 __global__ void k_tc_quant_w(const float* __restrict__ w1, const int32_t* __restrict__ pos_rows, int n_pos, int cap_pos,
-                             int B, int Bp, int L, int F, const unsigned int* __restrict__ wmax, int8_t* __restrict__ uq) {
+                             int B, int Bp, int L, int F, const unsigned int* __restrict__ wmax, int8_t* __restrict__ uq,
+                             const uint8_t* __restrict__ fill, int32_t* __restrict__ pos_meta) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pos * B) return;
   const int p = idx % n_pos, b = idx / n_pos;
   const int row = pos_rows[p];
+  if (b == 0) pos_meta[p] = row >= 0 ? (row | ((int)fill[row] << 24)) : -1;   // row + this step's fill value
   const int e = (int)((wmax[b] >> 23) & 255u) - 126;
   const long long q = row >= 0 ? llrint(ldexp((double)w1[(size_t)row * B + b], F - e)) : 0ll;
   tc_limbs(q, L, uq + (size_t)b * cap_pos + p, (size_t)Bp * cap_pos);
@@ -624,7 +723,7 @@ int rhe_tc_create(rhe_ctx* c) {
   s->Bp = round_up(g.n_vec, 2);
   s->NCb = round_up(s->L * s->Bp, 16);
   s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
-  if (s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255) {
+  if (s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || g.n_bins * g.n_vec > PB_MAX_KB || g.n_vec > 64) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     delete s;
     return RHE_ERR_UNSUPPORTED;
@@ -660,7 +759,7 @@ void rhe_tc_destroy(rhe_ctx* c) {
     if (b.stage_info) cudaFree(b.stage_info);
     if (b.bin_count) cudaFree(b.bin_count);
   }
-  void* ptrs[] = {s->rq, s->col_dq, s->uq, s->wmax};
+  void* ptrs[] = {s->rq, s->col_dq, s->uq, s->wmax, s->pos_meta};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete s;
   c->tc = nullptr;
@@ -742,10 +841,13 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   int rc = tc_block_meta(c, s, m, bin_rows, bin_off, bin_off_host, st, &meta);
   if (rc) return rc;
   const int n_pos = meta->n_pos;
+  if (n_pos / 128 > PB_MAX_STAGES) { rhe_set_error("RHE_PATH_TCGEN05: block has %d bin-sorted positions (max %d)", n_pos, PB_MAX_STAGES * 128); return RHE_ERR_UNSUPPORTED; }
   if (n_pos > s->cap_pos) {
     RHE_CUDA(cudaStreamSynchronize(st));
     if (s->uq) cudaFree(s->uq);
+    if (s->pos_meta) cudaFree(s->pos_meta);
     s->cap_pos = round_up(n_pos + n_pos / 8, 128);
+    RHE_CUDA(cudaMalloc((void**)&s->pos_meta, sizeof(int32_t) * s->cap_pos));
     RHE_CUDA(cudaMalloc((void**)&s->uq, (size_t)s->NCb * s->cap_pos));
     RHE_CUDA(cudaMemset(s->uq, 0, (size_t)s->NCb * s->cap_pos));
     rc = tc_encode_2d(s, &s->tm_uq, s->uq, (uint64_t)s->cap_pos, (uint64_t)s->NCb, (uint32_t)s->NCb);
@@ -753,19 +855,19 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   }
   if (n_pos > 0) {
     k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B, 256), 256, 0, st>>>(c->w1, meta->pos_rows, n_pos, s->cap_pos, B, s->Bp, s->L,
-                                                                      s->F, s->wmax, s->uq);
+                                                                      s->F, s->wmax, s->uq, c->fill, s->pos_meta);
     RHE_LAUNCH_CHECK(c);
   }
   const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
   const int smem = pb_smem_bytes(s->NCb);
   if (s->MT == 2)
-    k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, meta->pos_rows,
-                                                          meta->stage_info, meta->bin_count, c->fill, K, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols);
+    k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, s->pos_meta,
+                                                          meta->stage_info, meta->bin_count, K, B, s->Bp, s->L, s->NCb,
+                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
   else
-    k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, meta->pos_rows,
-                                                          meta->stage_info, meta->bin_count, c->fill, K, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols);
+    k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, s->pos_meta,
+                                                          meta->stage_info, meta->bin_count, K, B, s->Bp, s->L, s->NCb,
+                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
