@@ -41,6 +41,18 @@ __global__ void k_colsum(const float* __restrict__ rhs, int Np, double* __restri
   }
 }
 
+__device__ __forceinline__ uint4 rhe_ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void rhe_popc_word(uint32_t x, uint32_t keep, int& n1, int& n2, int& nm) {
+  const uint32_t k = keep & 0x55555555u, lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+  n2 += __popc(hi & lo & k);
+  n1 += __popc(hi & ~lo & k);
+  nm += __popc(~hi & lo & k);
+}
+
 // Masked popcount statistics: one warp per SNP row (base.py:277-289 needs the observed mean).
 __global__ void __launch_bounds__(256)
 k_stats(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t* __restrict__ keep2,
@@ -50,12 +62,18 @@ k_stats(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t* __res
   int lane = threadIdx.x & 31;
   const uint32_t* row = reinterpret_cast<const uint32_t*>(bed + (size_t)s * pitch);
   int n1 = 0, n2 = 0, nm = 0;
-  for (int w = lane; w < pitch / 4; w += 32) {
-    uint32_t x = __ldg(row + w), k = __ldg(keep2 + w) & 0x55555555u;
-    uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
-    n2 += __popc(hi & lo & k);
-    n1 += __popc(hi & ~lo & k);
-    nm += __popc(~hi & lo & k);
+  {
+    const uint4* row4 = reinterpret_cast<const uint4*>(row);
+    const uint4* keep4 = reinterpret_cast<const uint4*>(keep2);
+    const int n4 = pitch / 16;                      // pitch is a multiple of 128 bytes
+#pragma unroll 4
+    for (int w = lane; w < n4; w += 32) {
+      const uint4 x = rhe_ldg_stream(row4 + w), k = __ldg(keep4 + w);
+      rhe_popc_word(x.x, k.x, n1, n2, nm);
+      rhe_popc_word(x.y, k.y, n1, n2, nm);
+      rhe_popc_word(x.z, k.z, n1, n2, nm);
+      rhe_popc_word(x.w, k.w, n1, n2, nm);
+    }
   }
   for (int o = 16; o; o >>= 1) {
     n1 += __shfl_xor_sync(0xffffffffu, n1, o);
@@ -114,12 +132,18 @@ k_stats_params(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t
     for (int c = lane; c < t_cols; c += 32) t_raw[((size_t)op * m + s) * t_cols + c] = 0.0;
   const uint32_t* row = reinterpret_cast<const uint32_t*>(bed + (size_t)s * pitch);
   int n1 = 0, n2 = 0, nm = 0;
-  for (int w = lane; w < pitch / 4; w += 32) {
-    uint32_t x = __ldg(row + w), k = __ldg(keep2 + w) & 0x55555555u;
-    uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
-    n2 += __popc(hi & lo & k);
-    n1 += __popc(hi & ~lo & k);
-    nm += __popc(~hi & lo & k);
+  {
+    const uint4* row4 = reinterpret_cast<const uint4*>(row);
+    const uint4* keep4 = reinterpret_cast<const uint4*>(keep2);
+    const int n4 = pitch / 16;                      // pitch is a multiple of 128 bytes
+#pragma unroll 4
+    for (int w = lane; w < n4; w += 32) {
+      const uint4 x = rhe_ldg_stream(row4 + w), k = __ldg(keep4 + w);
+      rhe_popc_word(x.x, k.x, n1, n2, nm);
+      rhe_popc_word(x.y, k.y, n1, n2, nm);
+      rhe_popc_word(x.z, k.z, n1, n2, nm);
+      rhe_popc_word(x.w, k.w, n1, n2, nm);
+    }
   }
   for (int o = 16; o; o >>= 1) {
     n1 += __shfl_xor_sync(0xffffffffu, n1, o);
@@ -464,6 +488,55 @@ __global__ void k_synth(uint8_t* __restrict__ bed, int64_t n_rows, int64_t pitch
   }
 }
 
+// Fast path for E <= 8 (RHE with up to 8 bins): one thread per position, the (at most 36) pair products stay in
+// fp64 registers over a grid-stride loop, one warp + block reduction at the end.  Memory bound: reads S and P once.
+template <int E>
+__global__ void __launch_bounds__(256)
+k_loo_gram_small(const float* __restrict__ S, const float* __restrict__ P, int64_t len, double* __restrict__ out) {
+  constexpr int NP = E * (E + 1) / 2;
+  double acc[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = 0.0;
+  for (int64_t g = blockIdx.x * (int64_t)256 + threadIdx.x; g < len; g += (int64_t)gridDim.x * 256) {
+    double d[E];
+#pragma unroll
+    for (int a = 0; a < E; ++a) {
+      float v = __ldg(S + (size_t)a * len + g);
+      d[a] = P ? (double)v - (double)__ldg(P + (size_t)a * len + g) : (double)v;
+    }
+    int p = 0;
+#pragma unroll
+    for (int a = 0; a < E; ++a)
+#pragma unroll
+      for (int c = a; c < E; ++c) { acc[p] = fma(d[a], d[c], acc[p]); ++p; }
+  }
+  __shared__ double red[8][NP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    double v = acc[p];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][p] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NP) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    int a = 0, rem = threadIdx.x;
+    while (rem >= E - a) { rem -= E - a; ++a; }
+    const int c = a + rem;
+    atomicAdd(out + a * E + c, v);
+    if (a != c) atomicAdd(out + c * E + a, v);
+  }
+}
+
+template <int E>
+static void launch_loo_small(const float* S, const float* P, int64_t len, double* out, cudaStream_t st) {
+  int64_t blocks = (len + 255) / 256;
+  int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  k_loo_gram_small<E><<<grid, 256, 0, st>>>(S, P, len, out);
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 
@@ -748,9 +821,21 @@ extern "C" int rhe_loo_gram(rhe_ctx* c, const float* S, const float* P, int32_t 
   if (n_est < 1 || n_est > GRAM_MAX_E) { rhe_set_error("rhe_loo_gram: n_est %d outside [1, %d]", n_est, GRAM_MAX_E); return RHE_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   RHE_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_est * n_est, st));
-  int64_t nchunks = (len + GRAM_CHUNK - 1) / GRAM_CHUNK;
-  int grid = (int)(nchunks < 148 * 4 ? nchunks : 148 * 4);
-  k_loo_gram<<<grid, 256, 0, st>>>(S, P, n_est, len, out);
+  switch (n_est) {
+    case 1: launch_loo_small<1>(S, P, len, out, st); break;
+    case 2: launch_loo_small<2>(S, P, len, out, st); break;
+    case 3: launch_loo_small<3>(S, P, len, out, st); break;
+    case 4: launch_loo_small<4>(S, P, len, out, st); break;
+    case 5: launch_loo_small<5>(S, P, len, out, st); break;
+    case 6: launch_loo_small<6>(S, P, len, out, st); break;
+    case 7: launch_loo_small<7>(S, P, len, out, st); break;
+    case 8: launch_loo_small<8>(S, P, len, out, st); break;
+    default: {
+      int64_t nchunks = (len + GRAM_CHUNK - 1) / GRAM_CHUNK;
+      int grid = (int)(nchunks < 148 * 4 ? nchunks : 148 * 4);
+      k_loo_gram<<<grid, 256, 0, st>>>(S, P, n_est, len, out);
+    }
+  }
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
