@@ -450,7 +450,7 @@ template <int MT>
 __global__ void __launch_bounds__(PB_THREADS, 1)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
             const int32_t* __restrict__ pos_meta, const int32_t* __restrict__ stage_info,
-            const int32_t* __restrict__ bin_count, int K, int B, int Bp, int L, int NC,
+            const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, float* __restrict__ P_out, float* __restrict__ S_accum,
             uint32_t tmem_cols, int a_major, int kcap) {
@@ -475,7 +475,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   }
   if (warp == PB_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
   for (int i = threadIdx.x; i < n_stage; i += PB_THREADS) sm->info[i] = stage_info[i];
-  for (int i = threadIdx.x; i < K * B; i += PB_THREADS) sm->cs[i] = cs[i];
+  for (int i = threadIdx.x; i < WG * K * B; i += PB_THREADS) sm->cs[i] = cs[i];
   for (int i = threadIdx.x; i < K; i += PB_THREADS) sm->cnt[i] = bin_count[i];
   // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
   for (int i = threadIdx.x; i < B; i += PB_THREADS) sm->dq[i] = ldexp(1.0, (int)((wmax[i] >> 23) & 255u) - 126 - F);
@@ -558,21 +558,24 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     tc_fence_after();
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
-    const double rs = (double)rowscale[i];
     for (int k = par; k < K; k += SI) {
       const bool has = sm->cnt[k] > 0;
       const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
-      for (int c0 = 0; c0 < Bp; c0 += 2) {
-        double val[2] = {0.0, 0.0};
-        if (has) tmem_combine2(tcol + (uint32_t)c0, L, Bp, val);
+      for (int wg = 0; wg < WG; ++wg) {              // weight group = RHS set (GxE: rows scaled by env) -> estimate wg * K + k
+        const int e = wg * K + k;
+        const double rs = (double)rowscale[(size_t)wg * Np + i];
+        for (int c0 = 0; c0 < Bp; c0 += 2) {
+          double val[2] = {0.0, 0.0};
+          if (has) tmem_combine2(tcol + (uint32_t)(wg * L * Bp + c0), L, Bp, val);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int b = c0 + j;
-          if (b < B) {
-            const float xf = has ? (float)(rs * (val[j] * sm->dq[b] - sm->cs[k * B + b])) : 0.f;
-            const size_t o = ((size_t)k * B + b) * Np + i;
-            if (P_out) P_out[o] = xf;
-            if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
+          for (int j = 0; j < 2; ++j) {
+            const int b = c0 + j;
+            if (b < B) {
+              const float xf = has ? (float)(rs * (val[j] * sm->dq[b] - sm->cs[e * B + b])) : 0.f;
+              const size_t o = ((size_t)e * B + b) * Np + i;
+              if (P_out) P_out[o] = xf;
+              if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
+            }
           }
         }
       }
@@ -681,13 +684,15 @@ __global__ void k_tc_wmax(const float* __restrict__ w1, int m, int B, unsigned i
 }
 
 __global__ void k_tc_quant_w(const float* __restrict__ w1, const int32_t* __restrict__ pos_rows, int n_pos, int cap_pos,
-                             int B, int Bp, int L, int F, const unsigned int* __restrict__ wmax, int8_t* __restrict__ uq,
-                             const uint8_t* __restrict__ fill, int32_t* __restrict__ pos_meta) {
+                             int m, int WG, int B, int Bp, int L, int F, const unsigned int* __restrict__ wmax,
+                             int8_t* __restrict__ uq, const uint8_t* __restrict__ fill, int32_t* __restrict__ pos_meta) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_pos * B) return;
-  const int p = idx % n_pos, b = idx / n_pos;
+  if (idx >= n_pos * B * WG) return;
+  const int p = idx % n_pos, b = (idx / n_pos) % B, wg = idx / (n_pos * B);
   const int row = pos_rows[p];
-  if (b == 0) pos_meta[p] = row >= 0 ? (row | ((int)fill[row] << 24)) : -1;   // row + this step's fill value
+  if (b == 0 && wg == 0) pos_meta[p] = row >= 0 ? (row | ((int)fill[row] << 24)) : -1;   // row + this step's fill value
+  w1 += (size_t)wg * m * B;                          // weights of group wg: [m][B]
+  uq += (size_t)wg * L * Bp * cap_pos;               // its limb rows follow those of the previous group
   const int e = (int)((wmax[b] >> 23) & 255u) - 126;
   const long long q = row >= 0 ? llrint(ldexp((double)w1[(size_t)row * B + b], F - e)) : 0ll;
   tc_limbs(q, L, uq + (size_t)b * cap_pos + p, (size_t)Bp * cap_pos);
@@ -712,7 +717,7 @@ static inline int pb_smem_bytes(int nc) { return PB_G * TC_TILE_A + PB_BS * nc *
 
 int rhe_tc_create(rhe_ctx* c) {
   const rhe_config& g = c->cfg;
-  if (g.n_ops != 1 || g.n_sets != 1) { rhe_set_error("RHE_PATH_TCGEN05 currently covers the RHE model (one operand, one RHS set)"); return RHE_ERR_UNSUPPORTED; }
+  if (g.n_ops != 1) { rhe_set_error("RHE_PATH_TCGEN05 covers one genotype operand (RHE, GENIE); RHE-DOM runs on RHE_PATH_SIMT"); return RHE_ERR_UNSUPPORTED; }
   TcState* s = new TcState();
   const char* envL = getenv("PYRHE_B200_LIMBS");
   s->L = envL ? atoi(envL) : 3;
@@ -721,9 +726,9 @@ int rhe_tc_create(rhe_ctx* c) {
   s->R1p = round_up(c->R1, 4);
   s->NBa = round_up(s->L * s->R1p, 16);
   s->Bp = round_up(g.n_vec, 2);
-  s->NCb = round_up(s->L * s->Bp, 16);
+  s->NCb = round_up(c->n_groups * s->L * s->Bp, 16);   // weight groups (RHS sets) are stacked along N
   s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
-  if (s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || g.n_bins * g.n_vec > PB_MAX_KB || g.n_vec > 64) {
+  if (s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || g.n_vec > 64) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     delete s;
     return RHE_ERR_UNSUPPORTED;
@@ -854,19 +859,19 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
     if (rc) return rc;
   }
   if (n_pos > 0) {
-    k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B, 256), 256, 0, st>>>(c->w1, meta->pos_rows, n_pos, s->cap_pos, B, s->Bp, s->L,
-                                                                      s->F, s->wmax, s->uq, c->fill, s->pos_meta);
+    k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B * c->n_groups, 256), 256, 0, st>>>(
+        c->w1, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, B, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill, s->pos_meta);
     RHE_LAUNCH_CHECK(c);
   }
   const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
   const int smem = pb_smem_bytes(s->NCb);
   if (s->MT == 2)
     k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, s->pos_meta,
-                                                          meta->stage_info, meta->bin_count, K, B, s->Bp, s->L, s->NCb,
+                                                          meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
                                                           s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
   else
     k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, s->pos_meta,
-                                                          meta->stage_info, meta->bin_count, K, B, s->Bp, s->L, s->NCb,
+                                                          meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
                                                           s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
