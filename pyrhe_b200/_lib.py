@@ -79,3 +79,14 @@ def ptr(t):
     if hasattr(t, "data_ptr"):
         return C.c_void_p(t.data_ptr())
     return C.c_void_p(t.ctypes.data)
+
+
+def tcgen05_supported(plan, limbs: int = None) -> bool:
+    """Mirror of the limits rhe_tc_create enforces (TMEM columns per CTA, staged metadata sizes)."""
+    L = int(os.environ.get("PYRHE_B200_LIMBS", "3")) if limbs is None else limbs
+    r1p = -(-(plan.n_sets * plan.Rs) // 4) * 4
+    nba = -(-(L * r1p) // 16) * 16
+    bp = -(-plan.B // 2) * 2
+    ncb = -(-(plan.n_groups * L * bp) // 16) * 16
+    return (nba <= 256 and plan.K * ncb <= 512 and plan.K <= 255 and plan.n_groups * plan.K * plan.B <= 1024
+            and plan.B <= 64)

@@ -219,9 +219,9 @@ class Base(ABC):
             import torch.distributed as dist
             if not dist.is_initialized():
                 dist.init_process_group("nccl", device_id=self.device)
-        # int8 tcgen05 kernels for one genotype operand (RHE, GENIE incl. the env-scaled GxE set); the CUDA-core
-        # kernels of the same library for RHE-DOM until its [g == 2] operand is ported
-        default_path = _lib.PATH_TCGEN05 if plan.n_ops == 1 and plan.K <= 16 else _lib.PATH_SIMT
+        # int8 tcgen05 kernels (RHE, RHE-DOM with its [g == 2] operand, GENIE with the env-scaled GxE set) whenever
+        # the accumulators of all bins fit one TMEM allocation; otherwise the CUDA-core kernels of the same library
+        default_path = _lib.PATH_TCGEN05 if _lib.tcgen05_supported(plan) else _lib.PATH_SIMT
         path = self.kernel_path if self.kernel_path is not None else int(os.environ.get("PYRHE_B200_PATH", default_path))
         eng = RheEngine(plan, n_indv=self.num_indv_original, keep=keep, annot=self.annot_matrix,
                         num_jack=self.num_jack, impute=self.geno_impute_methods, seed=self.seed, device=self.device,

@@ -292,7 +292,8 @@ __global__ void k_standardize(int m, int Rs, int R1, int B, int n_ops, int n_set
     w1[o] = (float)a1;
     w2[o] = (float)a2;
     shiftv[o] = sh;
-    if (wmax) atomicMax(wmax + c, __float_as_uint(fabsf((float)a1)));   // tensor path: per-column quantisation range
+    if (wmax)   // tensor path: per-column quantisation range over both operand weights (count, [g == 2] extra)
+      atomicMax(wmax + c, __float_as_uint(fmaxf(fabsf((float)a1), fabsf((float)a2 - 2.0f * (float)a1))));
   }
 }
 

@@ -162,6 +162,12 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N, int a_mn_major) {
 __device__ __forceinline__ int tc_perm16(int p) { return ((p & 7) << 1) | (p >> 3); }        // byte -> individual
 __device__ __forceinline__ int tc_invperm16(int x) { return (x >> 1) | ((x & 1) << 3); }     // individual -> byte
 
+// Per-SNP value table, byte c = operand value of 2-bit code c.  mode 0: A2 count {0, fill, 1, 2};
+// mode 1: the dominance indicator [count == 2] = {0, fill == 2, 0, 1} (rhe_dom.py:36-39 after h = mu g - 2 [g == 2]).
+__device__ __forceinline__ uint32_t tc_value_table(uint32_t fill, int mode) {
+  return mode ? (0x01000000u | ((fill == 2u ? 1u : 0u) << 8)) : (0x02010000u | (fill << 8));
+}
+
 // Expand one packed word (16 genotypes) into 16 int8 values with the per-SNP value table
 // tab = {0, fill, 1, 2} (byte c = value of code c), in the permuted order above.
 __device__ __forceinline__ uint4 tc_expand(uint32_t w, uint32_t tab) {
@@ -297,7 +303,7 @@ struct PaSmem {
 __global__ void __launch_bounds__(PA_THREADS, 2)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict__ bed, int pitch, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
-            double* __restrict__ t_raw, int chunk, uint32_t tmem_cols, uint32_t col_a) {
+            double* __restrict__ t_raw, int chunk, uint32_t tmem_cols, uint32_t col_a, int mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileB = smem;
@@ -332,7 +338,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   if (warp < PA_DW) {
     const int t = threadIdx.x & 127, g = warp >> 2;
     const int s = min(snp0 + t, m - 1);
-    const uint32_t tab = ((uint32_t)fill[s] << 8) | (1u << 16) | (2u << 24);
+    const uint32_t tab = tc_value_table(fill[s], mode);
     const uint8_t* src = bed + (size_t)s * pitch + (i_begin >> 2);
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     // group g fetches only the chunks of its own sub-tiles (q = g, g + 2 -> chunks 2q, 2q + 1)
@@ -452,7 +458,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
             const int32_t* __restrict__ pos_meta, const int32_t* __restrict__ stage_info,
             const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
-            const float* __restrict__ rowscale, float* __restrict__ P_out, float* __restrict__ S_accum,
+            const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
             uint32_t tmem_cols, int a_major, int kcap) {
   constexpr int SI = PB_G / MT;                      // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
@@ -536,7 +542,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
           cp_async_wait<PB_PKG - 1>();
           PROF_ADD(0);
           const int meta = tabs[r];
-          const uint32_t tab = 0x02010000u | (meta >= 0 ? ((uint32_t)meta >> 24) << 8 : 0u);
+          const uint32_t tab = meta >= 0 ? tc_value_table(((uint32_t)meta >> 24) & 3u, (meta >> 26) & 1) : 0u;
           const uint32_t slot = ring + (u % PB_PKG) * 4096;
           const uint4 lo = lds128(slot), hi = lds128(slot + 2048);
           PROF_ADD(1);
@@ -561,9 +567,9 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     for (int k = par; k < K; k += SI) {
       const bool has = sm->cnt[k] > 0;
       const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
-      for (int wg = 0; wg < WG; ++wg) {              // weight group = RHS set (GxE: rows scaled by env) -> estimate wg * K + k
+      for (int wg = 0; wg < WG; ++wg) {              // weight group = RHS set (GxE) or operand (dominance) -> estimate wg * K + k
         const int e = wg * K + k;
-        const double rs = (double)rowscale[(size_t)wg * Np + i];
+        const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
         for (int c0 = 0; c0 < Bp; c0 += 2) {
           double val[2] = {0.0, 0.0};
           if (has) tmem_combine2(tcol + (uint32_t)(wg * L * Bp + c0), L, Bp, val);
@@ -683,19 +689,27 @@ __global__ void k_tc_wmax(const float* __restrict__ w1, int m, int B, unsigned i
   atomicMax(wmax + (idx % B), __float_as_uint(fabsf(w1[idx])));
 }
 
-__global__ void k_tc_quant_w(const float* __restrict__ w1, const int32_t* __restrict__ pos_rows, int n_pos, int cap_pos,
-                             int m, int WG, int B, int Bp, int L, int F, const unsigned int* __restrict__ wmax,
-                             int8_t* __restrict__ uq, const uint8_t* __restrict__ fill, int32_t* __restrict__ pos_meta) {
+// Quantise the pass-B weights of one block into int8 limbs, in bin-sorted position order, and emit the
+// per-position decode metadata (SNP row | fill << 24 | mode << 26).  mode 0 multiplies the count operand
+// (weight w1, with w2 = 2 w1 + extra); mode 1 multiplies the [g == 2] indicator operand (weight extra = w2 - 2 w1,
+// non-zero only for the dominance group) and occupies positions [n_pos, 2 n_pos).
+__global__ void k_tc_quant_w(const float* __restrict__ w1, const float* __restrict__ w2, const int32_t* __restrict__ pos_rows,
+                             int n_pos, int cap_pos, int m, int WG, int n_modes, int B, int Bp, int L, int F,
+                             const unsigned int* __restrict__ wmax, int8_t* __restrict__ uq,
+                             const uint8_t* __restrict__ fill, int32_t* __restrict__ pos_meta) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_pos * B * WG) return;
-  const int p = idx % n_pos, b = (idx / n_pos) % B, wg = idx / (n_pos * B);
+  if (idx >= n_pos * B * WG * n_modes) return;
+  const int p = idx % n_pos, b = (idx / n_pos) % B, wg = (idx / (n_pos * B)) % WG, mode = idx / (n_pos * B * WG);
   const int row = pos_rows[p];
-  if (b == 0 && wg == 0) pos_meta[p] = row >= 0 ? (row | ((int)fill[row] << 24)) : -1;   // row + this step's fill value
-  w1 += (size_t)wg * m * B;                          // weights of group wg: [m][B]
-  uq += (size_t)wg * L * Bp * cap_pos;               // its limb rows follow those of the previous group
+  if (b == 0 && wg == 0) pos_meta[mode * n_pos + p] = row >= 0 ? (row | ((int)fill[row] << 24) | (mode << 26)) : -1;
   const int e = (int)((wmax[b] >> 23) & 255u) - 126;
-  const long long q = row >= 0 ? llrint(ldexp((double)w1[(size_t)row * B + b], F - e)) : 0ll;
-  tc_limbs(q, L, uq + (size_t)b * cap_pos + p, (size_t)Bp * cap_pos);
+  long long q = 0ll;
+  if (row >= 0) {
+    const size_t o = ((size_t)wg * m + row) * B + b;
+    const double w = mode == 0 ? (double)w1[o] : (double)w2[o] - 2.0 * (double)w1[o];
+    q = llrint(ldexp(w, F - e));
+  }
+  tc_limbs(q, L, uq + ((size_t)wg * L * Bp + b) * cap_pos + mode * n_pos + p, (size_t)Bp * cap_pos);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -717,7 +731,6 @@ static inline int pb_smem_bytes(int nc) { return PB_G * TC_TILE_A + PB_BS * nc *
 
 int rhe_tc_create(rhe_ctx* c) {
   const rhe_config& g = c->cfg;
-  if (g.n_ops != 1) { rhe_set_error("RHE_PATH_TCGEN05 covers one genotype operand (RHE, GENIE); RHE-DOM runs on RHE_PATH_SIMT"); return RHE_ERR_UNSUPPORTED; }
   TcState* s = new TcState();
   const char* envL = getenv("PYRHE_B200_LIMBS");
   s->L = envL ? atoi(envL) : 3;
@@ -794,8 +807,14 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   const uint32_t col_a = (uint32_t)round_up(s->NBa, 32);
   k_tc_pass_a<<<dim3(tiles, splits), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
       s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw, chunk,
-      pow2_cols((int)col_a + 32 * PA_AS), col_a);
+      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0);
   RHE_LAUNCH_CHECK(c);
+  if (c->cfg.n_ops == 2) {   // RHE-DOM: the same pass over the [g == 2] indicator operand
+    k_tc_pass_a<<<dim3(tiles, splits), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
+        s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq,
+        c->t_raw + (size_t)m * c->R1, chunk, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1);
+    RHE_LAUNCH_CHECK(c);
+  }
   return RHE_OK;
 }
 
@@ -820,7 +839,12 @@ static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows,
   b.n_pos = pstart[K];
   const int n_alloc = b.n_pos > 0 ? b.n_pos : 128;
   RHE_CUDA(cudaMalloc((void**)&b.pos_rows, sizeof(int32_t) * n_alloc));
-  RHE_CUDA(cudaMalloc((void**)&b.stage_info, sizeof(int32_t) * (n_alloc / 128)));
+  const int n_modes = c->cfg.n_ops;                  // RHE-DOM runs the position list twice (count, then [g == 2] operand)
+  {
+    const size_t one = info.size();
+    for (int mo = 1; mo < n_modes; ++mo) for (size_t i = 0; i < one; ++i) info.push_back(info[i]);
+  }
+  RHE_CUDA(cudaMalloc((void**)&b.stage_info, sizeof(int32_t) * (n_alloc / 128) * n_modes));
   RHE_CUDA(cudaMalloc((void**)&b.bin_count, sizeof(int32_t) * K));
   int32_t* d_pstart = nullptr;
   RHE_CUDA(cudaMalloc((void**)&d_pstart, sizeof(int32_t) * (K + 1)));
@@ -845,13 +869,13 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   TcBlockMeta* meta = nullptr;
   int rc = tc_block_meta(c, s, m, bin_rows, bin_off, bin_off_host, st, &meta);
   if (rc) return rc;
-  const int n_pos = meta->n_pos;
-  if (n_pos / 128 > PB_MAX_STAGES) { rhe_set_error("RHE_PATH_TCGEN05: block has %d bin-sorted positions (max %d)", n_pos, PB_MAX_STAGES * 128); return RHE_ERR_UNSUPPORTED; }
-  if (n_pos > s->cap_pos) {
+  const int n_pos = meta->n_pos, n_modes = g.n_ops;
+  if (n_modes * n_pos / 128 > PB_MAX_STAGES) { rhe_set_error("RHE_PATH_TCGEN05: block has %d bin-sorted positions (max %d)", n_pos, PB_MAX_STAGES * 128); return RHE_ERR_UNSUPPORTED; }
+  if (n_modes * n_pos > s->cap_pos) {
     RHE_CUDA(cudaStreamSynchronize(st));
     if (s->uq) cudaFree(s->uq);
     if (s->pos_meta) cudaFree(s->pos_meta);
-    s->cap_pos = round_up(n_pos + n_pos / 8, 128);
+    s->cap_pos = round_up(n_modes * (n_pos + n_pos / 8), 128);
     RHE_CUDA(cudaMalloc((void**)&s->pos_meta, sizeof(int32_t) * s->cap_pos));
     RHE_CUDA(cudaMalloc((void**)&s->uq, (size_t)s->NCb * s->cap_pos));
     RHE_CUDA(cudaMemset(s->uq, 0, (size_t)s->NCb * s->cap_pos));
@@ -859,20 +883,21 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
     if (rc) return rc;
   }
   if (n_pos > 0) {
-    k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B * c->n_groups, 256), 256, 0, st>>>(
-        c->w1, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, B, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill, s->pos_meta);
+    k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B * c->n_groups * n_modes, 256), 256, 0, st>>>(
+        c->w1, c->w2, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, n_modes, B, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill,
+        s->pos_meta);
     RHE_LAUNCH_CHECK(c);
   }
   const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
   const int smem = pb_smem_bytes(s->NCb);
   if (s->MT == 2)
-    k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, s->pos_meta,
+    k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
   else
-    k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_pos / 128, s->pos_meta,
+    k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }

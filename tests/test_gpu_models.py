@@ -87,5 +87,7 @@ def test_genie_g_and_gxe_models_run_and_are_consistent(tmp_path):
         res = m(trait=0)
         T, _ = m.setup_lhs_rhs_jackknife(m.num_jack, None)
         E = m.num_estimates
-        np.testing.assert_allclose(T[:E, :E], T_full[:E, :E], rtol=1e-9)
+        # the fixed-point scale of the pass-B weights is shared by the weight groups, so the G rows differ
+        # at quantisation level (2^-22 of the column maximum) between the three models
+        np.testing.assert_allclose(T[:E, :E], T_full[:E, :E], rtol=1e-6)
         assert np.all(np.isfinite(res["sigma_ests_total"]))

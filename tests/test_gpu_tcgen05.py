@@ -10,7 +10,7 @@ from test_gpu_parity import make_engine, plan_for, solve_all
 pytestmark = pytest.mark.gpu
 TC = 1
 RHE_CASES = ["rhe_cov_binary", "rhe_nocov_mean", "rhe_overlap", "rhe_one_block", "rhe_example_shape",
-             "genie_full_cov", "genie_full_nocov"]
+             "genie_full_cov", "genie_full_nocov", "dom_cov", "dom_nocov"]
 
 
 @pytest.mark.parametrize("name", RHE_CASES)
