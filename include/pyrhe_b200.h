@@ -100,12 +100,6 @@ int rhe_block_stats(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
 int rhe_decode_block(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
                      int32_t apply_impute, int8_t* out_dev, void* stream);
 
-/* Optional: run the statistics + imputation-parameter pass of a block ahead of time on `stream` (a side
- * stream), so that this HBM-bound pass overlaps the tensor passes of the previous block.  The next
- * rhe_block_accumulate call for the same `bed_dev` waits on it (stream-ordered, no host sync).  At most two
- * prefetches may be outstanding; the caller orders the side stream after the block that last used the slot. */
-int rhe_block_prefetch_stats(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps, void* stream);
-
 /* rhe.py:13-22 / rhe_dom.py:43-68 / genie.py:46-82 for ONE jackknife block:
  *   bin_rows_dev     int32 [bin_offsets[K]]  block-local SNP rows of every bin, concatenated
  *   bin_offsets_host int32 [K + 1]           (host memory)

@@ -575,14 +575,10 @@ extern "C" int rhe_ctx_create(rhe_ctx** out, const rhe_config* cfg) {
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   alloc((void**)&c->colsum, sizeof(double) * c->R1);
-  for (auto& sl : c->slots) {
-    alloc((void**)&sl.counts, sizeof(int32_t) * 4 * m);
-    alloc((void**)&sl.fill, m);
-    alloc((void**)&sl.mu, sizeof(double) * m);
-    alloc((void**)&sl.f2, sizeof(double) * m);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming);
-  }
-  c->counts = c->slots[0].counts; c->fill = c->slots[0].fill; c->mu = c->slots[0].mu; c->f2 = c->slots[0].f2;
+  alloc((void**)&c->counts, sizeof(int32_t) * 4 * m);
+  alloc((void**)&c->fill, m);
+  alloc((void**)&c->mu, sizeof(double) * m);
+  alloc((void**)&c->f2, sizeof(double) * m);
   alloc((void**)&c->t_raw, sizeof(double) * cfg->n_ops * m * c->R1);
   alloc((void**)&c->t_std, sizeof(double) * c->n_groups * m * Rs);
   alloc((void**)&c->w1, sizeof(float) * c->n_groups * m * B);
@@ -610,12 +606,7 @@ extern "C" int rhe_ctx_destroy(rhe_ctx* c) {
   if (c->tc) rhe_tc_destroy(c);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->off_cache) cudaFree(e.dev);
-  for (auto& sl : c->slots) {
-    void* sp[] = {sl.counts, sl.fill, sl.mu, sl.f2};
-    for (void* p : sp) if (p) cudaFree(p);
-    if (sl.ready) cudaEventDestroy(sl.ready);
-  }
-  void* ptrs[] = {c->colsum, c->t_raw, c->t_std, c->w1, c->w2, c->shiftv, c->cs, c->bin_off};
+  void* ptrs[] = {c->colsum, c->counts, c->fill, c->mu, c->f2, c->t_raw, c->t_std, c->w1, c->w2, c->shiftv, c->cs, c->bin_off};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete c;
   return RHE_OK;
@@ -703,42 +694,6 @@ static void launch_pass_b(rhe_ctx* c, dim3 grid, cudaStream_t st, const uint8_t*
                                      rows, off, c->fill, c->w1, c->w2, c->cs, c->rowscale, P_out, S_accum);
 }
 
-static void use_slot(rhe_ctx* c, int i) {
-  c->counts = c->slots[i].counts; c->fill = c->slots[i].fill; c->mu = c->slots[i].mu; c->f2 = c->slots[i].f2;
-}
-
-extern "C" int rhe_block_prefetch_stats(rhe_ctx* c, const uint8_t* bed, int32_t m, void* stream) {
-  int rc = check_block(c, bed, m, "rhe_block_prefetch_stats");
-  if (rc) return rc;
-  const rhe_config& g = c->cfg;
-  if (g.impute_binary && (!c->uniforms || c->n_uniforms < m)) {
-    rhe_set_error("binary imputation needs rhe_set_uniforms with >= %d values", m);
-    return RHE_ERR_STATE;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  rhe_ctx::ParamSlot& sl = c->slots[c->next_slot];
-  c->next_slot ^= 1;
-  k_stats_params<<<rhe_div_up(m, 8), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
-                                                   sl.counts, sl.fill, sl.mu, sl.f2, nullptr, 0, 0, nullptr, 0, nullptr, 0,
-                                                   nullptr, 0);
-  RHE_LAUNCH_CHECK(c);
-  RHE_CUDA(cudaEventRecord(sl.ready, st));
-  sl.key = bed;
-  sl.m = m;
-  sl.pending = true;
-  return RHE_OK;
-}
-
-// Zero everything a block accumulates into (the fused front end does this itself when the statistics are not prefetched).
-__global__ void k_zero_block(double* __restrict__ t_raw, size_t n_t, double* __restrict__ cs, int n_cs,
-                             double* __restrict__ gram, int n_gram, unsigned int* __restrict__ wmax, int n_wmax) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  for (size_t i = i0; i < n_t; i += stride) t_raw[i] = 0.0;
-  for (size_t i = i0; i < (size_t)n_cs; i += stride) cs[i] = 0.0;
-  for (size_t i = i0; i < (size_t)n_gram; i += stride) gram[i] = 0.0;
-  for (size_t i = i0; i < (size_t)n_wmax; i += stride) wmax[i] = 0u;
-}
-
 extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, const int32_t* bin_rows,
                                     const int32_t* bin_off_host, float* P_out, float* S_accum, double* gram_out,
                                     void* stream) {
@@ -771,22 +726,9 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
     s_off_dev = e.dev;
   }
   unsigned int* wmax = g.kernel_path == RHE_PATH_TCGEN05 ? rhe_tc_wmax(c) : nullptr;
-  int pre = -1;
-  for (int i = 0; i < 2; ++i)
-    if (c->slots[i].pending && c->slots[i].key == bed && c->slots[i].m == m) pre = i;
-  if (pre >= 0) {   // statistics were prefetched on a side stream: wait for them, zero the accumulators here
-    c->slots[pre].pending = false;
-    use_slot(c, pre);
-    RHE_CUDA(cudaStreamWaitEvent(st, c->slots[pre].ready, 0));
-    k_zero_block<<<148, 256, 0, st>>>(c->t_raw, (size_t)g.n_ops * m * c->R1, c->cs, c->E_reg * B, gram_out,
-                                      c->E_reg * Rs * Rs, wmax, wmax ? B : 0);
-  } else {
-    use_slot(c, c->next_slot);
-    c->next_slot ^= 1;
-    k_stats_params<<<rhe_div_up(m, 8), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
-                                                     c->counts, c->fill, c->mu, c->f2, c->t_raw, c->R1, g.n_ops, c->cs,
-                                                     c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? B : 0);
-  }
+  k_stats_params<<<rhe_div_up(m, 8), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
+                                                   c->counts, c->fill, c->mu, c->f2, c->t_raw, c->R1, g.n_ops, c->cs,
+                                                   c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? B : 0);
   RHE_LAUNCH_CHECK(c);
   if (c->timing) RHE_CUDA(cudaEventRecord(tev[1], st));
 

@@ -37,11 +37,6 @@ struct rhe_ctx {
   // device copies of the per-block bin offsets, keyed by the caller's bin_rows pointer (annotation metadata)
   struct OffEntry { const int32_t* key; std::vector<int32_t> host; int32_t* dev; };
   std::vector<OffEntry> off_cache;
-  // double-buffered per-SNP parameters so that the popcount pass of the NEXT block (rhe_block_prefetch_stats, on a
-  // side stream) overlaps the tensor passes of the current one; counts/fill/mu/f2 point at the slot in use
-  struct ParamSlot { int32_t* counts; uint8_t* fill; double* mu; double* f2; const uint8_t* key; int m; cudaEvent_t ready; bool pending; };
-  ParamSlot slots[2] = {};
-  int next_slot = 0;
 };
 
 void rhe_set_error(const char* fmt, ...);

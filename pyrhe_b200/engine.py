@@ -108,7 +108,6 @@ class RheEngine:
             cur += self.ranges[j][1] - self.ranges[j][0]
         self.m_own = cur
         self.nxe_S = None
-        self._aux = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -206,31 +205,10 @@ class RheEngine:
             P_all = None
             if self.store_partials:
                 P_all = torch.zeros((max(len(self.own), 1), E, B, Np), dtype=torch.float32, device=dev)
-            # the HBM-bound popcount pass of block j+2 runs on a side stream underneath the tensor passes of
-            # block j+1 (double-buffered parameter slots inside the library)
-            if self._aux is None:
-                self._aux = torch.cuda.Stream(dev)
-            aux = self._aux
-            aux.wait_stream(cur)
-
-            def prefetch(j):
-                if upload_events is not None:
-                    aux.wait_event(upload_events[j])
-                rows, m = self.block_view(j)
-                _lib.check(self.lib.rhe_block_prefetch_stats(self._ctx, C.c_void_p(rows.data_ptr()), m,
-                                                             C.c_void_p(aux.cuda_stream)))
-
-            for j in self.own[:2]:
-                prefetch(j)
             for jl, j in enumerate(self.own):
                 if upload_events is not None:
                     cur.wait_event(upload_events[j])
                 self._accumulate(j, P_all[jl] if self.store_partials else None, S, G_blk[j])
-                if jl + 2 < len(self.own):
-                    done = torch.cuda.Event()
-                    done.record(cur)
-                    aux.wait_event(done)
-                    prefetch(self.own[jl + 2])
             if self.world > 1:
                 allreduce_sum([S, G_blk], self.pg)
             if plan.has_nxe:
