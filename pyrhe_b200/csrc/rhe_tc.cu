@@ -440,11 +440,12 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 #define PB_THREADS (32 * (PB_DW + 1 + PB_G))   // decode warps, one TMA warp, one MMA-issue warp per group
 #define PB_BS 4                   // smem ring of Uq tiles (TMA)
 #define PB_PKG 4                  // per-group cp.async ring depth (in the group's own stages)
+#define PB_AS 2                   // shared-memory A slots per decode group (decode of tile u+1 overlaps the MMAs of tile u)
 
 #define PB_MAX_STAGES 512
 #define PB_MAX_KB 1024            // K * B entries of the per-bin mean term staged in shared memory
 struct PbSmem {
-  uint64_t full_a[PB_G], empty_a[PB_G], full_b[PB_BS], empty_b[PB_BS], acc_full;
+  uint64_t full_a[PB_G * PB_AS], empty_a[PB_G * PB_AS], full_b[PB_BS], empty_b[PB_BS], acc_full;
   uint32_t tmem_base;
   int32_t info[PB_MAX_STAGES];    // stage_info of the block
   double cs[PB_MAX_KB];           // per-(bin, column) mean term
@@ -464,7 +465,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileA = smem;
-  uint8_t* tileB = tileA + PB_G * TC_TILE_A;
+  uint8_t* tileB = tileA + PB_G * PB_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
   uint8_t* packed = tileB + PB_BS * tileB_bytes;     // [group][PB_PKG][2 chunks][128 threads][16 B]
   PbSmem* sm = reinterpret_cast<PbSmem*>(packed + PB_G * PB_PKG * 4096);
@@ -474,7 +475,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   const int i0 = blockIdx.x * (MT * 128);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PB_G; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
+    for (int s = 0; s < PB_G * PB_AS; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
     for (int s = 0; s < PB_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], MT); }
     mbar_init(&sm->acc_full, PB_G);
     fence_barrier_init();
@@ -503,7 +504,6 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const int par = g / MT, q = g % MT;
     const uint8_t* base = bed + (i0 >> 2) + q * 32;
     const uint32_t ring = packed_s + g * (PB_PKG * 4096) + t * 16;
-    const uint32_t tile = tileA_s + g * TC_TILE_A;
     const int n_own = n_stage > par ? (n_stage - par + SI - 1) / SI : 0;   // stages st = par + SI * u
     // pos_meta[p] = SNP row | fill << 24 (or -1 for padding); loaded one iteration before it is needed so
     // that the dependent address never stalls the (in-order) decode thread
@@ -546,12 +546,13 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
           const uint32_t slot = ring + (u % PB_PKG) * 4096;
           const uint4 lo = lds128(slot), hi = lds128(slot + 2048);
           PROF_ADD(1);
-          mbar_wait(&sm->empty_a[g], (u & 1) ^ 1);
+          const int a = g * PB_AS + (u % PB_AS);       // this group's slots alternate; use index u / PB_AS
+          mbar_wait(&sm->empty_a[a], ((u / PB_AS) & 1) ^ 1);
           PROF_ADD(2);
-          tc_store_row(tile, t, lo, hi, tab);
+          tc_store_row(tileA_s + a * TC_TILE_A, t, lo, hi, tab);
           PROF_ADD(3);
           fence_proxy_async();
-          mbar_arrive(&sm->full_a[g]);
+          mbar_arrive(&sm->full_a[a]);
           PROF_ADD(4);
         }
       }
@@ -603,7 +604,6 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       const int g = warp - (PB_DW + 1);
       const int par = g / MT, q = g % MT;
       const uint32_t idesc = idesc_i8(128, NC, a_major);   // A is MN-major: 128 individuals contiguous per SNP row
-      const uint64_t adesc = smem_desc_sw128(tileA_s + g * TC_TILE_A, TC_TILE_A, 1024);
       const uint32_t tileB_s = smem_u32(tileB);
       PROF_T0();
 #ifdef RHE_TC_PROF
@@ -618,13 +618,15 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
         PROF_ADD(6);
         mbar_wait(&sm->full_b[b], (st / PB_BS) & 1);
         PROF_ADD(7);
-        mbar_wait(&sm->full_a[g], u & 1);
+        const int a = g * PB_AS + (u % PB_AS);
+        const uint64_t adesc = smem_desc_sw128(tileA_s + a * TC_TILE_A, TC_TILE_A, 1024);
+        mbar_wait(&sm->full_a[a], (u / PB_AS) & 1);
         PROF_ADD(8);
         tc_fence_after();
         const uint32_t dcol = tmem + (uint32_t)((k * MT + q) * NC);
         for (int j = 0; j < ksteps; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
           umma_i8(dcol, desc_advance(adesc, j * 4096), desc_advance(bdesc, j * 32), idesc, 1u);
-        umma_commit(&sm->empty_a[g]);
+        umma_commit(&sm->empty_a[a]);
         umma_commit(&sm->empty_b[b]);
         PROF_ADD(9);
       }
@@ -727,7 +729,7 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 static inline int pa_smem_bytes(int nb) { return PA_BS * nb * 128 + PA_PK * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
-static inline int pb_smem_bytes(int nc) { return PB_G * TC_TILE_A + PB_BS * nc * 128 + PB_G * PB_PKG * 4096 + (int)sizeof(PbSmem) + 1024; }
+static inline int pb_smem_bytes(int nc) { return PB_G * PB_AS * TC_TILE_A + PB_BS * nc * 128 + PB_G * PB_PKG * 4096 + (int)sizeof(PbSmem) + 1024; }
 
 int rhe_tc_create(rhe_ctx* c) {
   const rhe_config& g = c->cfg;
