@@ -460,14 +460,14 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
             const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
-            uint32_t tmem_cols, int a_major, int kcap) {
+            uint32_t tmem_cols, int a_major, int kcap, int bs) {
   constexpr int SI = PB_G / MT;                      // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileA = smem;
   uint8_t* tileB = tileA + PB_G * PB_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
-  uint8_t* packed = tileB + PB_BS * tileB_bytes;     // [group][PB_PKG][2 chunks][128 threads][16 B]
+  uint8_t* packed = tileB + bs * tileB_bytes;     // [group][PB_PKG][2 chunks][128 threads][16 B]
   PbSmem* sm = reinterpret_cast<PbSmem*>(packed + PB_G * PB_PKG * 4096);
   const uint32_t tileA_s = smem_u32(tileA), packed_s = smem_u32(packed);
 
@@ -592,7 +592,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   } else if (warp == PB_DW) {
     if (lane == 0) {
       for (int st = 0; st < n_stage; ++st) {
-        const int b = st % PB_BS, use = st / PB_BS;
+        const int b = st % bs, use = st / bs;
         mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
         mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
         tma_load_2d(tileB + b * tileB_bytes, &tm_uq, &sm->full_b[b], st * 128, 0);
@@ -611,12 +611,12 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
 #endif
       int u = 0;
       for (int st = par; st < n_stage; st += SI, ++u) {
-        const int b = st % PB_BS;
+        const int b = st % bs;
         const int info = sm->info[st];
         const int k = info & 255, ksteps = min(info >> 16, kcap);
         const uint64_t bdesc = smem_desc_sw128(tileB_s + b * tileB_bytes, 16, 1024);
         PROF_ADD(6);
-        mbar_wait(&sm->full_b[b], (st / PB_BS) & 1);
+        mbar_wait(&sm->full_b[b], (st / bs) & 1);
         PROF_ADD(7);
         const int a = g * PB_AS + (u % PB_AS);
         const uint64_t adesc = smem_desc_sw128(tileA_s + a * TC_TILE_A, TC_TILE_A, 1024);
@@ -729,7 +729,9 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 static inline int pa_smem_bytes(int nb) { return PA_BS * nb * 128 + PA_PK * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
-static inline int pb_smem_bytes(int nc) { return PB_G * PB_AS * TC_TILE_A + PB_BS * nc * 128 + PB_G * PB_PKG * 4096 + (int)sizeof(PbSmem) + 1024; }
+static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_G * PB_PKG * 4096 + (int)sizeof(PbSmem) + 1024; }
+// Uq ring depth: 4 when it fits next to the A slots and packed rings in 227 KB, else 2
+static inline int pb_ring(int nc) { return pb_smem_bytes(nc, 4) <= 232448 ? 4 : 2; }
 
 int rhe_tc_create(rhe_ctx* c) {
   const rhe_config& g = c->cfg;
@@ -766,8 +768,8 @@ int rhe_tc_create(rhe_ctx* c) {
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa)));
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb)));
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb)));
+  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb))));
+  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb))));
   return RHE_OK;
 }
 
@@ -891,15 +893,15 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
     RHE_LAUNCH_CHECK(c);
   }
   const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
-  const int smem = pb_smem_bytes(s->NCb);
+  const int bs = pb_ring(s->NCb), smem = pb_smem_bytes(s->NCb, bs);
   if (s->MT == 2)
     k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs);
   else
     k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
