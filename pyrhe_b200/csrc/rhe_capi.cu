@@ -53,6 +53,16 @@ __device__ __forceinline__ void rhe_popc_word(uint32_t x, uint32_t keep, int& n1
   nm += __popc(~hi & lo & k);
 }
 
+// Cheaper variant for the fused front end: only S = n1 + 2 n2 and n_miss are needed (plus n2 for RHE-DOM).
+// popc(x & keep) = (n1 + n2) + (n2 + n_miss), so S = popc(x & keep) - n_miss: two POPC per word instead of three.
+template <bool NEED_N2>
+__device__ __forceinline__ void rhe_popc_word2(uint32_t x, uint32_t keep, int& bits, int& nm, int& n2) {
+  const uint32_t t = x & keep, sh = t >> 1;
+  bits += __popc(t);
+  nm += __popc(t & ~sh & 0x55555555u);
+  if (NEED_N2) n2 += __popc(t & sh & 0x55555555u);
+}
+
 // Masked popcount statistics: one warp per SNP row (base.py:277-289 needs the observed mean).
 __global__ void __launch_bounds__(256)
 k_stats(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t* __restrict__ keep2,
@@ -131,30 +141,40 @@ k_stats_params(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t
   for (int op = 0; op < n_ops; ++op)
     for (int c = lane; c < t_cols; c += 32) t_raw[((size_t)op * m + s) * t_cols + c] = 0.0;
   const uint32_t* row = reinterpret_cast<const uint32_t*>(bed + (size_t)s * pitch);
-  int n1 = 0, n2 = 0, nm = 0;
+  int bits = 0, n2 = 0, nm = 0;
   {
     const uint4* row4 = reinterpret_cast<const uint4*>(row);
     const uint4* keep4 = reinterpret_cast<const uint4*>(keep2);
     const int n4 = pitch / 16;                      // pitch is a multiple of 128 bytes
+    if (n_ops == 2) {
 #pragma unroll 4
-    for (int w = lane; w < n4; w += 32) {
-      const uint4 x = rhe_ldg_stream(row4 + w), k = __ldg(keep4 + w);
-      rhe_popc_word(x.x, k.x, n1, n2, nm);
-      rhe_popc_word(x.y, k.y, n1, n2, nm);
-      rhe_popc_word(x.z, k.z, n1, n2, nm);
-      rhe_popc_word(x.w, k.w, n1, n2, nm);
+      for (int w = lane; w < n4; w += 32) {
+        const uint4 x = rhe_ldg_stream(row4 + w), k = __ldg(keep4 + w);
+        rhe_popc_word2<true>(x.x, k.x, bits, nm, n2); rhe_popc_word2<true>(x.y, k.y, bits, nm, n2);
+        rhe_popc_word2<true>(x.z, k.z, bits, nm, n2); rhe_popc_word2<true>(x.w, k.w, bits, nm, n2);
+      }
+    } else {
+#pragma unroll 4
+      for (int w = lane; w < n4; w += 32) {
+        const uint4 x = rhe_ldg_stream(row4 + w), k = __ldg(keep4 + w);
+        rhe_popc_word2<false>(x.x, k.x, bits, nm, n2); rhe_popc_word2<false>(x.y, k.y, bits, nm, n2);
+        rhe_popc_word2<false>(x.z, k.z, bits, nm, n2); rhe_popc_word2<false>(x.w, k.w, bits, nm, n2);
+      }
     }
   }
   for (int o = 16; o; o >>= 1) {
-    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    bits += __shfl_xor_sync(0xffffffffu, bits, o);
     n2 += __shfl_xor_sync(0xffffffffu, n2, o);
     nm += __shfl_xor_sync(0xffffffffu, nm, o);
   }
+  const int ssum = bits - nm;                        // n1 + 2 n2 over kept individuals
   if (lane == 0) {
-    reinterpret_cast<int4*>(counts)[s] = make_int4(n_kept - n1 - n2 - nm, n1, n2, nm);
+    // n1 / n0 are filled in only when n2 was counted (RHE-DOM); the exact four-way counts come from k_stats
+    reinterpret_cast<int4*>(counts)[s] = make_int4(n_kept - (ssum - n2) - nm, ssum - 2 * n2, n2, nm);
     int f = 0;
+    int n1 = ssum - 2 * n2;
     if (binary) {   // same float32 replay as k_snp_params
-      float mean32 = (float)((double)(n1 + 2 * n2) / (double)(n_kept - nm));
+      float mean32 = (float)((double)ssum / (double)(n_kept - nm));
       float p = __fmul_rn(mean32, 0.5f);
       float om = __fsub_rn(1.0f, p);
       float d0 = __fmul_rn(om, om);
@@ -165,8 +185,8 @@ k_stats_params(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t
     if (f == 1) n1 += nm;
     if (f == 2) n2 += nm;
     fill[s] = (uint8_t)f;
-    mu[s] = (double)(n1 + 2 * n2) / (double)n_kept;
-    f2[s] = (double)n2 / (double)n_kept;
+    mu[s] = (double)(n1 + 2 * n2) / (double)n_kept;   // = (S + fill * n_miss) / N, valid without n2 as well
+    f2[s] = (double)n2 / (double)n_kept;               // used by the dominance operand only (n2 counted then)
   }
 }
 
