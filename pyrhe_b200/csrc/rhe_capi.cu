@@ -518,18 +518,28 @@ k_loo_gram_small(const float* __restrict__ S, const float* __restrict__ P, int64
   double acc[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p) acc[p] = 0.0;
-  for (int64_t g = blockIdx.x * (int64_t)256 + threadIdx.x; g < len; g += (int64_t)gridDim.x * 256) {
-    double d[E];
+  // two adjacent positions per thread and iteration (8-byte loads; `len` is a multiple of 512)
+  const int64_t len2 = len >> 1;
+  const float2* S2 = reinterpret_cast<const float2*>(S);
+  const float2* P2 = reinterpret_cast<const float2*>(P);
+  for (int64_t g = blockIdx.x * (int64_t)256 + threadIdx.x; g < len2; g += (int64_t)gridDim.x * 256) {
+    double d0[E], d1[E];
 #pragma unroll
     for (int a = 0; a < E; ++a) {
-      float v = __ldg(S + (size_t)a * len + g);
-      d[a] = P ? (double)v - (double)__ldg(P + (size_t)a * len + g) : (double)v;
+      const float2 v = __ldg(S2 + (size_t)a * len2 + g);
+      d0[a] = (double)v.x;
+      d1[a] = (double)v.y;
+      if (P) {
+        const float2 w = __ldg(P2 + (size_t)a * len2 + g);
+        d0[a] -= (double)w.x;
+        d1[a] -= (double)w.y;
+      }
     }
     int p = 0;
 #pragma unroll
     for (int a = 0; a < E; ++a)
 #pragma unroll
-      for (int c = a; c < E; ++c) { acc[p] = fma(d[a], d[c], acc[p]); ++p; }
+      for (int c = a; c < E; ++c) { acc[p] = fma(d0[a], d0[c], fma(d1[a], d1[c], acc[p])); ++p; }
   }
   __shared__ double red[8][NP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -553,7 +563,7 @@ k_loo_gram_small(const float* __restrict__ S, const float* __restrict__ P, int64
 
 template <int E>
 static void launch_loo_small(const float* S, const float* P, int64_t len, double* out, cudaStream_t st) {
-  int64_t blocks = (len + 255) / 256;
+  int64_t blocks = (len / 2 + 255) / 256;
   int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
   k_loo_gram_small<E><<<grid, 256, 0, st>>>(S, P, len, out);
 }
@@ -777,7 +787,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
                                                            c->mu, c->f2, c->t_std, c->w1, c->w2, c->shiftv, wmax);
     RHE_LAUNCH_CHECK(c);
   }
-  k_bin_gram<<<dim3(c->E_reg, 8), 256, 0, st>>>(m, Rs, B, K, bin_rows, s_off_dev, c->t_std, c->shiftv, gram_out, c->cs);
+  k_bin_gram<<<dim3(c->E_reg, 32), 256, 0, st>>>(m, Rs, B, K, bin_rows, s_off_dev, c->t_std, c->shiftv, gram_out, c->cs);
   RHE_LAUNCH_CHECK(c);
   if (c->timing) RHE_CUDA(cudaEventRecord(tev[3], st));
   // ---- pass B
@@ -842,7 +852,8 @@ extern "C" int rhe_loo_gram(rhe_ctx* c, const float* S, const float* P, int32_t 
   if (n_est < 1 || n_est > GRAM_MAX_E) { rhe_set_error("rhe_loo_gram: n_est %d outside [1, %d]", n_est, GRAM_MAX_E); return RHE_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   RHE_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_est * n_est, st));
-  switch (n_est) {
+  // register-resident kernels for up to 8 estimates (8-byte loads: even length, always true for B * Np)
+  switch (len % 2 == 0 ? n_est : 0) {
     case 1: launch_loo_small<1>(S, P, len, out, st); break;
     case 2: launch_loo_small<2>(S, P, len, out, st); break;
     case 3: launch_loo_small<3>(S, P, len, out, st); break;

@@ -204,7 +204,11 @@ class RheEngine:
             XX = torch.zeros((J + 1, E, E), dtype=torch.float64, device=dev)
             P_all = None
             if self.store_partials:
-                P_all = torch.zeros((max(len(self.own), 1), E, B, Np), dtype=torch.float32, device=dev)
+                # every (estimate, column) row of a block partial is fully written by pass B; only the NxE row
+                # (no genotype contribution) has to be zeroed
+                P_all = torch.empty((max(len(self.own), 1), E, B, Np), dtype=torch.float32, device=dev)
+                if E > E_reg:
+                    P_all[:, E_reg:].zero_()
             for jl, j in enumerate(self.own):
                 if upload_events is not None:
                     cur.wait_event(upload_events[j])
