@@ -32,8 +32,12 @@ WORKLOADS = {
     # BASELINE.json configs[4]: the configuration the metric is quoted on
     "config5": dict(N=500_000, M=1_000_000, J=100, K=8, C=5, B=10, model="rhe"),
     "config2": dict(N=200_000, M=500_000, J=100, K=8, C=5, B=10, model="rhe"),
-    # a few config2-sized blocks: short enough to run under ncu
+    # BASELINE.json configs[2], configs[3] (parity-scale runs of the other two model families)
+    "config3": dict(N=200_000, M=500_000, J=100, K=8, C=5, B=10, model="rhe_dom"),
+    "config4": dict(N=300_000, M=500_000, J=100, K=8, C=5, B=10, model="genie"),
+    # a few config2 / config5 sized blocks: short enough to run under ncu
     "profile": dict(N=200_000, M=20_000, J=4, K=8, C=5, B=10, model="rhe"),
+    "profile5": dict(N=500_000, M=40_000, J=4, K=8, C=5, B=10, model="rhe"),
     "small": dict(N=20_000, M=40_000, J=20, K=8, C=5, B=10, model="rhe"),
 }
 METRIC = "rhe_genotype_throughput"
@@ -159,7 +163,8 @@ def main():
     y = rng.standard_normal((N, 1))
     y -= y.mean()
     plan = PathPlan(model=wl["model"], K=K, B=B, C=Cc, Ty=1)
-    ht, Y_res = host_terms(plan, Z, W, y, None)
+    env = (rng.random(N) < 0.4).astype(np.float64) if wl["model"] == "genie" else None
+    ht, Y_res = host_terms(plan, Z, W, y, env)
     keep = np.ones(N, dtype=bool)
 
     # memory policy: keep every block's partial in HBM when it fits next to the genotypes
@@ -173,7 +178,7 @@ def main():
     store = bytes_geno + bytes_part + 6e9 < free_b
     eng = RheEngine(plan, n_indv=N, keep=keep, annot=annot, num_jack=J, impute="binary", seed=0, device=dev,
                     kernel_path=args.kernel_path, rank=rank, world=world, store_partials=store)
-    eng.set_rhs(Z, W, Y_res)
+    eng.set_rhs(Z, W, Y_res, env)
     eng.alloc_genotypes()
     stream = torch.cuda.current_stream(dev)
     for j in eng.own:                                          # synthetic genotypes generated in HBM
@@ -259,7 +264,7 @@ def main():
         d2h_holder = {}
 
         def step_e2e():
-            eng.set_rhs(Z, W, Y_res)
+            eng.set_rhs(Z, W, Y_res, env)
             events = {}
             for idx, j in enumerate(eng.own):
                 eng.upload_block(j, ring[idx % R], stream=copy_stream)

@@ -44,12 +44,15 @@ def allreduce_sum(tensors, group=None):
 class RheEngine:
     def __init__(self, plan: PathPlan, *, n_indv: int, keep: np.ndarray, annot: np.ndarray, num_jack: int,
                  impute: str = "binary", seed: int = 0, device: Optional[torch.device] = None,
-                 kernel_path: int = _lib.PATH_SIMT, rank: int = 0, world: int = 1,
+                 kernel_path: Optional[int] = None, rank: int = 0, world: int = 1,
                  store_partials: bool = True, process_group=None):
         if not torch.cuda.is_available():
             raise _lib.RheError("pyrhe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.plan = plan
+        if kernel_path is None:      # int8 tcgen05 kernels whenever the layout fits one TMEM allocation
+            kernel_path = _lib.PATH_TCGEN05 if _lib.tcgen05_supported(plan) else _lib.PATH_SIMT
+        self.kernel_path = kernel_path
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rank, self.world, self.pg = rank, world, process_group
         self.store_partials = store_partials

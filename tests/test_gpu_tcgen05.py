@@ -79,3 +79,53 @@ def test_tcgen05_larger_shape_against_simt_and_split_invariance():
     # indexes its uniforms by block-local SNP, base.py:510, so it legitimately depends on J)
     Gt4, Gt2 = res[(TC, 4, "mean")][0]["G_blk"].sum(0), res[(TC, 2, "mean")][0]["G_blk"].sum(0)
     np.testing.assert_allclose(Gt2, Gt4, rtol=1e-9, atol=1e-9 * np.abs(Gt4).max())
+
+
+def test_full_size_block_properties():
+    """BASELINE full size in N (500k individuals, two jackknife blocks of 2 000 SNPs generated on the device):
+    size-independent properties through the C ABI -- tensor path == CUDA-core path, exact repeatability of the
+    integer pass A, and exact linearity in the right-hand sides (scaling Z by a power of two)."""
+    import ctypes as C
+    import torch
+    from pyrhe_b200 import _lib, synth
+    from pyrhe_b200.assemble import PathPlan
+    from pyrhe_b200.engine import RheEngine
+    from pyrhe_b200.hostmath import host_terms
+    rng = np.random.default_rng(11)
+    N, M, K, B, J = 500_000, 4_000, 8, 10, 2
+    annot = synth.random_annot(M, K, rng)
+    Z = rng.standard_normal((N, B))
+    W = rng.standard_normal((N, 5))
+    y = rng.standard_normal((N, 1))
+    y -= y.mean()
+    plan = PathPlan(model="rhe", K=K, B=B, C=5)
+    ht, Y_res = host_terms(plan, Z, W, y, None)
+    lib = _lib.load()
+
+    def run(path, zscale=1.0):
+        eng = RheEngine(plan, n_indv=N, keep=np.ones(N, bool), annot=annot, num_jack=J, impute="binary", seed=3,
+                        kernel_path=path)
+        eng.set_rhs(Z * zscale, W, Y_res)
+        eng.alloc_genotypes()
+        st = torch.cuda.current_stream()
+        for j in eng.own:
+            rows, m = eng.block_view(j)
+            _lib.check(lib.rhe_synth_genotypes(C.c_void_p(rows.data_ptr()), m, eng.pitch, N, eng.ranges[j][0], 99, 0.001,
+                                               C.c_void_p(st.cuda_stream)))
+        pieces = eng.run()
+        S = eng.S.cpu().numpy()
+        eng.close()
+        return pieces, S
+
+    simt, S0 = run(0)
+    tc1, S1 = run(1)
+    tc2, S2 = run(1)
+    tc4, S4 = run(1, zscale=4.0)
+    np.testing.assert_allclose(tc1["XX"], simt["XX"], rtol=2e-6)
+    np.testing.assert_allclose(tc1["G_blk"], simt["G_blk"], rtol=1e-5, atol=1e-6 * np.abs(simt["G_blk"]).max())
+    np.testing.assert_array_equal(tc1["G_blk"], tc2["G_blk"])          # exact integer accumulation: bit-repeatable
+    # Z -> 4 Z: the Z block of the Gram scales by 16, Z x (W, y) by 4, the rest is unchanged -- exactly
+    scale = np.ones(plan.Rs)
+    scale[:B] = 4.0
+    np.testing.assert_array_equal(tc4["G_blk"], tc1["G_blk"] * np.outer(scale, scale))
+    np.testing.assert_allclose(S4, 4.0 * S1, rtol=0, atol=1e-6 * np.abs(S1).max())
