@@ -439,7 +439,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 #define PB_DW (4 * PB_G)
 #define PB_THREADS (32 * (PB_DW + 1 + PB_G))   // decode warps, one TMA warp, one MMA-issue warp per group
 #define PB_BS 4                   // smem ring of Uq tiles (TMA)
-#define PB_PKG 4                  // per-group cp.async ring depth (in the group's own stages)
+#define PB_PKG 3                  // per-group cp.async ring depth (in the group's own stages)
 #define PB_AS 2                   // shared-memory A slots per decode group (decode of tile u+1 overlaps the MMAs of tile u)
 
 #define PB_MAX_STAGES 512
@@ -730,8 +730,9 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 static inline int pa_smem_bytes(int nb) { return PA_BS * nb * 128 + PA_PK * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
 static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_G * PB_PKG * 4096 + (int)sizeof(PbSmem) + 1024; }
-// Uq ring depth: 4 when it fits next to the A slots and packed rings in 227 KB, else 2
-static inline int pb_ring(int nc) { return pb_smem_bytes(nc, 4) <= 232448 ? 4 : 2; }
+// The Uq ring depth must be a multiple of the stage interleave (4 / MT): consecutive uses of one slot are then
+// consumed by the same issuer, which keeps every waiter within one mbarrier phase of its barrier.
+static inline int pb_ring(int) { return PB_BS; }
 
 int rhe_tc_create(rhe_ctx* c) {
   const rhe_config& g = c->cfg;
@@ -745,7 +746,7 @@ int rhe_tc_create(rhe_ctx* c) {
   s->Bp = round_up(g.n_vec, 2);
   s->NCb = round_up(c->n_groups * s->L * s->Bp, 16);   // weight groups (RHS sets) are stacked along N
   s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
-  if (s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || g.n_vec > 64) {
+  if (pb_smem_bytes(s->NCb, PB_BS) > 232448 || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || g.n_vec > 64) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     delete s;
     return RHE_ERR_UNSUPPORTED;

@@ -121,7 +121,7 @@ def test_full_size_block_properties():
     tc1, S1 = run(1)
     tc2, S2 = run(1)
     tc4, S4 = run(1, zscale=4.0)
-    np.testing.assert_allclose(tc1["XX"], simt["XX"], rtol=2e-6)
+    np.testing.assert_allclose(tc1["XX"], simt["XX"], rtol=2e-6, atol=1e-8 * np.abs(simt["XX"]).max())
     np.testing.assert_allclose(tc1["G_blk"], simt["G_blk"], rtol=1e-5, atol=1e-6 * np.abs(simt["G_blk"]).max())
     np.testing.assert_array_equal(tc1["G_blk"], tc2["G_blk"])          # exact integer accumulation: bit-repeatable
     # Z -> 4 Z: the Z block of the Gram scales by 16, Z x (W, y) by 4, the rest is unchanged -- exactly
@@ -129,3 +129,37 @@ def test_full_size_block_properties():
     scale[:B] = 4.0
     np.testing.assert_array_equal(tc4["G_blk"], tc1["G_blk"] * np.outer(scale, scale))
     np.testing.assert_allclose(S4, 4.0 * S1, rtol=0, atol=1e-6 * np.abs(S1).max())
+
+
+@pytest.mark.parametrize("model", ["rhe_dom", "genie"])
+def test_tcgen05_eight_bins_wide_weight_groups(model):
+    """K = 8, B = 10 with two weight groups: the accumulators of all bins only fit TMEM with one M-tile per CTA
+    (the MT = 1 kernel variant).  Tensor path against the CUDA-core path."""
+    from pyrhe_b200 import synth
+    from pyrhe_b200.assemble import PathPlan
+    from pyrhe_b200.engine import RheEngine
+    from pyrhe_b200.hostmath import host_terms
+    rng = np.random.default_rng(21)
+    N, M, K, B, J = 1_500, 2_400, 8, 10, 3
+    packed = synth.pack_counts(synth.random_counts(N, M, rng, missing_rate=0.003))
+    annot = synth.random_annot(M, K, rng)
+    Z = rng.standard_normal((N, B))
+    W = rng.standard_normal((N, 2))
+    y = rng.standard_normal((N, 1))
+    y -= y.mean()
+    env = (rng.random(N) < 0.4).astype(np.float64) if model == "genie" else None
+    plan = PathPlan(model=model, K=K, B=B, C=2)
+    ht, Y_res = host_terms(plan, Z, W, y, env)
+    out = {}
+    for path in (0, TC):
+        eng = RheEngine(plan, n_indv=N, keep=np.ones(N, bool), annot=annot, num_jack=J, impute="binary", seed=2,
+                        kernel_path=path)
+        eng.set_rhs(Z, W, Y_res, env)
+        eng.load_genotypes(packed)
+        pieces = eng.run()
+        out[path] = (pieces, eng.S.cpu().numpy().astype(np.float64))
+        eng.close()
+    a, b = out[0], out[TC]
+    np.testing.assert_allclose(b[1], a[1], rtol=0, atol=3e-6 * np.abs(a[1]).max())
+    np.testing.assert_allclose(b[0]["XX"], a[0]["XX"], rtol=1e-5, atol=1e-7 * np.abs(a[0]["XX"]).max())
+    np.testing.assert_allclose(b[0]["G_blk"], a[0]["G_blk"], rtol=1e-5, atol=1e-6 * np.abs(a[0]["G_blk"]).max())
