@@ -84,7 +84,7 @@ def test_tcgen05_larger_shape_against_simt_and_split_invariance():
 def test_full_size_block_properties():
     """BASELINE full size in N (500k individuals, two jackknife blocks of 2 000 SNPs generated on the device):
     size-independent properties through the C ABI -- tensor path == CUDA-core path, exact repeatability of the
-    integer pass A, and exact linearity in the right-hand sides (scaling Z by a power of two)."""
+    integer pass A, and linearity in the right-hand sides (scaling Z by a power of two changes nothing but exponents)."""
     import ctypes as C
     import torch
     from pyrhe_b200 import _lib, synth
@@ -123,11 +123,14 @@ def test_full_size_block_properties():
     tc4, S4 = run(1, zscale=4.0)
     np.testing.assert_allclose(tc1["XX"], simt["XX"], rtol=2e-6, atol=1e-8 * np.abs(simt["XX"]).max())
     np.testing.assert_allclose(tc1["G_blk"], simt["G_blk"], rtol=1e-5, atol=1e-6 * np.abs(simt["G_blk"]).max())
-    np.testing.assert_array_equal(tc1["G_blk"], tc2["G_blk"])          # exact integer accumulation: bit-repeatable
+    # pass A is exact integer arithmetic; the per-bin Gram then sums fp64 products with atomics, so two runs agree
+    # to fp64 round-off (not to the fp32 level a floating-point pass A would give)
+    gmax = np.abs(tc1["G_blk"]).max()
+    np.testing.assert_allclose(tc1["G_blk"], tc2["G_blk"], rtol=0, atol=1e-12 * gmax)
     # Z -> 4 Z: the Z block of the Gram scales by 16, Z x (W, y) by 4, the rest is unchanged -- exactly
     scale = np.ones(plan.Rs)
     scale[:B] = 4.0
-    np.testing.assert_array_equal(tc4["G_blk"], tc1["G_blk"] * np.outer(scale, scale))
+    np.testing.assert_allclose(tc4["G_blk"], tc1["G_blk"] * np.outer(scale, scale), rtol=0, atol=1e-11 * 16 * gmax)
     np.testing.assert_allclose(S4, 4.0 * S1, rtol=0, atol=1e-6 * np.abs(S1).max())
 
 
