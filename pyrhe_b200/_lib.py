@@ -89,4 +89,4 @@ def tcgen05_supported(plan, limbs: int = None) -> bool:
     bp = -(-plan.B // 2) * 2
     ncb = -(-(plan.n_groups * L * bp) // 16) * 16
     return (nba <= 256 and plan.K * ncb <= 512 and plan.K <= 255 and plan.n_groups * plan.K * plan.B <= 1024
-            and plan.B <= 64)
+            and plan.n_groups * plan.B <= 64)

@@ -313,7 +313,7 @@ __global__ void k_standardize(int m, int Rs, int R1, int B, int n_ops, int n_set
     w2[o] = (float)a2;
     shiftv[o] = sh;
     if (wmax)   // tensor path: per-column quantisation range over both operand weights (count, [g == 2] extra)
-      atomicMax(wmax + c, __float_as_uint(fmaxf(fabsf((float)a1), fabsf((float)a2 - 2.0f * (float)a1))));
+      atomicMax(wmax + grp * B + c, __float_as_uint(fmaxf(fabsf((float)a1), fabsf((float)a2 - 2.0f * (float)a1))));
   }
 }
 
@@ -758,7 +758,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
   unsigned int* wmax = g.kernel_path == RHE_PATH_TCGEN05 ? rhe_tc_wmax(c) : nullptr;
   k_stats_params<<<rhe_div_up(m, 8), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
                                                    c->counts, c->fill, c->mu, c->f2, c->t_raw, c->R1, g.n_ops, c->cs,
-                                                   c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? B : 0);
+                                                   c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? c->n_groups * B : 0);
   RHE_LAUNCH_CHECK(c);
   if (c->timing) RHE_CUDA(cudaEventRecord(tev[1], st));
 

@@ -52,7 +52,7 @@ struct TcState {
   double* col_dq = nullptr;   // [R1]        power-of-two dequantisation factor of every RHS column
   int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights of the current block
   int32_t* pos_meta = nullptr;  // [cap_pos]      SNP row | fill << 24 of the current block
-  unsigned int* wmax = nullptr; // [B]         max |weight| per column (float bits)
+  unsigned int* wmax = nullptr; // [n_groups][B] max |weight| per weight group and column (float bits)
   int cap_pos = 0;
   std::vector<TcBlockMeta> blocks;
   CUtensorMap tm_rq, tm_uq;
@@ -485,7 +485,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   for (int i = threadIdx.x; i < WG * K * B; i += PB_THREADS) sm->cs[i] = cs[i];
   for (int i = threadIdx.x; i < K; i += PB_THREADS) sm->cnt[i] = bin_count[i];
   // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
-  for (int i = threadIdx.x; i < B; i += PB_THREADS) sm->dq[i] = ldexp(1.0, (int)((wmax[i] >> 23) & 255u) - 126 - F);
+  for (int i = threadIdx.x; i < WG * B; i += PB_THREADS) sm->dq[i] = ldexp(1.0, (int)((wmax[i] >> 23) & 255u) - 126 - F);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -578,7 +578,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
           for (int j = 0; j < 2; ++j) {
             const int b = c0 + j;
             if (b < B) {
-              const float xf = has ? (float)(rs * (val[j] * sm->dq[b] - sm->cs[e * B + b])) : 0.f;
+              const float xf = has ? (float)(rs * (val[j] * sm->dq[wg * B + b] - sm->cs[e * B + b])) : 0.f;
               const size_t o = ((size_t)e * B + b) * Np + i;
               if (P_out) P_out[o] = xf;
               if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
@@ -704,7 +704,7 @@ __global__ void k_tc_quant_w(const float* __restrict__ w1, const float* __restri
   const int p = idx % n_pos, b = (idx / n_pos) % B, wg = (idx / (n_pos * B)) % WG, mode = idx / (n_pos * B * WG);
   const int row = pos_rows[p];
   if (b == 0 && wg == 0) pos_meta[mode * n_pos + p] = row >= 0 ? (row | ((int)fill[row] << 24) | (mode << 26)) : -1;
-  const int e = (int)((wmax[b] >> 23) & 255u) - 126;
+  const int e = (int)((wmax[wg * B + b] >> 23) & 255u) - 126;   // one fixed-point scale per (weight group, column)
   long long q = 0ll;
   if (row >= 0) {
     const size_t o = ((size_t)wg * m + row) * B + b;
@@ -746,7 +746,7 @@ int rhe_tc_create(rhe_ctx* c) {
   s->Bp = round_up(g.n_vec, 2);
   s->NCb = round_up(c->n_groups * s->L * s->Bp, 16);   // weight groups (RHS sets) are stacked along N
   s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
-  if (pb_smem_bytes(s->NCb, PB_BS) > 232448 || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || g.n_vec > 64) {
+  if (pb_smem_bytes(s->NCb, PB_BS) > 232448 || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     delete s;
     return RHE_ERR_UNSUPPORTED;
@@ -764,7 +764,7 @@ int rhe_tc_create(rhe_ctx* c) {
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
   alloc((void**)&s->rq, (size_t)s->NBa * c->Np);
   alloc((void**)&s->col_dq, sizeof(double) * c->R1);
-  alloc((void**)&s->wmax, sizeof(unsigned int) * g.n_vec);
+  alloc((void**)&s->wmax, sizeof(unsigned int) * c->n_groups * g.n_vec);
   if (e != cudaSuccess) { rhe_set_error("tensor-core workspace allocation failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
