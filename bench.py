@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--cpu_snps", type=int, default=200, help="SNPs per block of the CPU sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
-    ap.add_argument("--ring_blocks", type=int, default=8, help="pinned host ring (blocks) for the e2e leg")
+    ap.add_argument("--ring_blocks", type=int, default=4, help="pinned host ring (blocks) for the e2e leg")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
