@@ -85,7 +85,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": "warm-up + timed steps"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -218,10 +218,12 @@ def main():
             ms = float(t.item())
         return ms, out
 
-    for _ in range(args.warmup):
-        sigma = step_resident()
-    launches0 = eng.launches
+    # clocks are sampled (200 ms period) from the first warm-up step to the end of the timed region: at 8 GPUs the
+    # timed steps alone are shorter than one sampling period
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup):
+            sigma = step_resident()
+        launches0 = eng.launches
         ms_total, sigma = timed(step_resident, args.steps)
     launches = (eng.launches - launches0)
     ms_step = ms_total / args.steps
@@ -260,7 +262,7 @@ def main():
             rows, m = eng.block_view(eng.own[r])
             ring[r, :m].copy_(rows[:, : eng.row_bytes])
         copy_stream = torch.cuda.Stream(dev)
-        h2d = sum((eng.ranges[j][1] - eng.ranges[j][0]) * eng.row_bytes for j in eng.own) + eng.R.numel() * 4
+        h2d_total = M * eng.row_bytes + world * eng.R.numel() * 4      # all ranks: every .bed row once + the RHS per rank
         d2h_holder = {}
 
         def step_e2e():
@@ -279,7 +281,7 @@ def main():
         ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 2)))
         ms_e2e /= max(1, min(args.steps, 2))
         e2e = {"value": total_bytes / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h_holder["n"]),
+               "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_holder["n"]),
                "host_ring_blocks": R}
         del ring
 
