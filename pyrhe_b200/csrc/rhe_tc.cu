@@ -300,7 +300,7 @@ struct PaSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(PA_THREADS, 2)
+__global__ void __launch_bounds__(PA_THREADS, PA_G == 2 ? 2 : 1)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict__ bed, int pitch, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
             double* __restrict__ t_raw, int chunk, uint32_t tmem_cols, uint32_t col_a, int mode) {
@@ -800,13 +800,19 @@ unsigned int* rhe_tc_wmax(rhe_ctx* c) { return c->tc ? ((TcState*)c->tc)->wmax :
 int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
   const int tiles = rhe_div_up(m, 128);
-  // whole waves of 2 resident CTAs per SM (a nearly empty last wave costs a full CTA time); at least
-  // 8 super-stages (4096 individuals) per CTA so that prologue / epilogue stay amortised
+  // Split the individuals so that the grid fills whole waves of 2 resident CTAs per SM (a nearly empty last wave
+  // costs a full CTA time): pick the split count with the best wave efficiency, keeping at least 16 super-stages
+  // (8192 individuals) per CTA so that prologue / epilogue stay amortised.
   const int slots = 148 * 2;
-  int splits = tiles >= slots ? 1 : slots / tiles;
-  if (tiles * splits < slots / 2 + slots / 4 && tiles < slots) splits = (2 * slots) / tiles;   // poor fill: use two waves
+  int splits = 1;
+  double best = 0.0;
+  for (int cand = 1; cand <= 16; ++cand) {
+    if (cand > 1 && rhe_div_up(c->Np, cand) < 8192) break;
+    const int ctas = tiles * cand;
+    const double eff = (double)ctas / ((double)rhe_div_up(ctas, slots) * slots);
+    if (eff > best + 0.02) { best = eff; splits = cand; }
+  }
   int chunk = round_up(rhe_div_up(c->Np, splits), 512);
-  if (chunk < 4096) chunk = 4096;
   if (chunk > c->Np) chunk = c->Np;
   splits = rhe_div_up(c->Np, chunk);
   const uint32_t col_a = (uint32_t)round_up(s->NBa, 32);
