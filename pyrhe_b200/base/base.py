@@ -29,11 +29,12 @@ from ..hostmath import block_ranges, host_terms
 from ..util.file_processing import (generate_annot, read_annot, read_bim, read_cov, read_fam, read_pheno)
 from ..util.logger import Logger
 from ..util.types import CovImputeMethod, GenoImputeMethod  # noqa: F401
+from .legacy_ops import LegacyBlockOps
 
 _BED_MAGIC = bytes([0x6C, 0x1B, 0x01])
 
 
-class Base(ABC):
+class Base(LegacyBlockOps, ABC):
     #: False -> keep every block's XXz partial in HBM (one pass over the genotypes);
     #: True  -> the reference's two-pass "streaming" memory policy (recompute each block).
     _recompute_blocks = False
@@ -328,6 +329,9 @@ class Base(ABC):
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+        if getattr(self, "_dec_engine", None) is not None:
+            self._dec_engine.close()
+            self._dec_engine = None
 
     def __call__(self, trait, method: str = "QR"):
         self._trait = trait

@@ -512,7 +512,7 @@ __global__ void k_synth(uint8_t* __restrict__ bed, int64_t n_rows, int64_t pitch
 // Fast path for E <= 8 (RHE with up to 8 bins): one thread per position, the (at most 36) pair products stay in
 // fp64 registers over a grid-stride loop, one warp + block reduction at the end.  Memory bound: reads S and P once.
 template <int E>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_loo_gram_small(const float* __restrict__ S, const float* __restrict__ P, int64_t len, double* __restrict__ out) {
   constexpr int NP = E * (E + 1) / 2;
   double acc[NP];

@@ -242,6 +242,22 @@ class RheEngine:
             out = dict(XX=XX.cpu().numpy(), G_blk=G_blk.cpu().numpy(), M=self.Mjk)
         return out
 
+    def decode_rows(self, packed_rows: np.ndarray) -> np.ndarray:
+        """Decode arbitrary `.bed` rows ([m, row_bytes] uint8) -> int8 [m, N0], 3 = missing (no imputation)."""
+        m = packed_rows.shape[0]
+        out = np.empty((m, self.n_indv), dtype=np.int8)
+        with torch.cuda.device(self.device):
+            for a in range(0, m, self.max_m):
+                b = min(m, a + self.max_m)
+                dev = torch.zeros((b - a, self.pitch), dtype=torch.uint8, device=self.device)
+                _lib.check(self.lib.rhe_upload_rows(_lib.ptr(packed_rows[a:b]), self.row_bytes, b - a,
+                                                    C.c_void_p(dev.data_ptr()), self.pitch, self._stream()))
+                dec = torch.empty((b - a, self.Np), dtype=torch.int8, device=self.device)
+                _lib.check(self.lib.rhe_decode_block(self._ctx, C.c_void_p(dev.data_ptr()), b - a, 0, _lib.ptr(dec),
+                                                     self._stream()))
+                out[a:b] = dec.cpu().numpy()[:, : self.n_indv]
+        return out
+
     # ------------------------------------------------------------------ test hooks
     def decode_block(self, j: int, apply_impute: bool) -> np.ndarray:
         rows, m = self.block_view(j)

@@ -91,3 +91,34 @@ def test_genie_g_and_gxe_models_run_and_are_consistent(tmp_path):
         # at quantisation level (2^-22 of the column maximum) between the three models
         np.testing.assert_allclose(T[:E, :E], T_full[:E, :E], rtol=1e-6)
         assert np.all(np.isfinite(res["sigma_ests_total"]))
+
+
+def test_extender_block_ops_match_oracle():
+    """The per-op helpers a custom `Base` subclass may call (read_geno, impute_geno, partition_bins,
+    standardize_geno, _compute_*) against the oracle's restatement of the reference ops."""
+    from helpers import oracle_problem
+    from oracle import rhe_oracle
+    model, _ = build_model("rhe_cov_binary")
+    p = oracle_problem("rhe_cov_binary")
+    o = rhe_oracle.Oracle(p)
+    start, end = rhe_oracle.block_range(o.M_snps, o.J, 2)
+    ref_raw = rhe_oracle.decode_bed_rows(p.packed[start:end], p.n_indv_original)
+    ref_raw = np.delete(ref_raw, list(p.missing_indv), axis=0)
+    got_raw = model.read_geno(start, end)
+    np.testing.assert_array_equal(np.isnan(got_raw), np.isnan(ref_raw))
+    np.testing.assert_array_equal(np.nan_to_num(got_raw, nan=-1), np.nan_to_num(ref_raw, nan=-1))
+    np.random.seed(p.seed)
+    ref_imp = rhe_oracle.impute_block(ref_raw.copy(), p.impute)
+    np.random.seed(p.seed)
+    got_imp = model.impute_geno(got_raw.copy())
+    np.testing.assert_array_equal(got_imp, ref_imp)
+    bins = model.partition_bins(got_imp, model.annot_matrix[start:end])
+    X = model.standardize_geno(bins[0])
+    np.testing.assert_allclose(X, rhe_oracle.standardize(bins[0]), rtol=2e-6, atol=2e-6)
+    xxz = model._compute_XXz(1, X)
+    ref = rhe_oracle.mm(X, rhe_oracle.mm(X.T, p.Z[:, 1].reshape(-1, 1))).flatten()
+    np.testing.assert_allclose(xxz, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    model.pheno = model.pheno_cp[:, 0].reshape(-1, 1)
+    yxxy = model._compute_yXXy(X, model.pheno)
+    assert np.isfinite(yxxy).all() and yxxy.shape == (1, 1)
+    model._finalize()
