@@ -170,13 +170,27 @@ __device__ __forceinline__ uint32_t tc_value_table(uint32_t fill, int mode) {
 
 // Expand one packed word (16 genotypes) into 16 int8 values with the per-SNP value table
 // tab = {0, fill, 1, 2} (byte c = value of code c), in the permuted order above.
+// PRMT reads only the low four nibbles of its selector, and the ALU pipe (LOP3 / SHF / PRMT) is what limits the
+// decode, so: the two masks are computed once per word (inline PTX keeps the compiler from re-deriving a mask per
+// PRMT) and the right shifts run as multiply-high on the FMA pipe (x >> s == umulhi(x, 2^(32 - s))).
+__device__ __forceinline__ uint32_t tc_prmt(uint32_t tab, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(tab), "r"(0u), "r"(sel));
+  return r;
+}
+__device__ __forceinline__ uint32_t tc_shr_fma(uint32_t x, uint32_t pow2) {   // pow2 = 2^(32 - shift)
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(pow2));
+  return r;
+}
 __device__ __forceinline__ uint4 tc_expand(uint32_t w, uint32_t tab) {
-  const uint32_t e = w & 0x33333333u, o = (w >> 2) & 0x33333333u;
+  const uint32_t e = w & 0x33333333u;
+  const uint32_t o = tc_shr_fma(w, 1u << 30) & 0x33333333u;
   uint4 r;
-  r.x = __byte_perm(tab, 0, e);
-  r.y = __byte_perm(tab, 0, e >> 16);
-  r.z = __byte_perm(tab, 0, o);
-  r.w = __byte_perm(tab, 0, o >> 16);
+  r.x = tc_prmt(tab, e);
+  r.y = tc_prmt(tab, tc_shr_fma(e, 1u << 16));
+  r.z = tc_prmt(tab, o);
+  r.w = tc_prmt(tab, tc_shr_fma(o, 1u << 16));
   return r;
 }
 
