@@ -229,8 +229,8 @@ class Base(LegacyBlockOps, ABC):
                         kernel_path=path, rank=self._rank, world=self._world,
                         store_partials=not self._recompute_blocks, process_group=pg)
         eng.set_rhs(self.all_zb, self.cov_matrix, Y_res, self._env_vector())
-        eng.load_genotypes(self.geno_bed)
-        self._pieces = eng.run()
+        # ingest overlapped with compute: block j+1 is staged and copied while block j runs
+        self._pieces = eng.run(upload=eng.load_genotypes_async(self.geno_bed))
         self._engine = eng
         self._plan_cached = plan
         self._G_tot = self._pieces["G_blk"].sum(axis=0)

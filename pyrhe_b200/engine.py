@@ -180,6 +180,37 @@ class RheEngine:
             self.upload_block(j, np.ascontiguousarray(packed[a:b]))
         torch.cuda.current_stream(self.device).synchronize()
 
+    def load_genotypes_async(self, packed: np.ndarray):
+        """Start uploading this rank's blocks on a side stream from a background thread (the ctypes call releases
+        the GIL, so host staging of block j+1 overlaps the kernels of block j).  Pass the returned handle to
+        `run(upload=...)`; block j is consumed as soon as its own copy has finished."""
+        import threading
+        if self.bed is None:
+            self.alloc_genotypes()
+        copy_stream = torch.cuda.Stream(self.device)
+        ready = {j: threading.Event() for j in self.own}
+        events = {}
+        errors = []
+
+        def worker():
+            try:
+                with torch.cuda.device(self.device):
+                    for j in self.own:
+                        a, b = self.ranges[j]
+                        self.upload_block(j, np.ascontiguousarray(packed[a:b]), stream=copy_stream)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        events[j] = ev
+                        ready[j].set()
+            except Exception as exc:          # surfaced by run()
+                errors.append(exc)
+                for e in ready.values():
+                    e.set()
+
+        thread = threading.Thread(target=worker, daemon=True)
+        thread.start()
+        return dict(ready=ready, events=events, errors=errors, thread=thread)
+
     def block_view(self, j: int):
         m = self.ranges[j][1] - self.ranges[j][0]
         return self.bed[self._row_off[j]: self._row_off[j] + m], m
@@ -192,11 +223,12 @@ class RheEngine:
             self._ctx, C.c_void_p(rows.data_ptr()), m, C.c_void_p(self.bin_rows.data_ptr() + 4 * lo),
             self._offs[j], _lib.ptr(P_out), _lib.ptr(S_accum), _lib.ptr(gram_out), self._stream()))
 
-    def run(self, upload_events=None) -> dict:
+    def run(self, upload_events=None, upload=None) -> dict:
         """All own blocks -> totals -> all-reduce -> leave-one-out Grams.
 
         Returns host arrays XX [J+1, E, E] and G_blk [J, E_reg, Rs, Rs] (identical on all ranks).
-        `upload_events[j]`, when given, is a CUDA event the block's genotype upload signals."""
+        `upload_events[j]`, when given, is a CUDA event the block's genotype upload signals; `upload` is the handle
+        of `load_genotypes_async` (events appear as the background thread records them)."""
         plan = self.plan
         E, E_reg, B, Rs, Np, J = plan.E, plan.E_reg, plan.B, plan.Rs, self.Np, self.J
         dev = self.device
@@ -213,6 +245,11 @@ class RheEngine:
                 if E > E_reg:
                     P_all[:, E_reg:].zero_()
             for jl, j in enumerate(self.own):
+                if upload is not None:
+                    upload["ready"][j].wait()
+                    if upload["errors"]:
+                        raise upload["errors"][0]
+                    cur.wait_event(upload["events"][j])
                 if upload_events is not None:
                     cur.wait_event(upload_events[j])
                 self._accumulate(j, P_all[jl] if self.store_partials else None, S, G_blk[j])
