@@ -191,7 +191,10 @@ def main():
         G_tot = pieces["G_blk"].sum(axis=0)
         G_loo = np.concatenate([G_tot[None] - pieces["G_blk"], G_tot[None]], axis=0)
         T, q = normal_equations_batch(plan, ht, pieces["XX"], G_loo, pieces["M"])
-        return np.linalg.solve(T, q[..., None])[..., 0]
+        try:
+            return np.linalg.solve(T, q[..., None])[..., 0]
+        except np.linalg.LinAlgError:        # only with the kernel debug switches (PYRHE_TC_DEBUG_*) that skip work
+            return np.full(q.shape, np.nan)
 
     def step_resident():
         return tail(eng.run())

@@ -84,6 +84,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   asm volatile("trap;");
 }
+// The same primitives on raw shared-space addresses: the single-thread producer / issuer loops are pure latency
+// chains, so they keep every address in a register and advance it incrementally (no cvta, no div / mod).
+__device__ __forceinline__ void mbar_arrive_s(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t addr, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  asm volatile("trap;");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -93,6 +117,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_commit_s(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -259,6 +292,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint4 (&r)[8]) {
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// 16 registers -> 16 consecutive TMEM columns of this thread's lane; completion is awaited by tmem_st_wait()
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4 (&r)[4]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0].x), "r"(r[0].y), "r"(r[0].z), "r"(r[0].w), "r"(r[1].x), "r"(r[1].y), "r"(r[1].z), "r"(r[1].w),
+        "r"(r[2].x), "r"(r[2].y), "r"(r[2].z), "r"(r[2].w), "r"(r[3].x), "r"(r[3].y), "r"(r[3].z), "r"(r[3].w)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Zero 32 consecutive TMEM columns of this thread's lane (accumulators start at 0 so that every MMA can
 // accumulate and the issuing threads need no ordering among themselves).
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
@@ -278,23 +320,28 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(zero) : "memory");
 }
 
-// Optional cycle accounting (PYRHE_TC_PROF=1 at build time): where each role spends its time.
+// Optional cycle accounting (-DRHE_TC_PROF): where each role spends its time.  Every thread accumulates in
+// registers and lane 0 of each warp adds its totals once at the end, so the timed code is barely disturbed.
 #ifdef RHE_TC_PROF
 __device__ unsigned long long g_prof[32];
-#define PROF_T0() long long _t0 = clock64()
-#define PROF_ADD(slot) do { long long _t1 = clock64(); if ((threadIdx.x & 127) == 0 || threadIdx.x == 32 * (PB_DW + 1)) atomicAdd(&g_prof[slot], (unsigned long long)(_t1 - _t0)); _t0 = _t1; } while (0)
+#define PROF_T0() long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long _t0 = clock64()
+#define PROF_ADD(slot) do { long long _t1 = clock64(); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+#define PROF_FLUSH(base) do { if ((threadIdx.x & 31) == 0) { _Pragma("unroll") for (int _i = 0; _i < 8; ++_i) if (_acc[_i]) atomicAdd(&g_prof[(base) + _i], (unsigned long long)_acc[_i]); } } while (0)
 extern "C" void rhe_tc_prof_dump() {
   unsigned long long h[32];
   cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
-  const char* names[] = {"B.dec.cpwait", "B.dec.lds+meta", "B.dec.empty_wait", "B.dec.store", "B.dec.fence+arrive", "B.dec.epilogue",
-                         "B.mma.info", "B.mma.full_b", "B.mma.full_a", "B.mma.issue", "B.mma.total", "B.tma.empty_b", "B.dec.total", "B.dec.issue"};
-  for (int i = 0; i < 14; ++i) printf("  %-20s %12.3f Mcyc\n", names[i], h[i] / 1e6);
+  const char* names[] = {"B.dec.top(meta,tab)", "B.dec.empty_wait", "B.dec.store", "B.dec.fetch", "B.dec.fence+arrive", "B.dec.acc_wait", "B.dec.epilogue", "B.dec.-",
+                         "B.mma.info", "B.mma.full_b", "B.mma.full_a", "B.mma.issue+commit", "B.mma.-", "B.mma.-", "B.mma.-", "B.mma.-",
+                         "A.dec.lds", "A.dec.empty_wait", "A.dec.expand+st", "A.dec.st_wait+arrive", "A.dec.cpwait", "A.dec.acc_wait", "A.dec.epilogue", "A.dec.-",
+                         "A.mma.full_b", "A.mma.full_a", "A.mma.issue+commit", "A.mma.-", "A.mma.-", "A.mma.-", "A.mma.-", "A.mma.-"};
+  for (int i = 0; i < 32; ++i) if (h[i]) printf("  %-22s %12.3f Mcyc (sum over warps)\n", names[i], h[i] / 1e6);
   unsigned long long z[32] = {0};
   cudaMemcpyToSymbol(g_prof, z, sizeof(z));
 }
 #else
 #define PROF_T0()
 #define PROF_ADD(slot)
+#define PROF_FLUSH(base)
 #endif
 
 // ------------------------------------------------------------------------------------------ pass A
@@ -305,7 +352,7 @@ extern "C" void rhe_tc_prof_dump() {
 #define PA_DW (4 * PA_G)
 #define PA_THREADS (32 * (PA_DW + 1 + PA_G))   // decode warps, one TMA warp, one MMA-issue warp per group
 #define PA_AS 4                   // TMEM A slots (32 columns each) = sub-tiles of one super-stage
-#define PA_BS 4                   // smem ring of Rq tiles (TMA)
+#define PA_BS 8                   // maximum depth of the smem ring of Rq tiles (TMA); the launch picks bsa <= PA_BS
 #define PA_PK 4                   // cp.async ring of packed super-stages (128 rows x 128 B)
 #define PA_PACKED (128 * 128)
 
@@ -317,24 +364,28 @@ struct PaSmem {
 __global__ void __launch_bounds__(PA_THREADS, PA_G == 2 ? 2 : 1)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict__ bed, int pitch, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
-            double* __restrict__ t_raw, int chunk, uint32_t tmem_cols, uint32_t col_a, int mode) {
+            double* __restrict__ t_raw, int chunk, uint32_t tmem_cols, uint32_t col_a, int mode, int bsa, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileB = smem;
   const int tileB_bytes = NB * 128;
-  uint8_t* packed = tileB + PA_BS * tileB_bytes;
+  uint8_t* packed = tileB + bsa * tileB_bytes;
   PaSmem* sm = reinterpret_cast<PaSmem*>(packed + PA_PK * PA_PACKED);
   const uint32_t packed_s = smem_u32(packed);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int snp0 = blockIdx.x * 128;
-  const int i_begin = blockIdx.y * chunk, i_end = min(Np, i_begin + chunk);
-  const int n_ss = (i_end - i_begin) >> 9;          // super-stages of 512 individuals
+  // grid = (splits, SNP tiles), split index fastest: the CTAs of one SNP tile are co-resident and CTA y takes the
+  // super-stages y, y + splits, ... (512 individuals = one 128-byte line per SNP row), so at any moment the tile's
+  // CTAs read `splits` adjacent lines of the same 128 rows -- DRAM pages are opened once for the whole group.
+  const int snp0 = blockIdx.y * 128;
+  const int splits = gridDim.x, y = blockIdx.x;
+  const int total_ss = Np >> 9;
+  const int n_ss = total_ss > y ? (total_ss - y + splits - 1) / splits : 0;   // super-stages of 512 individuals
   if (n_ss <= 0) return;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PA_AS; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
-    for (int s = 0; s < PA_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
+    for (int s = 0; s < PA_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
+    for (int s = 0; s < bsa; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
     mbar_init(&sm->acc_full, PA_G);
     fence_barrier_init();
   }
@@ -353,12 +404,13 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     const int t = threadIdx.x & 127, g = warp >> 2;
     const int s = min(snp0 + t, m - 1);
     const uint32_t tab = tc_value_table(fill[s], mode);
-    const uint8_t* src = bed + (size_t)s * pitch + (i_begin >> 2);
+    const uint8_t* src = bed + (size_t)s * pitch + (size_t)y * 128;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     // group g fetches only the chunks of its own sub-tiles (q = g, g + 2 -> chunks 2q, 2q + 1)
     auto issue = [&](int ss) {
       const uint32_t slot = packed_s + (ss % PA_PK) * PA_PACKED + t * 16;
-      const uint8_t* p = src + (size_t)ss * 128;
+      const uint8_t* p = src + (size_t)ss * splits * 128;
+      if (dbg & 4) return;
 #pragma unroll
       for (int q = 0; q < 4; q += PA_G) {
         const int c = 2 * (q + g);
@@ -371,29 +423,51 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
       if (pre < n_ss) issue(pre);
       cp_async_commit();
     }
+    // Software pipeline: the packed words of the next sub-tile are read from the ring before the current one is
+    // expanded, and each sub-tile goes to TMEM as two 16-column stores so that the first store overlaps the
+    // expansion of the second half.
+    static_assert(PA_G == 2, "two sub-tiles per group and super-stage");
+    PROF_T0();
+    auto put = [&](int q, int ss, const uint4& lo, const uint4& hi) {
+      uint4 r[4];
+      PROF_ADD(0);
+      mbar_wait(&sm->empty_a[q], (ss & 1) ^ 1);
+      tc_fence_after();
+      PROF_ADD(1);
+      const uint32_t dst = lane_base + col_a + 32 * q;
+      if (dbg & 8) { if (lane == 0) mbar_arrive(&sm->full_a[q]); return; }
+      r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
+      tmem_st16(dst, r);
+      uint4 r2[4];
+      r2[0] = tc_expand(hi.x, tab); r2[1] = tc_expand(hi.y, tab); r2[2] = tc_expand(hi.z, tab); r2[3] = tc_expand(hi.w, tab);
+      tmem_st16(dst + 16, r2);
+      PROF_ADD(2);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();                                    // every lane's stores are complete and fenced: one arrival per warp
+      if (lane == 0) mbar_arrive(&sm->full_a[q]);
+      PROF_ADD(3);
+    };
+    cp_async_wait<PA_PK - 2>();
+    uint32_t slot = packed_s + t * 16;
+    uint4 lo = lds128(slot + (2 * g) * 2048), hi = lds128(slot + (2 * g + 1) * 2048);
     for (int ss = 0; ss < n_ss; ++ss) {
       if (ss + PA_PK - 1 < n_ss) issue(ss + PA_PK - 1);
       cp_async_commit();
-      cp_async_wait<PA_PK - 1>();
-      const uint32_t slot = packed_s + (ss % PA_PK) * PA_PACKED + t * 16;
-#pragma unroll
-      for (int q0 = 0; q0 < 4; q0 += PA_G) {
-        const int q = q0 + g;                        // TMEM A slot q, used once per super-stage
-        const uint4 lo = lds128(slot + (2 * q) * 2048);
-        const uint4 hi = lds128(slot + (2 * q + 1) * 2048);
-        uint4 r[8];
-        r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
-        r[4] = tc_expand(hi.x, tab); r[5] = tc_expand(hi.y, tab); r[6] = tc_expand(hi.z, tab); r[7] = tc_expand(hi.w, tab);
-        mbar_wait(&sm->empty_a[q], (ss & 1) ^ 1);
-        tc_fence_after();
-        tmem_st32(lane_base + col_a + 32 * q, r);
-        tc_fence_before();
-        mbar_arrive(&sm->full_a[q]);
-      }
+      const uint4 lo2 = lds128(slot + (2 * g + 4) * 2048), hi2 = lds128(slot + (2 * g + 5) * 2048);
+      put(g, ss, lo, hi);
+      cp_async_wait<PA_PK - 2>();                      // super-stage ss + 1 has landed
+      PROF_ADD(4);
+      slot = packed_s + ((ss + 1) % PA_PK) * PA_PACKED + t * 16;
+      lo = lds128(slot + (2 * g) * 2048);
+      hi = lds128(slot + (2 * g + 1) * 2048);
+      put(g + 2, ss, lo2, hi2);
     }
     // ---- epilogue: lane quadrant (warp & 3) of TMEM, row = SNP; the two groups split the columns
+    PROF_ADD(0);
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
+    PROF_ADD(5);
     const int snp = snp0 + t;
     for (int c0 = 4 * g; c0 < R1p; c0 += 4 * PA_G) {
       double val[4];
@@ -404,40 +478,65 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
           if (c0 + j < R1) atomicAdd(t_raw + (size_t)snp * R1 + c0 + j, val[j] * col_dq[c0 + j]);
       }
     }
+    PROF_ADD(6);
+    PROF_FLUSH(16);
     tc_fence_before();
   } else if (warp == PA_DW) {
-    if (lane == 0) {
-      const int n_sub = n_ss * 4;
-      for (int sub = 0; sub < n_sub; ++sub) {
-        const int b = sub % PA_BS, use = sub / PA_BS;
-        mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
-        mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
-        tma_load_2d(tileB + b * tileB_bytes, &tm_rq, &sm->full_b[b], i_begin + sub * 128, 0);
+    if (lane == 0) {                                   // TMA producer: Rq tile of sub-tile sub = 4 ss + q -> slot sub % bsa
+      const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
+      uint32_t bar = 0, dst = smem_u32(tileB), wait_par = 1;
+      int b = 0, x = y * 512;
+      for (int ss = 0; ss < n_ss; ++ss, x += splits * 512) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          mbar_wait_s(eb + bar, wait_par);
+          if (dbg & 1) mbar_arrive_s(fb + bar);
+          else {
+            mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
+            tma_load_2d_s(dst, &tm_rq, fb + bar, x + q * 128, 0);
+          }
+          bar += 8; dst += (uint32_t)tileB_bytes;
+          if (++b == bsa) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
+        }
       }
     }
   } else {
     // ---- MMA issue: one warp (one elected lane) per decode group, so no single thread serialises the block.
-    // Every MMA accumulates (the accumulator was zeroed), hence the issuers need no mutual ordering.
+    // Every MMA accumulates (the accumulator was zeroed), hence the issuers need no mutual ordering.  Group g takes
+    // the sub-tiles sub = g, g + 2, ...: ring slot sub % bsa (bsa even), TMEM A slot alternating between g and g + 2.
     if (lane == 0) {
       const int g = warp - (PA_DW + 1);
       const uint32_t idesc = idesc_i8(128, NB, 0);
-      static_assert(PA_BS == 4, "sub-tile q of every super-stage uses Rq ring slot q");
-      for (int ss = 0; ss < n_ss; ++ss) {
-#pragma unroll
-        for (int q0 = 0; q0 < 4; q0 += PA_G) {         // sub = 4 ss + q: TMEM A slot q, Rq ring slot q, use ss
-          const int q = q0 + g;
-          const uint64_t bdesc = smem_desc_sw128(smem_u32(tileB + q * tileB_bytes), 16, 1024);
-          mbar_wait(&sm->full_b[q], ss & 1);
-          mbar_wait(&sm->full_a[q], ss & 1);
-          tc_fence_after();
+      const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
+      const uint32_t fa = smem_u32(&sm->full_a[0]), ea = smem_u32(&sm->empty_a[0]);
+      const uint64_t bdesc0 = smem_desc_sw128(smem_u32(tileB), 16, 1024);
+      PROF_T0();
+      int b = g;
+      uint32_t ph_b = 0, ph_a = 0, q = (uint32_t)g;
+      const int n_sub = 2 * n_ss;
+      for (int n = 0; n < n_sub; ++n) {
+        mbar_wait_s(fb + 8u * (uint32_t)b, ph_b);
+        PROF_ADD(0);
+        mbar_wait_s(fa + 8u * q, ph_a);
+        tc_fence_after();
+        PROF_ADD(1);
+        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)b * (uint32_t)(tileB_bytes >> 4));
+        const uint32_t acol = tmem + col_a + 32u * q;
+        if (!(dbg & 2)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
-            umma_i8_ts(tmem, tmem + col_a + 32 * q + 8 * j, desc_advance(bdesc, j * 32), idesc, 1u);
-          umma_commit(&sm->empty_a[q]);
-          umma_commit(&sm->empty_b[q]);
+            umma_i8_ts(tmem, acol + 8u * j, bdesc + (uint64_t)(j * 2), idesc, 1u);
         }
+        umma_commit_s(ea + 8u * q);
+        umma_commit_s(eb + 8u * (uint32_t)b);
+        PROF_ADD(2);
+        b += 2;
+        if (b >= bsa) { b -= bsa; ph_b ^= 1u; }
+        q ^= 2u;                                       // g <-> g + 2
+        if (q == (uint32_t)g) ph_a ^= 1u;
       }
       umma_commit(&sm->acc_full);
+      PROF_FLUSH(24);
     }
   }
   __syncthreads();
@@ -452,8 +551,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 #define PB_G 4
 #define PB_DW (4 * PB_G)
 #define PB_THREADS (32 * (PB_DW + 1 + PB_G))   // decode warps, one TMA warp, one MMA-issue warp per group
-#define PB_BS 4                   // smem ring of Uq tiles (TMA)
-#define PB_PKG 3                  // per-group cp.async ring depth (in the group's own stages)
+#define PB_BS 16                  // maximum depth of the smem ring of Uq tiles (TMA); the launch picks bs <= PB_BS
 #define PB_AS 2                   // shared-memory A slots per decode group (decode of tile u+1 overlaps the MMAs of tile u)
 
 #define PB_MAX_STAGES 512
@@ -467,6 +565,74 @@ struct PbSmem {
   int32_t cnt[256];               // rows per bin
 };
 
+// W adjacent accumulator columns of the L limb rows (limb l sits `stride` columns further on) -> exact doubles
+template <int W>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, int32_t (&v)[W]) {
+  static_assert(W == 2 || W == 8, "column chunk");
+  if constexpr (W == 2) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+  }
+}
+template <int L, int W>
+__device__ __forceinline__ void tmem_combine(uint32_t taddr, int stride, double (&val)[W]) {
+  int32_t v[L][W];
+#pragma unroll
+  for (int l = 0; l < L; ++l) tmem_ldw<W>(taddr + (uint32_t)(l * stride), v[l]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    double acc = (double)v[L - 1][j];
+#pragma unroll
+    for (int l = L - 2; l >= 0; --l) acc = fma(acc, 256.0, (double)v[l][j]);   // exact: |value| < 2^53
+    val[j] = acc;
+  }
+}
+
+// Pass-B epilogue of one decode thread (TMEM lane = individual i): P[e][b][i] = rs_i * (acc * dq - cs) for the
+// bins k = par (mod SI) of M-tile q.  Columns are read eight at a time (one tcgen05.ld per limb row), the
+// remainder of a row in pairs, so nothing is read beyond the limb rows of the (bin, tile) accumulator.
+template <int L>
+__device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq_s, const double* cs_s, uint32_t trow, int i,
+                                            int par, int SI, int q, int MT, int K, int WG, int B, int Bp, int NC, int Np,
+                                            const float* __restrict__ rowscale, int rs_stride,
+                                            float* __restrict__ P_out, float* __restrict__ S_accum) {
+  for (int k = par; k < K; k += SI) {
+    const bool has = cnt[k] > 0;
+    const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
+    for (int wg = 0; wg < WG; ++wg) {                // weight group = RHS set (GxE) or operand (dominance) -> estimate wg * K + k
+      const int e = wg * K + k;
+      const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
+      const size_t o0 = (size_t)e * B * Np + i;
+      const double* dq = dq_s + wg * B;
+      const double* cs = cs_s + e * B;
+      auto emit = [&](int b, double val) {
+        const float xf = has ? (float)(rs * (val * dq[b] - cs[b])) : 0.f;
+        const size_t o = o0 + (size_t)b * Np;
+        if (P_out) P_out[o] = xf;
+        if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
+      };
+      int c0 = 0;
+      for (; c0 + 8 <= Bp; c0 += 8) {
+        double val[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (has) tmem_combine<L, 8>(tcol + (uint32_t)(wg * L * Bp + c0), Bp, val);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < B) emit(c0 + j, val[j]);
+      }
+      for (; c0 < Bp; c0 += 2) {
+        double val[2] = {0.0, 0.0};
+        if (has) tmem_combine<L, 2>(tcol + (uint32_t)(wg * L * Bp + c0), Bp, val);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (c0 + j < B) emit(c0 + j, val[j]);
+      }
+    }
+  }
+}
+
 template <int MT>
 __global__ void __launch_bounds__(PB_THREADS, 1)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
@@ -474,23 +640,23 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
             const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
-            uint32_t tmem_cols, int a_major, int kcap, int bs) {
+            uint32_t tmem_cols, int a_major, int kcap, int bs, int dbg) {
+  if (dbg & 16) n_stage = 0;
   constexpr int SI = PB_G / MT;                      // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileA = smem;
   uint8_t* tileB = tileA + PB_G * PB_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
-  uint8_t* packed = tileB + bs * tileB_bytes;     // [group][PB_PKG][2 chunks][128 threads][16 B]
-  PbSmem* sm = reinterpret_cast<PbSmem*>(packed + PB_G * PB_PKG * 4096);
-  const uint32_t tileA_s = smem_u32(tileA), packed_s = smem_u32(packed);
+  PbSmem* sm = reinterpret_cast<PbSmem*>(tileB + bs * tileB_bytes);
+  const uint32_t tileA_s = smem_u32(tileA);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * (MT * 128);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PB_G * PB_AS; ++s) { mbar_init(&sm->full_a[s], 128); mbar_init(&sm->empty_a[s], 1); }
-    for (int s = 0; s < PB_BS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], MT); }
+    for (int s = 0; s < PB_G * PB_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
+    for (int s = 0; s < bs; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], MT); }
     mbar_init(&sm->acc_full, PB_G);
     fence_barrier_init();
   }
@@ -504,7 +670,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
-  if (warp < PB_DW) {                                  // zero the accumulators: quadrant per warp, columns split by group
+  if (warp < PB_DW && !(dbg & 32)) {                   // zero the accumulators: quadrant per warp, columns split by group
     const uint32_t used = (uint32_t)(K * MT * NC);
     for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < used; c += 32 * PB_G)
       tmem_zero32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c);
@@ -517,137 +683,130 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const int t = threadIdx.x & 127, g = warp >> 2;
     const int par = g / MT, q = g % MT;
     const uint8_t* base = bed + (i0 >> 2) + q * 32;
-    const uint32_t ring = packed_s + g * (PB_PKG * 4096) + t * 16;
     const int n_own = n_stage > par ? (n_stage - par + SI - 1) / SI : 0;   // stages st = par + SI * u
-    // pos_meta[p] = SNP row | fill << 24 (or -1 for padding); loaded one iteration before it is needed so
-    // that the dependent address never stalls the (in-order) decode thread
+    // Register rings, statically indexed by unrolling six stages: M[j % 6] = pos_meta of stage j (SNP row |
+    // fill << 24 | mode << 26, or -1 for padding), loaded five stages ahead; W[j % 3] = the 32 packed bytes of
+    // stage j, loaded three stages ahead straight into registers (the row address depends on M, so the two-stage
+    // gap between them keeps the in-order decode thread off the L2 latency).
+    int M[6];
+    uint4 Wlo[3], Whi[3];
     auto meta_of = [&](int u) { return u < n_own ? __ldg(pos_meta + (par + SI * u) * 128 + t) : -1; };
-    auto issue = [&](int u, int meta) {
-      if (meta >= 0) {
-        const uint8_t* p = base + (size_t)(meta & 0xFFFFFF) * pitch;
-        const uint32_t slot = ring + (u % PB_PKG) * 4096;
-        cp_async16(slot, p);
-        cp_async16(slot + 2048, p + 16);
+    auto fetch = [&](int meta, uint4& lo, uint4& hi) {
+      if (meta >= 0 && !(dbg & 1)) {
+        const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)(meta & 0xFFFFFF) * pitch);
+        lo = ldg_nc(p);
+        hi = ldg_nc(p + 1);
+      } else {
+        lo = make_uint4(0u, 0u, 0u, 0u);
+        hi = lo;
       }
     };
-    int tabs[PB_PKG];                                  // value tables of the stages in flight (register ring)
 #pragma unroll
-    for (int pre = 0; pre < PB_PKG - 1; ++pre) {
-      const int meta = meta_of(pre);
-      issue(pre, meta);
-      tabs[pre] = meta;
-      cp_async_commit();
-    }
-    int meta_next = meta_of(PB_PKG - 1);
+    for (int j = 0; j < 5; ++j) M[j] = meta_of(j);
+    M[5] = -1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) fetch(M[j], Wlo[j], Whi[j]);
+    const uint32_t tile0 = tileA_s + g * PB_AS * TC_TILE_A;
+    uint64_t* const full0 = &sm->full_a[g * PB_AS];
+    uint64_t* const empty0 = &sm->empty_a[g * PB_AS];
     PROF_T0();
-#ifdef RHE_TC_PROF
-    const long long _tstart = clock64();
-#endif
-    for (int u0 = 0; u0 < n_own; u0 += PB_PKG) {
+    static_assert(PB_AS == 2, "slot parity below assumes two A slots per group");
+    for (int u0 = 0; u0 < n_own; u0 += 6) {
 #pragma unroll
-      for (int r = 0; r < PB_PKG; ++r) {               // unrolled so that the register ring is statically indexed
+      for (int r = 0; r < 6; ++r) {
         const int u = u0 + r;
         if (u < n_own) {
-          issue(u + PB_PKG - 1, meta_next);
-          tabs[(r + PB_PKG - 1) % PB_PKG] = meta_next;
-          meta_next = meta_of(u + PB_PKG);
-          cp_async_commit();
-          PROF_ADD(13);
-          cp_async_wait<PB_PKG - 1>();
-          PROF_ADD(0);
-          const int meta = tabs[r];
+          M[(r + 5) % 6] = meta_of(u + 5);
+          const int meta = M[r];
           const uint32_t tab = meta >= 0 ? tc_value_table(((uint32_t)meta >> 24) & 3u, (meta >> 26) & 1) : 0u;
-          const uint32_t slot = ring + (u % PB_PKG) * 4096;
-          const uint4 lo = lds128(slot), hi = lds128(slot + 2048);
+          const int a = r & 1;                           // u0 is even: slot = u % 2, use index u / 2
+          PROF_ADD(0);
+          mbar_wait(empty0 + a, ((u >> 1) & 1) ^ 1);
           PROF_ADD(1);
-          const int a = g * PB_AS + (u % PB_AS);       // this group's slots alternate; use index u / PB_AS
-          mbar_wait(&sm->empty_a[a], ((u / PB_AS) & 1) ^ 1);
+          if (!(dbg & 2)) tc_store_row(tile0 + a * TC_TILE_A, t, Wlo[r % 3], Whi[r % 3], tab);
           PROF_ADD(2);
-          tc_store_row(tileA_s + a * TC_TILE_A, t, lo, hi, tab);
+          fetch(M[(r + 3) % 6], Wlo[r % 3], Whi[r % 3]);
           PROF_ADD(3);
           fence_proxy_async();
-          mbar_arrive(&sm->full_a[a]);
+          __syncwarp();                                  // every lane's rows are fenced: one arrival per warp
+          if (lane == 0) mbar_arrive(full0 + a);
           PROF_ADD(4);
         }
       }
     }
-#ifdef RHE_TC_PROF
-    if ((threadIdx.x & 127) == 0) atomicAdd(&g_prof[12], (unsigned long long)(clock64() - _tstart));
-#endif
     // ---- epilogue: TMEM lane = position inside M-tile q; group (par, q) takes the bins k = par (mod SI)
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
+    PROF_ADD(5);
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
-    for (int k = par; k < K; k += SI) {
-      const bool has = sm->cnt[k] > 0;
-      const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
-      for (int wg = 0; wg < WG; ++wg) {              // weight group = RHS set (GxE) or operand (dominance) -> estimate wg * K + k
-        const int e = wg * K + k;
-        const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
-        for (int c0 = 0; c0 < Bp; c0 += 2) {
-          double val[2] = {0.0, 0.0};
-          if (has) tmem_combine2(tcol + (uint32_t)(wg * L * Bp + c0), L, Bp, val);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int b = c0 + j;
-            if (b < B) {
-              const float xf = has ? (float)(rs * (val[j] * sm->dq[wg * B + b] - sm->cs[e * B + b])) : 0.f;
-              const size_t o = ((size_t)e * B + b) * Np + i;
-              if (P_out) P_out[o] = xf;
-              if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
-            }
-          }
-        }
-      }
+    if (!(dbg & 4)) switch (L) {
+      case 2: pb_epilogue<2>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
+      case 3: pb_epilogue<3>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
+      default: pb_epilogue<4>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
     }
-    PROF_ADD(5);
+    PROF_ADD(6);
+    PROF_FLUSH(0);
     tc_fence_before();
   } else if (warp == PB_DW) {
-    if (lane == 0) {
+    if (lane == 0) {                                   // TMA producer: Uq tile of stage st -> ring slot st % bs
+      const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
+      uint32_t bar = 0, dst = smem_u32(tileB), wait_par = 1;
+      int b = 0;
       for (int st = 0; st < n_stage; ++st) {
-        const int b = st % bs, use = st / bs;
-        mbar_wait(&sm->empty_b[b], (use & 1) ^ 1);
-        mbar_expect_tx(&sm->full_b[b], (uint32_t)tileB_bytes);
-        tma_load_2d(tileB + b * tileB_bytes, &tm_uq, &sm->full_b[b], st * 128, 0);
+        mbar_wait_s(eb + bar, wait_par);
+        if (dbg & 8) mbar_arrive_s(fb + bar);
+        else {
+          mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
+          tma_load_2d_s(dst, &tm_uq, fb + bar, st * 128, 0);
+        }
+        bar += 8; dst += (uint32_t)tileB_bytes;
+        if (++b == bs) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
       }
     }
   } else {
-    // ---- MMA issue: one warp (one elected lane) per decode group (par, q); all MMAs accumulate into zeroed TMEM
+    // ---- MMA issue: one warp (one elected lane) per decode group (par, q); all MMAs accumulate into zeroed TMEM.
+    // The loop is one thread's dependent-latency chain: slot indices, parities and descriptors advance incrementally.
     if (lane == 0) {
       const int g = warp - (PB_DW + 1);
       const int par = g / MT, q = g % MT;
       const uint32_t idesc = idesc_i8(128, NC, a_major);   // A is MN-major: 128 individuals contiguous per SNP row
-      const uint32_t tileB_s = smem_u32(tileB);
+      const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
+      const uint32_t fa = smem_u32(&sm->full_a[g * PB_AS]), ea = smem_u32(&sm->empty_a[g * PB_AS]);
+      const uint32_t info_s = smem_u32(&sm->info[0]);
+      const uint64_t adesc0 = smem_desc_sw128(tileA_s + g * PB_AS * TC_TILE_A, TC_TILE_A, 1024);
+      const uint64_t bdesc0 = smem_desc_sw128(smem_u32(tileB), 16, 1024);
+      const uint32_t dq = tmem + (uint32_t)(q * NC);
       PROF_T0();
-#ifdef RHE_TC_PROF
-      const long long _tstart = clock64();
-#endif
-      int u = 0;
-      for (int st = par; st < n_stage; st += SI, ++u) {
-        const int b = st % bs;
-        const int info = sm->info[st];
-        const int k = info & 255, ksteps = min(info >> 16, kcap);
-        const uint64_t bdesc = smem_desc_sw128(tileB_s + b * tileB_bytes, 16, 1024);
-        PROF_ADD(6);
-        mbar_wait(&sm->full_b[b], (st / bs) & 1);
-        PROF_ADD(7);
-        const int a = g * PB_AS + (u % PB_AS);
-        const uint64_t adesc = smem_desc_sw128(tileA_s + a * TC_TILE_A, TC_TILE_A, 1024);
-        mbar_wait(&sm->full_a[a], (u / PB_AS) & 1);
-        PROF_ADD(8);
+      int b = par;                                     // par < SI <= bs
+      uint32_t ph_b = 0, a = 0, ph_a = 0;
+      uint32_t info = par < n_stage ? lds32(info_s + 4u * par) : 0u;
+      for (int st = par; st < n_stage; st += SI) {
+        const uint32_t k = info & 255u;
+        const int ksteps = min((int)(info >> 16), kcap);
+        if (st + SI < n_stage) info = lds32(info_s + 4u * (uint32_t)(st + SI));
+        PROF_ADD(0);
+        mbar_wait_s(fb + 8u * (uint32_t)b, ph_b);
+        PROF_ADD(1);
+        mbar_wait_s(fa + 8u * a, ph_a);
+        PROF_ADD(2);
         tc_fence_after();
-        const uint32_t dcol = tmem + (uint32_t)((k * MT + q) * NC);
-        for (int j = 0; j < ksteps; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
-          umma_i8(dcol, desc_advance(adesc, j * 4096), desc_advance(bdesc, j * 32), idesc, 1u);
-        umma_commit(&sm->empty_a[a]);
-        umma_commit(&sm->empty_b[b]);
-        PROF_ADD(9);
+        const uint32_t dcol = dq + k * (uint32_t)(MT * NC);
+        const uint64_t adesc = adesc0 + (uint64_t)(a * (TC_TILE_A >> 4));
+        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)b * (uint32_t)(tileB_bytes >> 4));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
+          if (j < ksteps) umma_i8(dcol, adesc + (uint64_t)(j * 256), bdesc + (uint64_t)(j * 2), idesc, 1u);
+        if (dbg & 64) { mbar_arrive_s(ea + 8u * a); mbar_arrive_s(eb + 8u * (uint32_t)b); }
+        else { umma_commit_s(ea + 8u * a); umma_commit_s(eb + 8u * (uint32_t)b); }
+        PROF_ADD(3);
+        b += SI;
+        if (b >= bs) { b -= bs; ph_b ^= 1u; }
+        a ^= 1u;
+        if (a == 0u) ph_a ^= 1u;
       }
       umma_commit(&sm->acc_full);
-#ifdef RHE_TC_PROF
-      atomicAdd(&g_prof[10], (unsigned long long)(clock64() - _tstart));
-#endif
+      PROF_FLUSH(8);
     }
   }
   __syncthreads();
@@ -742,11 +901,29 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
-static inline int pa_smem_bytes(int nb) { return PA_BS * nb * 128 + PA_PK * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
-static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_G * PB_PKG * 4096 + (int)sizeof(PbSmem) + 1024; }
+static inline int pa_smem_bytes(int nb, int bsa) { return bsa * nb * 128 + PA_PK * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
+// Deepest Rq ring (the look-ahead that hides the TMA round trip) that still lets two CTAs share an SM.  The depth
+// stays even: sub-tile `sub` belongs to group sub % 2, so every slot is then always consumed by the same group and
+// no waiter can be two mbarrier phases away from its barrier (parity aliasing).
+static inline int pa_ring(int nb) {
+  int bsa = PA_BS;
+  while (bsa > 4 && pa_smem_bytes(nb, bsa) > 233472 / 2 - 1024) bsa -= 2;
+  const char* env = getenv("PYRHE_TC_DEBUG_RINGA");
+  if (env && atoi(env) >= 4 && atoi(env) <= bsa) bsa = atoi(env) / 2 * 2;
+  return bsa;
+}
+static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + (int)sizeof(PbSmem) + 1024; }
 // The Uq ring depth must be a multiple of the stage interleave (4 / MT): consecutive uses of one slot are then
 // consumed by the same issuer, which keeps every waiter within one mbarrier phase of its barrier.
-static inline int pb_ring(int) { return PB_BS; }
+// The TMA producer refills a slot only after the MMAs that read it have completed, so the ring depth is the
+// look-ahead that hides the TMA round trip: as deep as shared memory allows.
+static inline int pb_ring(int nc) {
+  int bs = PB_BS;
+  while (bs > 4 && pb_smem_bytes(nc, bs) > 232448 - 2048) bs -= 4;
+  const char* env = getenv("PYRHE_TC_DEBUG_RING");
+  if (env && atoi(env) >= 4 && atoi(env) <= bs) bs = atoi(env) / 4 * 4;
+  return bs;
+}
 
 int rhe_tc_create(rhe_ctx* c) {
   const rhe_config& g = c->cfg;
@@ -760,7 +937,7 @@ int rhe_tc_create(rhe_ctx* c) {
   s->Bp = round_up(g.n_vec, 2);
   s->NCb = round_up(c->n_groups * s->L * s->Bp, 16);   // weight groups (RHS sets) are stacked along N
   s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
-  if (pb_smem_bytes(s->NCb, PB_BS) > 232448 || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
+  if (pb_smem_bytes(s->NCb, 4) > 232448 || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     delete s;
     return RHE_ERR_UNSUPPORTED;
@@ -782,7 +959,7 @@ int rhe_tc_create(rhe_ctx* c) {
   if (e != cudaSuccess) { rhe_set_error("tensor-core workspace allocation failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa)));
+  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa, pa_ring(s->NBa))));
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb))));
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb))));
   return RHE_OK;
@@ -826,18 +1003,18 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
     const double eff = (double)ctas / ((double)rhe_div_up(ctas, slots) * slots);
     if (eff > best + 0.02) { best = eff; splits = cand; }
   }
-  int chunk = round_up(rhe_div_up(c->Np, splits), 512);
-  if (chunk > c->Np) chunk = c->Np;
-  splits = rhe_div_up(c->Np, chunk);
+  if (splits > c->Np / 512) splits = c->Np / 512 > 0 ? c->Np / 512 : 1;
+  const int chunk = 0;                               // (unused: super-stages are interleaved across the splits)
   const uint32_t col_a = (uint32_t)round_up(s->NBa, 32);
-  k_tc_pass_a<<<dim3(tiles, splits), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
+  const int bsa = pa_ring(s->NBa);
+  k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa, bsa), st>>>(
       s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw, chunk,
-      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0);
+      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0, bsa, getenv("PYRHE_TC_DEBUG_SKIPA") ? atoi(getenv("PYRHE_TC_DEBUG_SKIPA")) : 0);
   RHE_LAUNCH_CHECK(c);
   if (c->cfg.n_ops == 2) {   // RHE-DOM: the same pass over the [g == 2] indicator operand
-    k_tc_pass_a<<<dim3(tiles, splits), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
+    k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa, bsa), st>>>(
         s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq,
-        c->t_raw + (size_t)m * c->R1, chunk, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1);
+        c->t_raw + (size_t)m * c->R1, chunk, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1, bsa, 0);
     RHE_LAUNCH_CHECK(c);
   }
   return RHE_OK;
@@ -918,11 +1095,11 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   if (s->MT == 2)
     k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
   else
     k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
