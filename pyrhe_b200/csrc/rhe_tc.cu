@@ -108,6 +108,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
   return r;
 }
+// One elected lane of a converged warp (the role loops run warp-uniformly so that descriptors and barrier
+// addresses live in uniform registers; only the issue itself is predicated).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -373,7 +380,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   PaSmem* sm = reinterpret_cast<PaSmem*>(packed + PA_PK * PA_PACKED);
   const uint32_t packed_s = smem_u32(packed);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   // grid = (splits, SNP tiles), split index fastest: the CTAs of one SNP tile are co-resident and CTA y takes the
   // super-stages y, y + splits, ... (512 individuals = one 128-byte line per SNP row), so at any moment the tile's
   // CTAs read `splits` adjacent lines of the same 128 rows -- DRAM pages are opened once for the whole group.
@@ -482,7 +489,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     PROF_FLUSH(16);
     tc_fence_before();
   } else if (warp == PA_DW) {
-    if (lane == 0) {                                   // TMA producer: Rq tile of sub-tile sub = 4 ss + q -> slot sub % bsa
+    {                                                  // TMA producer: Rq tile of sub-tile sub = 4 ss + q -> slot sub % bsa
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
       uint32_t bar = 0, dst = smem_u32(tileB), wait_par = 1;
       int b = 0, x = y * 512;
@@ -490,11 +497,14 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           mbar_wait_s(eb + bar, wait_par);
-          if (dbg & 1) mbar_arrive_s(fb + bar);
-          else {
-            mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
-            tma_load_2d_s(dst, &tm_rq, fb + bar, x + q * 128, 0);
+          if (elect_one()) {
+            if (dbg & 1) mbar_arrive_s(fb + bar);
+            else {
+              mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
+              tma_load_2d_s(dst, &tm_rq, fb + bar, x + q * 128, 0);
+            }
           }
+          __syncwarp();
           bar += 8; dst += (uint32_t)tileB_bytes;
           if (++b == bsa) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
         }
@@ -504,7 +514,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     // ---- MMA issue: one warp (one elected lane) per decode group, so no single thread serialises the block.
     // Every MMA accumulates (the accumulator was zeroed), hence the issuers need no mutual ordering.  Group g takes
     // the sub-tiles sub = g, g + 2, ...: ring slot sub % bsa (bsa even), TMEM A slot alternating between g and g + 2.
-    if (lane == 0) {
+    {
       const int g = warp - (PA_DW + 1);
       const uint32_t idesc = idesc_i8(128, NB, 0);
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
@@ -522,20 +532,24 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
         PROF_ADD(1);
         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)b * (uint32_t)(tileB_bytes >> 4));
         const uint32_t acol = tmem + col_a + 32u * q;
-        if (!(dbg & 2)) {
+        if (elect_one()) {
+          if (!(dbg & 2)) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
-            umma_i8_ts(tmem, acol + 8u * j, bdesc + (uint64_t)(j * 2), idesc, 1u);
+            for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
+              umma_i8_ts(tmem, acol + 8u * j, bdesc + (uint64_t)(j * 2), idesc, 1u);
+          }
+          umma_commit_s(ea + 8u * q);
+          umma_commit_s(eb + 8u * (uint32_t)b);
         }
-        umma_commit_s(ea + 8u * q);
-        umma_commit_s(eb + 8u * (uint32_t)b);
+        __syncwarp();
         PROF_ADD(2);
         b += 2;
         if (b >= bsa) { b -= bsa; ph_b ^= 1u; }
         q ^= 2u;                                       // g <-> g + 2
         if (q == (uint32_t)g) ph_a ^= 1u;
       }
-      umma_commit(&sm->acc_full);
+      if (elect_one()) umma_commit(&sm->acc_full);
+      __syncwarp();
       PROF_FLUSH(24);
     }
   }
@@ -552,6 +566,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
 #define PB_DW (4 * PB_G)
 #define PB_THREADS (32 * (PB_DW + 1 + PB_G))   // decode warps, one TMA warp, one MMA-issue warp per group
 #define PB_BS 16                  // maximum depth of the smem ring of Uq tiles (TMA); the launch picks bs <= PB_BS
+#define PB_PKG 3                  // per-warp cp.async ring depth (in the group's own stages)
 #define PB_AS 2                   // shared-memory A slots per decode group (decode of tile u+1 overlaps the MMAs of tile u)
 
 #define PB_MAX_STAGES 512
@@ -648,10 +663,11 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   uint8_t* tileA = smem;
   uint8_t* tileB = tileA + PB_G * PB_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
-  PbSmem* sm = reinterpret_cast<PbSmem*>(tileB + bs * tileB_bytes);
+  uint8_t* packed = tileB + bs * tileB_bytes;     // [decode warp][PB_PKG][2 halves][32 rows][16 B]
+  PbSmem* sm = reinterpret_cast<PbSmem*>(packed + PB_DW * PB_PKG * 1024);
   const uint32_t tileA_s = smem_u32(tileA);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int i0 = blockIdx.x * (MT * 128);
 
   if (threadIdx.x == 0) {
@@ -684,52 +700,58 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const int par = g / MT, q = g % MT;
     const uint8_t* base = bed + (i0 >> 2) + q * 32;
     const int n_own = n_stage > par ? (n_stage - par + SI - 1) / SI : 0;   // stages st = par + SI * u
-    // Register rings, statically indexed by unrolling six stages: M[j % 6] = pos_meta of stage j (SNP row |
-    // fill << 24 | mode << 26, or -1 for padding), loaded five stages ahead; W[j % 3] = the 32 packed bytes of
-    // stage j, loaded three stages ahead straight into registers (the row address depends on M, so the two-stage
-    // gap between them keeps the in-order decode thread off the L2 latency).
+    // M[j % 6] = pos_meta of stage j (SNP row | fill << 24 | mode << 26, or -1 for padding), a register ring
+    // statically indexed by unrolling six stages and loaded five stages ahead.  The packed bytes travel through a
+    // per-warp cp.async ring, two stages ahead: lane pair (2 i, 2 i + 1) copies the two 16-byte halves of row
+    // 16 h + i of the warp's 32 rows (h = 0, 1), so every request is a whole 32-byte sector, and the row's owner
+    // thread reads it back after the warp has synchronised.  The row address of the pair comes from the owner's
+    // meta by shuffle.
     int M[6];
-    uint4 Wlo[3], Whi[3];
     auto meta_of = [&](int u) { return u < n_own ? __ldg(pos_meta + (par + SI * u) * 128 + t) : -1; };
-    auto fetch = [&](int meta, uint4& lo, uint4& hi) {
-      if (meta >= 0 && !(dbg & 1)) {
-        const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)(meta & 0xFFFFFF) * pitch);
-        lo = ldg_nc(p);
-        hi = ldg_nc(p + 1);
-      } else {
-        lo = make_uint4(0u, 0u, 0u, 0u);
-        hi = lo;
+    const uint32_t ring = smem_u32(packed) + (uint32_t)warp * (PB_PKG * 1024);
+    const uint32_t my_slot = ring + (uint32_t)lane * 16;                               // owner view: [half][row][16 B]
+    const uint32_t cp_dst = ring + (uint32_t)(lane & 1) * 512 + (uint32_t)(lane >> 1) * 16;   // copier view, h = 0
+    const uint8_t* cp_base = base + (lane & 1) * 16;
+    auto issue = [&](int meta, int slot) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int mrow = __shfl_sync(0xffffffffu, meta, 16 * h + (lane >> 1));
+        if (mrow >= 0 && !(dbg & 1))
+          cp_async16(cp_dst + (uint32_t)(slot * 1024 + h * 256), cp_base + (size_t)(mrow & 0xFFFFFF) * pitch);
       }
+      cp_async_commit();
     };
 #pragma unroll
     for (int j = 0; j < 5; ++j) M[j] = meta_of(j);
     M[5] = -1;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) fetch(M[j], Wlo[j], Whi[j]);
+    issue(M[0], 0);
+    issue(M[1], 1);
     const uint32_t tile0 = tileA_s + g * PB_AS * TC_TILE_A;
     uint64_t* const full0 = &sm->full_a[g * PB_AS];
     uint64_t* const empty0 = &sm->empty_a[g * PB_AS];
     PROF_T0();
-    static_assert(PB_AS == 2, "slot parity below assumes two A slots per group");
+    static_assert(PB_AS == 2 && PB_PKG == 3, "slot parity / ring indices below");
     for (int u0 = 0; u0 < n_own; u0 += 6) {
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         const int u = u0 + r;
-        if (u < n_own) {
+        if (u < n_own) {                                 // warp-uniform
           M[(r + 5) % 6] = meta_of(u + 5);
+          issue(M[(r + 2) % 6], (r + 2) % 3);            // stage u + 2
           const int meta = M[r];
           const uint32_t tab = meta >= 0 ? tc_value_table(((uint32_t)meta >> 24) & 3u, (meta >> 26) & 1) : 0u;
           const int a = r & 1;                           // u0 is even: slot = u % 2, use index u / 2
+          cp_async_wait<2>();                            // stage u has landed (u + 1, u + 2 may be in flight)
+          __syncwarp();
+          const uint4 lo = lds128(my_slot + (r % 3) * 1024), hi = lds128(my_slot + (r % 3) * 1024 + 512);
           PROF_ADD(0);
-          mbar_wait(empty0 + a, ((u >> 1) & 1) ^ 1);
+          if (!(dbg & 128)) mbar_wait(empty0 + a, ((u >> 1) & 1) ^ 1);
           PROF_ADD(1);
-          if (!(dbg & 2)) tc_store_row(tile0 + a * TC_TILE_A, t, Wlo[r % 3], Whi[r % 3], tab);
+          if (!(dbg & 2)) tc_store_row(tile0 + a * TC_TILE_A, t, lo, hi, tab);
           PROF_ADD(2);
-          fetch(M[(r + 3) % 6], Wlo[r % 3], Whi[r % 3]);
-          PROF_ADD(3);
           fence_proxy_async();
           __syncwarp();                                  // every lane's rows are fenced: one arrival per warp
-          if (lane == 0) mbar_arrive(full0 + a);
+          if (lane == 0 && !(dbg & 128)) mbar_arrive(full0 + a);
           PROF_ADD(4);
         }
       }
@@ -749,17 +771,20 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     PROF_FLUSH(0);
     tc_fence_before();
   } else if (warp == PB_DW) {
-    if (lane == 0) {                                   // TMA producer: Uq tile of stage st -> ring slot st % bs
+    {                                                  // TMA producer: Uq tile of stage st -> ring slot st % bs
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
       uint32_t bar = 0, dst = smem_u32(tileB), wait_par = 1;
       int b = 0;
-      for (int st = 0; st < n_stage; ++st) {
+      for (int st = 0; st < n_stage; ++st) {           // the whole warp runs the loop; one elected lane issues
         mbar_wait_s(eb + bar, wait_par);
-        if (dbg & 8) mbar_arrive_s(fb + bar);
-        else {
-          mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
-          tma_load_2d_s(dst, &tm_uq, fb + bar, st * 128, 0);
+        if (elect_one()) {
+          if (dbg & 8) mbar_arrive_s(fb + bar);
+          else {
+            mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
+            tma_load_2d_s(dst, &tm_uq, fb + bar, st * 128, 0);
+          }
         }
+        __syncwarp();
         bar += 8; dst += (uint32_t)tileB_bytes;
         if (++b == bs) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
       }
@@ -767,7 +792,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   } else {
     // ---- MMA issue: one warp (one elected lane) per decode group (par, q); all MMAs accumulate into zeroed TMEM.
     // The loop is one thread's dependent-latency chain: slot indices, parities and descriptors advance incrementally.
-    if (lane == 0) {
+    {
       const int g = warp - (PB_DW + 1);
       const int par = g / MT, q = g % MT;
       const uint32_t idesc = idesc_i8(128, NC, a_major);   // A is MN-major: 128 individuals contiguous per SNP row
@@ -788,24 +813,29 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
         PROF_ADD(0);
         mbar_wait_s(fb + 8u * (uint32_t)b, ph_b);
         PROF_ADD(1);
-        mbar_wait_s(fa + 8u * a, ph_a);
+        if (!(dbg & 128)) mbar_wait_s(fa + 8u * a, ph_a);
         PROF_ADD(2);
         tc_fence_after();
         const uint32_t dcol = dq + k * (uint32_t)(MT * NC);
         const uint64_t adesc = adesc0 + (uint64_t)(a * (TC_TILE_A >> 4));
         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)b * (uint32_t)(tileB_bytes >> 4));
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
-          if (j < ksteps) umma_i8(dcol, adesc + (uint64_t)(j * 256), bdesc + (uint64_t)(j * 2), idesc, 1u);
-        if (dbg & 64) { mbar_arrive_s(ea + 8u * a); mbar_arrive_s(eb + 8u * (uint32_t)b); }
-        else { umma_commit_s(ea + 8u * a); umma_commit_s(eb + 8u * (uint32_t)b); }
+          for (int j = 0; j < 4; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
+            if (j < ksteps) umma_i8(dcol, adesc + (uint64_t)(j * 256), bdesc + (uint64_t)(j * 2), idesc, 1u);
+          if (dbg & 128) { mbar_arrive_s(eb + 8u * (uint32_t)b); }
+          else if (dbg & 64) { mbar_arrive_s(ea + 8u * a); mbar_arrive_s(eb + 8u * (uint32_t)b); }
+          else { umma_commit_s(ea + 8u * a); umma_commit_s(eb + 8u * (uint32_t)b); }
+        }
+        __syncwarp();
         PROF_ADD(3);
         b += SI;
         if (b >= bs) { b -= bs; ph_b ^= 1u; }
         a ^= 1u;
         if (a == 0u) ph_a ^= 1u;
       }
-      umma_commit(&sm->acc_full);
+      if (elect_one()) umma_commit(&sm->acc_full);
+      __syncwarp();
       PROF_FLUSH(8);
     }
   }
@@ -912,7 +942,7 @@ static inline int pa_ring(int nb) {
   if (env && atoi(env) >= 4 && atoi(env) <= bsa) bsa = atoi(env) / 2 * 2;
   return bsa;
 }
-static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + (int)sizeof(PbSmem) + 1024; }
+static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_DW * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
 // The Uq ring depth must be a multiple of the stage interleave (4 / MT): consecutive uses of one slot are then
 // consumed by the same issuer, which keeps every waiter within one mbarrier phase of its barrier.
 // The TMA producer refills a slot only after the MMAs that read it have completed, so the ring depth is the
