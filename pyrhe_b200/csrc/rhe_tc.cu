@@ -74,6 +74,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // Bounded spin: a protocol bug traps (sticky launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     uint32_t ok;
     asm volatile(
@@ -93,6 +94,7 @@ __device__ __forceinline__ void mbar_expect_tx_s(uint32_t addr, uint32_t bytes) 
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_s(uint32_t addr, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     uint32_t ok;
     asm volatile(

@@ -168,3 +168,45 @@ def test_tcgen05_eight_bins_wide_weight_groups(model):
     np.testing.assert_allclose(b[1], a[1], rtol=0, atol=1e-5 * np.abs(a[1]).max())
     np.testing.assert_allclose(b[0]["XX"], a[0]["XX"], rtol=1e-5, atol=1e-7 * np.abs(a[0]["XX"]).max())
     np.testing.assert_allclose(b[0]["G_blk"], a[0]["G_blk"], rtol=1e-5, atol=1e-6 * np.abs(a[0]["G_blk"]).max())
+
+
+EDGE_SHAPES = [
+    # N,   M,   K, B, J, C, missing, dropped individuals, impute, model
+    (130,  257, 1, 3, 2, 0, 0.00, (),            "mean",   "rhe"),       # one bin, ragged last block, N % 16 != 0
+    (515,  300, 3, 5, 3, 2, 0.20, (0, 7, 514),   "binary", "rhe"),       # heavy missingness, first/last individual dropped
+    (1000, 96,  4, 2, 4, 1, 0.01, (),            "binary", "rhe"),       # 24 SNPs per block: far fewer rows than one 128-row stage
+    (777,  640, 2, 4, 5, 3, 0.02, (100, 101),    "mean",   "rhe_dom"),   # dominance operand with covariates
+    (640,  512, 2, 3, 4, 2, 0.01, (),            "binary", "genie"),     # G + GxE + NxE
+]
+
+
+@pytest.mark.parametrize("path", [0, TC])
+@pytest.mark.parametrize("shape", EDGE_SHAPES, ids=[f"N{s[0]}_M{s[1]}_K{s[2]}_{s[9]}" for s in EDGE_SHAPES])
+def test_edge_shapes_match_cpu_oracle(shape, path):
+    """Ragged / tiny / heavily-missing inputs through both kernel paths against the CPU oracle (T, q within 1e-5)."""
+    from oracle import rhe_oracle
+    from pyrhe_b200 import synth
+    N, M, K, B, J, C, miss, dropped, impute, model = shape
+    rng = np.random.default_rng(N * 7 + M)
+    counts = synth.random_counts(N, M, rng, missing_rate=miss)
+    annot = synth.random_annot(M, K, rng)
+    if K > 1:
+        annot[: M // J] = 0
+        annot[: M // J, 0] = 1                      # the first block has SNPs of bin 0 only: empty bins in a block
+    packed = synth.pack_counts(counts)
+    n_kept = N - len(dropped)
+    Z = rng.standard_normal((n_kept, B))
+    W = rng.standard_normal((n_kept, C)) if C else None
+    y = rng.standard_normal((n_kept, 1))
+    y -= y.mean()
+    env = (rng.random(n_kept) < 0.4).astype(np.float64) if model == "genie" else None
+    prob = rhe_oracle.OracleProblem(packed=packed, n_indv_original=N, annot=annot, Z=Z, y=y, num_jack=J, W=W,
+                                    impute=impute, seed=3, model=model, missing_indv=tuple(dropped), env=env)
+    ref = rhe_oracle.run(prob)
+    plan = plan_for(prob)
+    eng, ht, _ = make_engine(prob, plan, kernel_path=path)
+    pieces = eng.run()
+    eng.close()
+    T, q = assemble_all(plan, ht, pieces, J)
+    np.testing.assert_allclose(T, ref["T"], rtol=1e-5, atol=1e-6 * np.abs(ref["T"]).max())
+    np.testing.assert_allclose(q, ref["q"], rtol=1e-5, atol=1e-6 * np.abs(ref["q"]).max())
