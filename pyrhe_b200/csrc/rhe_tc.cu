@@ -354,47 +354,51 @@ extern "C" void rhe_tc_prof_dump() {
 #endif
 
 // ------------------------------------------------------------------------------------------ pass A
-// grid = (SNP tiles of 128, splits over individuals).  t_raw[s][c] += dq[c] * sum_i g_is * q_ic  (exact).
-// Two groups of four decode warps; group g expands sub-tiles q = g, g + 2 of every 512-individual super-stage
-// into TMEM A slot q.
-#define PA_G 2
+// grid = (splits over individuals, SNP tiles of 128).  t_raw[s][c] += dq[c] * sum_i g_is * q_ic  (exact).
+// The CTA owns the super-stages ss = y + splits * k (512 individuals = one 128-byte line of each of its 128 SNP
+// rows).  The producer warp brings every super-stage in with ONE 2-D TMA box (128 rows x 128 B, 128-byte swizzle)
+// and the four Rq tiles that go with it; no decode thread issues a global load.  The 4 n_ss sub-tiles (128
+// individuals) are taken round-robin by PA_G groups of four decode warps (group g: j = g, g + PA_G, ...), each
+// expanding its sub-tile into one of the group's two TMEM A slots.  512 threads x 64 registers x 2 CTAs per SM.
+#define PA_G 3
 #define PA_DW (4 * PA_G)
 #define PA_THREADS (32 * (PA_DW + 1 + PA_G))   // decode warps, one TMA warp, one MMA-issue warp per group
-#define PA_AS 4                   // TMEM A slots (32 columns each) = sub-tiles of one super-stage
-#define PA_BS 8                   // maximum depth of the smem ring of Rq tiles (TMA); the launch picks bsa <= PA_BS
-#define PA_PK 4                   // cp.async ring of packed super-stages (128 rows x 128 B)
+#define PA_AS (2 * PA_G)          // TMEM A slots (32 columns each): two per group
+#define PA_BS 6                   // maximum depth of the smem ring of Rq tiles (TMA); the launch picks a multiple of PA_G
+#define PA_GS 4                   // smem ring of packed super-stages (128 rows x 128 B each)
+#define PA_LEAD 2                 // super-stages by which the genotype boxes run ahead of the Rq tiles
 #define PA_PACKED (128 * 128)
 
 struct PaSmem {
-  uint64_t full_a[PA_AS], empty_a[PA_AS], full_b[PA_BS], empty_b[PA_BS], acc_full;
+  uint64_t full_a[PA_AS], empty_a[PA_AS], full_b[PA_BS], empty_b[PA_BS], full_g[PA_GS], empty_g[PA_GS], acc_full;
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(PA_THREADS, PA_G == 2 ? 2 : 1)
-k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict__ bed, int pitch, int m, int Np,
+__global__ void __launch_bounds__(PA_THREADS, 2)
+k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ CUtensorMap tm_bed, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
-            double* __restrict__ t_raw, int chunk, uint32_t tmem_cols, uint32_t col_a, int mode, int bsa, int dbg) {
+            double* __restrict__ t_raw, uint32_t tmem_cols, uint32_t col_a, int mode, int bsa, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* tileB = smem;
+  uint8_t* packed = smem;                            // [PA_GS][128 rows][128 B], 128-byte swizzle
+  uint8_t* tileB = packed + PA_GS * PA_PACKED;
   const int tileB_bytes = NB * 128;
-  uint8_t* packed = tileB + bsa * tileB_bytes;
-  PaSmem* sm = reinterpret_cast<PaSmem*>(packed + PA_PK * PA_PACKED);
+  PaSmem* sm = reinterpret_cast<PaSmem*>(tileB + bsa * tileB_bytes);
   const uint32_t packed_s = smem_u32(packed);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
-  // grid = (splits, SNP tiles), split index fastest: the CTAs of one SNP tile are co-resident and CTA y takes the
-  // super-stages y, y + splits, ... (512 individuals = one 128-byte line per SNP row), so at any moment the tile's
-  // CTAs read `splits` adjacent lines of the same 128 rows -- DRAM pages are opened once for the whole group.
+  // split index fastest: the CTAs of one SNP tile are co-resident and read adjacent lines of the same 128 rows
   const int snp0 = blockIdx.y * 128;
   const int splits = gridDim.x, y = blockIdx.x;
   const int total_ss = Np >> 9;
-  const int n_ss = total_ss > y ? (total_ss - y + splits - 1) / splits : 0;   // super-stages of 512 individuals
+  const int n_ss = total_ss > y ? (total_ss - y + splits - 1) / splits : 0;   // super-stages of this CTA
   if (n_ss <= 0) return;
+  const int n_sub = 4 * n_ss;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PA_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
     for (int s = 0; s < bsa; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
+    for (int s = 0; s < PA_GS; ++s) { mbar_init(&sm->full_g[s], 1); mbar_init(&sm->empty_g[s], 16); } // 4 sub-tiles x 4 warps
     mbar_init(&sm->acc_full, PA_G);
     fence_barrier_init();
   }
@@ -410,41 +414,37 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
   tc_fence_after();
 
   if (warp < PA_DW) {
-    const int t = threadIdx.x & 127, g = warp >> 2;
+    const int t = (warp & 3) * 32 + lane, g = warp >> 2;
     const int s = min(snp0 + t, m - 1);
     const uint32_t tab = tc_value_table(fill[s], mode);
-    const uint8_t* src = bed + (size_t)s * pitch + (size_t)y * 128;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    // group g fetches only the chunks of its own sub-tiles (q = g, g + 2 -> chunks 2q, 2q + 1)
-    auto issue = [&](int ss) {
-      const uint32_t slot = packed_s + (ss % PA_PK) * PA_PACKED + t * 16;
-      const uint8_t* p = src + (size_t)ss * splits * 128;
-      if (dbg & 4) return;
-#pragma unroll
-      for (int q = 0; q < 4; q += PA_G) {
-        const int c = 2 * (q + g);
-        cp_async16(slot + c * 2048, p + c * 16);
-        cp_async16(slot + (c + 1) * 2048, p + (c + 1) * 16);
-      }
+    const uint32_t row_s = packed_s + (uint32_t)t * 128;      // this thread's SNP row inside a staged box
+    const uint32_t sw = (uint32_t)(t & 7);                      // 128-byte swizzle: 16-byte chunk c sits at c ^ (row & 7)
+    const int n_own = n_sub > g ? (n_sub - g + PA_G - 1) / PA_G : 0;     // own sub-tiles j = g + PA_G * jj
+    PROF_T0();
+    // packed words of sub-tile j = 4 k + q: chunks 2 q, 2 q + 1 of the row in ring slot k % PA_GS
+    auto fetch = [&](int j, uint4& lo, uint4& hi) {
+      const int k = j >> 2, q = j & 3;
+      mbar_wait(&sm->full_g[k & (PA_GS - 1)], (uint32_t)(k / PA_GS) & 1u);
+      const uint32_t base = row_s + (uint32_t)(k & (PA_GS - 1)) * PA_PACKED;
+      lo = lds128(base + (((uint32_t)(2 * q) ^ sw) << 4));
+      hi = lds128(base + (((uint32_t)(2 * q + 1) ^ sw) << 4));
     };
-#pragma unroll
-    for (int pre = 0; pre < PA_PK - 1; ++pre) {
-      if (pre < n_ss) issue(pre);
-      cp_async_commit();
-    }
     // Software pipeline: the packed words of the next sub-tile are read from the ring before the current one is
     // expanded, and each sub-tile goes to TMEM as two 16-column stores so that the first store overlaps the
-    // expansion of the second half.
-    static_assert(PA_G == 2, "two sub-tiles per group and super-stage");
-    PROF_T0();
-    auto put = [&](int q, int ss, const uint4& lo, const uint4& hi) {
+    // expansion of the second half.  The ring slot is released once the words are in registers (consumed).
+    auto put = [&](uint32_t slot_a, uint32_t parity, const uint4& lo, const uint4& hi, int k) {
       uint4 r[4];
       PROF_ADD(0);
-      mbar_wait(&sm->empty_a[q], (ss & 1) ^ 1);
+      mbar_wait(&sm->empty_a[slot_a], parity ^ 1u);
       tc_fence_after();
       PROF_ADD(1);
-      const uint32_t dst = lane_base + col_a + 32 * q;
-      if (dbg & 8) { if (lane == 0) mbar_arrive(&sm->full_a[q]); return; }
+      const uint32_t dst = lane_base + col_a + 32u * slot_a;
+      if (dbg & 8) {
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&sm->empty_g[k & (PA_GS - 1)]); mbar_arrive(&sm->full_a[slot_a]); }
+        return;
+      }
       r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
       tmem_st16(dst, r);
       uint4 r2[4];
@@ -454,25 +454,21 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();                                    // every lane's stores are complete and fenced: one arrival per warp
-      if (lane == 0) mbar_arrive(&sm->full_a[q]);
+      if (lane == 0) { mbar_arrive(&sm->empty_g[k & (PA_GS - 1)]); mbar_arrive(&sm->full_a[slot_a]); }
       PROF_ADD(3);
     };
-    cp_async_wait<PA_PK - 2>();
-    uint32_t slot = packed_s + t * 16;
-    uint4 lo = lds128(slot + (2 * g) * 2048), hi = lds128(slot + (2 * g + 1) * 2048);
-    for (int ss = 0; ss < n_ss; ++ss) {
-      if (ss + PA_PK - 1 < n_ss) issue(ss + PA_PK - 1);
-      cp_async_commit();
-      const uint4 lo2 = lds128(slot + (2 * g + 4) * 2048), hi2 = lds128(slot + (2 * g + 5) * 2048);
-      put(g, ss, lo, hi);
-      cp_async_wait<PA_PK - 2>();                      // super-stage ss + 1 has landed
+    uint4 lo, hi;
+    if (n_own > 0) fetch(g, lo, hi);
+    for (int jj = 0; jj < n_own; ++jj) {
+      const int j = g + PA_G * jj;
+      uint4 nlo = lo, nhi = hi;
+      if (jj + 1 < n_own) fetch(j + PA_G, nlo, nhi);
       PROF_ADD(4);
-      slot = packed_s + ((ss + 1) % PA_PK) * PA_PACKED + t * 16;
-      lo = lds128(slot + (2 * g) * 2048);
-      hi = lds128(slot + (2 * g + 1) * 2048);
-      put(g + 2, ss, lo2, hi2);
+      put((uint32_t)(2 * g + (jj & 1)), (uint32_t)(jj >> 1) & 1u, lo, hi, j >> 2);
+      lo = nlo;
+      hi = nhi;
     }
-    // ---- epilogue: lane quadrant (warp & 3) of TMEM, row = SNP; the two groups split the columns
+    // ---- epilogue: lane quadrant (warp & 3) of TMEM, row = SNP; the groups split the columns
     PROF_ADD(0);
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
@@ -491,64 +487,83 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const uint8_t* __restrict
     PROF_FLUSH(16);
     tc_fence_before();
   } else if (warp == PA_DW) {
-    {                                                  // TMA producer: Rq tile of sub-tile sub = 4 ss + q -> slot sub % bsa
+    {
+      // TMA producer (the whole warp runs the loop; one elected lane issues).  Step k brings in the genotype box of
+      // super-stage k and the four Rq tiles of super-stage k - PA_LEAD: the large boxes run ahead of the small ones.
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
+      const uint32_t fg = smem_u32(&sm->full_g[0]), eg = smem_u32(&sm->empty_g[0]);
       uint32_t bar = 0, dst = smem_u32(tileB), wait_par = 1;
-      int b = 0, x = y * 512;
-      for (int ss = 0; ss < n_ss; ++ss, x += splits * 512) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          mbar_wait_s(eb + bar, wait_par);
+      int b = 0;
+      for (int k = 0; k < n_ss + PA_LEAD; ++k) {
+        if (k < n_ss) {
+          const uint32_t sg = (uint32_t)k & (PA_GS - 1);
+          mbar_wait_s(eg + 8u * sg, ((uint32_t)(k / PA_GS) & 1u) ^ 1u);
           if (elect_one()) {
-            if (dbg & 1) mbar_arrive_s(fb + bar);
+            if (dbg & 4) mbar_arrive_s(fg + 8u * sg);
             else {
-              mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
-              tma_load_2d_s(dst, &tm_rq, fb + bar, x + q * 128, 0);
+              mbar_expect_tx_s(fg + 8u * sg, PA_PACKED);
+              tma_load_2d_s(packed_s + sg * PA_PACKED, &tm_bed, fg + 8u * sg, (y + splits * k) * 128, snp0);
             }
           }
           __syncwarp();
-          bar += 8; dst += (uint32_t)tileB_bytes;
-          if (++b == bsa) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
+        }
+        if (k >= PA_LEAD) {
+          const int x = (y + splits * (k - PA_LEAD)) * 512;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mbar_wait_s(eb + bar, wait_par);
+            if (elect_one()) {
+              if (dbg & 1) mbar_arrive_s(fb + bar);
+              else {
+                mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
+                tma_load_2d_s(dst, &tm_rq, fb + bar, x + q * 128, 0);
+              }
+            }
+            __syncwarp();
+            bar += 8; dst += (uint32_t)tileB_bytes;
+            if (++b == bsa) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
+          }
         }
       }
     }
   } else {
-    // ---- MMA issue: one warp (one elected lane) per decode group, so no single thread serialises the block.
+    // ---- MMA issue: one warp per decode group (one elected lane issues), so no single thread serialises the block.
     // Every MMA accumulates (the accumulator was zeroed), hence the issuers need no mutual ordering.  Group g takes
-    // the sub-tiles sub = g, g + 2, ...: ring slot sub % bsa (bsa even), TMEM A slot alternating between g and g + 2.
+    // the sub-tiles j = g, g + PA_G, ...: ring slot j % bsa (bsa is a multiple of PA_G, so a slot always belongs to
+    // the same group), TMEM A slot alternating between 2 g and 2 g + 1.
     {
       const int g = warp - (PA_DW + 1);
       const uint32_t idesc = idesc_i8(128, NB, 0);
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
-      const uint32_t fa = smem_u32(&sm->full_a[0]), ea = smem_u32(&sm->empty_a[0]);
+      const uint32_t fa = smem_u32(&sm->full_a[2 * g]), ea = smem_u32(&sm->empty_a[2 * g]);
       const uint64_t bdesc0 = smem_desc_sw128(smem_u32(tileB), 16, 1024);
+      const int n_own = n_sub > g ? (n_sub - g + PA_G - 1) / PA_G : 0;
       PROF_T0();
       int b = g;
-      uint32_t ph_b = 0, ph_a = 0, q = (uint32_t)g;
-      const int n_sub = 2 * n_ss;
-      for (int n = 0; n < n_sub; ++n) {
+      uint32_t ph_b = 0, ph_a = 0, q = 0;
+      for (int jj = 0; jj < n_own; ++jj) {
         mbar_wait_s(fb + 8u * (uint32_t)b, ph_b);
         PROF_ADD(0);
         mbar_wait_s(fa + 8u * q, ph_a);
         tc_fence_after();
         PROF_ADD(1);
         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)b * (uint32_t)(tileB_bytes >> 4));
-        const uint32_t acol = tmem + col_a + 32u * q;
+        const uint32_t acol = tmem + col_a + 32u * (2u * (uint32_t)g + q);
         if (elect_one()) {
           if (!(dbg & 2)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
               umma_i8_ts(tmem, acol + 8u * j, bdesc + (uint64_t)(j * 2), idesc, 1u);
           }
-          umma_commit_s(ea + 8u * q);
-          umma_commit_s(eb + 8u * (uint32_t)b);
+          if (dbg & 16) { mbar_arrive_s(ea + 8u * q); mbar_arrive_s(eb + 8u * (uint32_t)b); }
+          else { umma_commit_s(ea + 8u * q); umma_commit_s(eb + 8u * (uint32_t)b); }
         }
         __syncwarp();
         PROF_ADD(2);
-        b += 2;
+        b += PA_G;
         if (b >= bsa) { b -= bsa; ph_b ^= 1u; }
-        q ^= 2u;                                       // g <-> g + 2
-        if (q == (uint32_t)g) ph_a ^= 1u;
+        q ^= 1u;
+        if (q == 0u) ph_a ^= 1u;
       }
       if (elect_one()) umma_commit(&sm->acc_full);
       __syncwarp();
@@ -933,15 +948,12 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
-static inline int pa_smem_bytes(int nb, int bsa) { return bsa * nb * 128 + PA_PK * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
-// Deepest Rq ring (the look-ahead that hides the TMA round trip) that still lets two CTAs share an SM.  The depth
-// stays even: sub-tile `sub` belongs to group sub % 2, so every slot is then always consumed by the same group and
-// no waiter can be two mbarrier phases away from its barrier (parity aliasing).
+static inline int pa_smem_bytes(int nb, int bsa) { return bsa * nb * 128 + PA_GS * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
+// Rq ring depth: a multiple of PA_G (sub-tile j belongs to group j % PA_G, so every slot is then always consumed by
+// the same group and no waiter can be two mbarrier phases away from its barrier), as deep as lets two CTAs share an SM.
 static inline int pa_ring(int nb) {
   int bsa = PA_BS;
-  while (bsa > 4 && pa_smem_bytes(nb, bsa) > 233472 / 2 - 1024) bsa -= 2;
-  const char* env = getenv("PYRHE_TC_DEBUG_RINGA");
-  if (env && atoi(env) >= 4 && atoi(env) <= bsa) bsa = atoi(env) / 2 * 2;
+  while (bsa > PA_G && pa_smem_bytes(nb, bsa) > 233472 / 2 - 1024) bsa -= PA_G;
   return bsa;
 }
 static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_DW * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
@@ -1024,7 +1036,7 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
   const int tiles = rhe_div_up(m, 128);
   // Split the individuals so that the grid fills whole waves of 2 resident CTAs per SM (a nearly empty last wave
-  // costs a full CTA time): pick the split count with the best wave efficiency, keeping at least 16 super-stages
+  // costs a full CTA time): pick the split count with the best wave efficiency, keeping at least 64 sub-tiles
   // (8192 individuals) per CTA so that prologue / epilogue stay amortised.
   const int slots = 148 * 2;
   int splits = 1;
@@ -1036,17 +1048,20 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
     if (eff > best + 0.02) { best = eff; splits = cand; }
   }
   if (splits > c->Np / 512) splits = c->Np / 512 > 0 ? c->Np / 512 : 1;
-  const int chunk = 0;                               // (unused: super-stages are interleaved across the splits)
   const uint32_t col_a = (uint32_t)round_up(s->NBa, 32);
   const int bsa = pa_ring(s->NBa);
+  CUtensorMap tm_bed;                                  // the block's packed rows as a 2-D byte tensor [m][pitch]
+  int rc = tc_encode_2d(s, &tm_bed, const_cast<uint8_t*>(bed), (uint64_t)c->cfg.pitch_bytes, (uint64_t)m, 128);
+  if (rc) return rc;
+  const int dbg = getenv("PYRHE_TC_DEBUG_SKIPA") ? atoi(getenv("PYRHE_TC_DEBUG_SKIPA")) : 0;
   k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa, bsa), st>>>(
-      s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw, chunk,
-      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0, bsa, getenv("PYRHE_TC_DEBUG_SKIPA") ? atoi(getenv("PYRHE_TC_DEBUG_SKIPA")) : 0);
+      s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw,
+      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0, bsa, dbg);
   RHE_LAUNCH_CHECK(c);
   if (c->cfg.n_ops == 2) {   // RHE-DOM: the same pass over the [g == 2] indicator operand
     k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa, bsa), st>>>(
-        s->tm_rq, bed, c->cfg.pitch_bytes, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq,
-        c->t_raw + (size_t)m * c->R1, chunk, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1, bsa, 0);
+        s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq,
+        c->t_raw + (size_t)m * c->R1, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1, bsa, 0);
     RHE_LAUNCH_CHECK(c);
   }
   return RHE_OK;
