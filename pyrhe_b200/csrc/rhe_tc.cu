@@ -362,15 +362,14 @@ extern "C" void rhe_tc_prof_dump() {
 // expanding its sub-tile into one of the group's two TMEM A slots.  512 threads x 64 registers x 2 CTAs per SM.
 #define PA_G 3
 #define PA_DW (4 * PA_G)
-#define PA_THREADS (32 * (PA_DW + 1 + PA_G))   // decode warps, one TMA warp, one MMA-issue warp per group
+#define PA_THREADS (32 * (PA_DW + 2 + PA_G))   // decode warps, two TMA warps (Rq tiles, genotype boxes), one MMA-issue warp per group
 #define PA_AS (2 * PA_G)          // TMEM A slots (32 columns each): two per group
-#define PA_BS 6                   // maximum depth of the smem ring of Rq tiles (TMA); the launch picks a multiple of PA_G
-#define PA_GS 4                   // smem ring of packed super-stages (128 rows x 128 B each)
-#define PA_LEAD 2                 // super-stages by which the genotype boxes run ahead of the Rq tiles
+#define PA_RS 2                   // smem ring of Rq super-stages (four NB x 128 B tiles each, one barrier pair per slot)
+#define PA_GS 3                   // smem ring of packed super-stages (128 rows x 128 B each)
 #define PA_PACKED (128 * 128)
 
 struct PaSmem {
-  uint64_t full_a[PA_AS], empty_a[PA_AS], full_b[PA_BS], empty_b[PA_BS], full_g[PA_GS], empty_g[PA_GS], acc_full;
+  uint64_t full_a[PA_AS], empty_a[PA_AS], full_b[PA_RS], empty_b[PA_RS], full_g[PA_GS], empty_g[PA_GS], acc_full;
   uint32_t tmem_base;
 };
 
@@ -383,7 +382,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
   uint8_t* packed = smem;                            // [PA_GS][128 rows][128 B], 128-byte swizzle
   uint8_t* tileB = packed + PA_GS * PA_PACKED;
   const int tileB_bytes = NB * 128;
-  PaSmem* sm = reinterpret_cast<PaSmem*>(tileB + bsa * tileB_bytes);
+  PaSmem* sm = reinterpret_cast<PaSmem*>(tileB + PA_RS * 4 * tileB_bytes);
   const uint32_t packed_s = smem_u32(packed);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
@@ -397,12 +396,12 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PA_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
-    for (int s = 0; s < bsa; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 1); }
+    for (int s = 0; s < PA_RS; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], 4); }           // 4 sub-tiles
     for (int s = 0; s < PA_GS; ++s) { mbar_init(&sm->full_g[s], 1); mbar_init(&sm->empty_g[s], 16); } // 4 sub-tiles x 4 warps
     mbar_init(&sm->acc_full, PA_G);
     fence_barrier_init();
   }
-  if (warp == PA_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
+  if (warp == PA_DW + 2) tmem_alloc(&sm->tmem_base, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -424,9 +423,9 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
     PROF_T0();
     // packed words of sub-tile j = 4 k + q: chunks 2 q, 2 q + 1 of the row in ring slot k % PA_GS
     auto fetch = [&](int j, uint4& lo, uint4& hi) {
-      const int k = j >> 2, q = j & 3;
-      mbar_wait(&sm->full_g[k & (PA_GS - 1)], (uint32_t)(k / PA_GS) & 1u);
-      const uint32_t base = row_s + (uint32_t)(k & (PA_GS - 1)) * PA_PACKED;
+      const int k = j >> 2, q = j & 3, sg = k % PA_GS;
+      mbar_wait(&sm->full_g[sg], (uint32_t)(k / PA_GS) & 1u);
+      const uint32_t base = row_s + (uint32_t)sg * PA_PACKED;
       lo = lds128(base + (((uint32_t)(2 * q) ^ sw) << 4));
       hi = lds128(base + (((uint32_t)(2 * q + 1) ^ sw) << 4));
     };
@@ -442,7 +441,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
       const uint32_t dst = lane_base + col_a + 32u * slot_a;
       if (dbg & 8) {
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&sm->empty_g[k & (PA_GS - 1)]); mbar_arrive(&sm->full_a[slot_a]); }
+        if (lane == 0) { mbar_arrive(&sm->empty_g[k % PA_GS]); mbar_arrive(&sm->full_a[slot_a]); }
         return;
       }
       r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
@@ -454,7 +453,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();                                    // every lane's stores are complete and fenced: one arrival per warp
-      if (lane == 0) { mbar_arrive(&sm->empty_g[k & (PA_GS - 1)]); mbar_arrive(&sm->full_a[slot_a]); }
+      if (lane == 0) { mbar_arrive(&sm->empty_g[k % PA_GS]); mbar_arrive(&sm->full_a[slot_a]); }
       PROF_ADD(3);
     };
     uint4 lo, hi;
@@ -487,43 +486,40 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
     PROF_FLUSH(16);
     tc_fence_before();
   } else if (warp == PA_DW) {
-    {
-      // TMA producer (the whole warp runs the loop; one elected lane issues).  Step k brings in the genotype box of
-      // super-stage k and the four Rq tiles of super-stage k - PA_LEAD: the large boxes run ahead of the small ones.
+    {                                                  // TMA producer 1: the four Rq tiles of super-stage k -> slot k % PA_RS
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
-      const uint32_t fg = smem_u32(&sm->full_g[0]), eg = smem_u32(&sm->empty_g[0]);
-      uint32_t bar = 0, dst = smem_u32(tileB), wait_par = 1;
-      int b = 0;
-      for (int k = 0; k < n_ss + PA_LEAD; ++k) {
-        if (k < n_ss) {
-          const uint32_t sg = (uint32_t)k & (PA_GS - 1);
-          mbar_wait_s(eg + 8u * sg, ((uint32_t)(k / PA_GS) & 1u) ^ 1u);
-          if (elect_one()) {
-            if (dbg & 4) mbar_arrive_s(fg + 8u * sg);
-            else {
-              mbar_expect_tx_s(fg + 8u * sg, PA_PACKED);
-              tma_load_2d_s(packed_s + sg * PA_PACKED, &tm_bed, fg + 8u * sg, (y + splits * k) * 128, snp0);
-            }
-          }
-          __syncwarp();
-        }
-        if (k >= PA_LEAD) {
-          const int x = (y + splits * (k - PA_LEAD)) * 512;
+      const uint32_t tileB_s = smem_u32(tileB);
+      static_assert(PA_RS == 2, "slot = k & 1, use = k >> 1");
+      for (int k = 0; k < n_ss; ++k) {                 // the whole warp runs the loop; one elected lane issues
+        const uint32_t sl = (uint32_t)k & 1u;
+        mbar_wait_s(eb + 8u * sl, (((uint32_t)k >> 1) & 1u) ^ 1u);
+        if (elect_one()) {
+          if (dbg & 1) mbar_arrive_s(fb + 8u * sl);
+          else {
+            const int x = (y + splits * k) * 512;
+            mbar_expect_tx_s(fb + 8u * sl, 4u * (uint32_t)tileB_bytes);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mbar_wait_s(eb + bar, wait_par);
-            if (elect_one()) {
-              if (dbg & 1) mbar_arrive_s(fb + bar);
-              else {
-                mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
-                tma_load_2d_s(dst, &tm_rq, fb + bar, x + q * 128, 0);
-              }
-            }
-            __syncwarp();
-            bar += 8; dst += (uint32_t)tileB_bytes;
-            if (++b == bsa) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
+            for (int q = 0; q < 4; ++q)
+              tma_load_2d_s(tileB_s + (sl * 4u + (uint32_t)q) * (uint32_t)tileB_bytes, &tm_rq, fb + 8u * sl, x + q * 128, 0);
           }
         }
+        __syncwarp();
+      }
+    }
+  } else if (warp == PA_DW + 1) {
+    {                                                  // TMA producer 2: genotype box of super-stage k -> slot k % PA_GS
+      const uint32_t fg = smem_u32(&sm->full_g[0]), eg = smem_u32(&sm->empty_g[0]);
+      for (int k = 0; k < n_ss; ++k) {
+        const uint32_t sg = (uint32_t)(k % PA_GS);
+        mbar_wait_s(eg + 8u * sg, ((uint32_t)(k / PA_GS) & 1u) ^ 1u);
+        if (elect_one()) {
+          if (dbg & 4) mbar_arrive_s(fg + 8u * sg);
+          else {
+            mbar_expect_tx_s(fg + 8u * sg, PA_PACKED);
+            tma_load_2d_s(packed_s + sg * PA_PACKED, &tm_bed, fg + 8u * sg, (y + splits * k) * 128, snp0);
+          }
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -532,36 +528,34 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
     // the sub-tiles j = g, g + PA_G, ...: ring slot j % bsa (bsa is a multiple of PA_G, so a slot always belongs to
     // the same group), TMEM A slot alternating between 2 g and 2 g + 1.
     {
-      const int g = warp - (PA_DW + 1);
+      const int g = warp - (PA_DW + 2);
       const uint32_t idesc = idesc_i8(128, NB, 0);
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
       const uint32_t fa = smem_u32(&sm->full_a[2 * g]), ea = smem_u32(&sm->empty_a[2 * g]);
       const uint64_t bdesc0 = smem_desc_sw128(smem_u32(tileB), 16, 1024);
       const int n_own = n_sub > g ? (n_sub - g + PA_G - 1) / PA_G : 0;
       PROF_T0();
-      int b = g;
-      uint32_t ph_b = 0, ph_a = 0, q = 0;
+      uint32_t ph_a = 0, q = 0;
       for (int jj = 0; jj < n_own; ++jj) {
-        mbar_wait_s(fb + 8u * (uint32_t)b, ph_b);
+        const uint32_t j = (uint32_t)(g + PA_G * jj), k = j >> 2, sl = k & 1u;     // Rq slot k % PA_RS, tile j & 3
+        mbar_wait_s(fb + 8u * sl, (k >> 1) & 1u);
         PROF_ADD(0);
         mbar_wait_s(fa + 8u * q, ph_a);
         tc_fence_after();
         PROF_ADD(1);
-        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)b * (uint32_t)(tileB_bytes >> 4));
+        const uint64_t bdesc = bdesc0 + (uint64_t)((sl * 4u + (j & 3u)) * (uint32_t)(tileB_bytes >> 4));
         const uint32_t acol = tmem + col_a + 32u * (2u * (uint32_t)g + q);
         if (elect_one()) {
           if (!(dbg & 2)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
-              umma_i8_ts(tmem, acol + 8u * j, bdesc + (uint64_t)(j * 2), idesc, 1u);
+            for (int i = 0; i < 4; ++i)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
+              umma_i8_ts(tmem, acol + 8u * i, bdesc + (uint64_t)(i * 2), idesc, 1u);
           }
-          if (dbg & 16) { mbar_arrive_s(ea + 8u * q); mbar_arrive_s(eb + 8u * (uint32_t)b); }
-          else { umma_commit_s(ea + 8u * q); umma_commit_s(eb + 8u * (uint32_t)b); }
+          if (dbg & 16) { mbar_arrive_s(ea + 8u * q); mbar_arrive_s(eb + 8u * sl); }
+          else { umma_commit_s(ea + 8u * q); umma_commit_s(eb + 8u * sl); }
         }
         __syncwarp();
         PROF_ADD(2);
-        b += PA_G;
-        if (b >= bsa) { b -= bsa; ph_b ^= 1u; }
         q ^= 1u;
         if (q == 0u) ph_a ^= 1u;
       }
@@ -571,7 +565,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
     }
   }
   __syncthreads();
-  if (warp == PA_DW + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
+  if (warp == PA_DW + 2) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------ pass B
@@ -948,14 +942,8 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
-static inline int pa_smem_bytes(int nb, int bsa) { return bsa * nb * 128 + PA_GS * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
-// Rq ring depth: a multiple of PA_G (sub-tile j belongs to group j % PA_G, so every slot is then always consumed by
-// the same group and no waiter can be two mbarrier phases away from its barrier), as deep as lets two CTAs share an SM.
-static inline int pa_ring(int nb) {
-  int bsa = PA_BS;
-  while (bsa > PA_G && pa_smem_bytes(nb, bsa) > 233472 / 2 - 1024) bsa -= PA_G;
-  return bsa;
-}
+static inline int pa_smem_bytes(int nb, int) { return PA_RS * 4 * nb * 128 + PA_GS * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
+static inline int pa_ring(int) { return PA_RS; }
 static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_DW * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
 // The Uq ring depth must be a multiple of the stage interleave (4 / MT): consecutive uses of one slot are then
 // consumed by the same issuer, which keeps every waiter within one mbarrier phase of its barrier.
