@@ -666,7 +666,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
             const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
-            uint32_t tmem_cols, int a_major, int kcap, int bs, int dbg) {
+            uint32_t tmem_cols, int a_major, int kcap, int bs, int bzsh, int dbg) {
   if (dbg & 16) n_stage = 0;
   constexpr int SI = PB_G / MT;                      // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
@@ -683,7 +683,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PB_G * PB_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
-    for (int s = 0; s < bs; ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], MT); }
+    for (int s = 0; s < (bs >> bzsh); ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], MT << bzsh); }   // one pair per batch of 2^bzsh Uq tiles
     mbar_init(&sm->acc_full, PB_G);
     fence_barrier_init();
   }
@@ -782,22 +782,27 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     PROF_FLUSH(0);
     tc_fence_before();
   } else if (warp == PB_DW) {
-    {                                                  // TMA producer: Uq tile of stage st -> ring slot st % bs
+    {
+      // TMA producer: Uq tile of stage st -> ring slot st % bs, in batches of 2^bzsh consecutive stages that share one
+      // barrier pair (one wait and one expect_tx per batch: this single thread is otherwise the CTA's serial bottleneck).
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
+      const int bz = 1 << bzsh;
       uint32_t bar = 0, dst = smem_u32(tileB), wait_par = 1;
       int b = 0;
-      for (int st = 0; st < n_stage; ++st) {           // the whole warp runs the loop; one elected lane issues
+      for (int st0 = 0; st0 < n_stage; st0 += bz) {    // the whole warp runs the loop; one elected lane issues
+        const int n_in = min(bz, n_stage - st0);
         mbar_wait_s(eb + bar, wait_par);
         if (elect_one()) {
           if (dbg & 8) mbar_arrive_s(fb + bar);
           else {
-            mbar_expect_tx_s(fb + bar, (uint32_t)tileB_bytes);
-            tma_load_2d_s(dst, &tm_uq, fb + bar, st * 128, 0);
+            mbar_expect_tx_s(fb + bar, (uint32_t)(n_in * tileB_bytes));
+            for (int i = 0; i < n_in; ++i)
+              tma_load_2d_s(dst + (uint32_t)(i * tileB_bytes), &tm_uq, fb + bar, (st0 + i) * 128, 0);
           }
         }
         __syncwarp();
-        bar += 8; dst += (uint32_t)tileB_bytes;
-        if (++b == bs) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
+        bar += 8; dst += (uint32_t)(bz * tileB_bytes); b += bz;
+        if (b == bs) { b = 0; bar = 0; dst = smem_u32(tileB); wait_par ^= 1u; }
       }
     }
   } else {
@@ -822,7 +827,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
         const int ksteps = min((int)(info >> 16), kcap);
         if (st + SI < n_stage) info = lds32(info_s + 4u * (uint32_t)(st + SI));
         PROF_ADD(0);
-        mbar_wait_s(fb + 8u * (uint32_t)b, ph_b);
+        mbar_wait_s(fb + 8u * (uint32_t)(b >> bzsh), ph_b);
         PROF_ADD(1);
         if (!(dbg & 128)) mbar_wait_s(fa + 8u * a, ph_a);
         PROF_ADD(2);
@@ -834,9 +839,10 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
 #pragma unroll
           for (int j = 0; j < 4; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
             if (j < ksteps) umma_i8(dcol, adesc + (uint64_t)(j * 256), bdesc + (uint64_t)(j * 2), idesc, 1u);
-          if (dbg & 128) { mbar_arrive_s(eb + 8u * (uint32_t)b); }
-          else if (dbg & 64) { mbar_arrive_s(ea + 8u * a); mbar_arrive_s(eb + 8u * (uint32_t)b); }
-          else { umma_commit_s(ea + 8u * a); umma_commit_s(eb + 8u * (uint32_t)b); }
+          const uint32_t ebb = eb + 8u * (uint32_t)(b >> bzsh);
+          if (dbg & 128) { mbar_arrive_s(ebb); }
+          else if (dbg & 64) { mbar_arrive_s(ea + 8u * a); mbar_arrive_s(ebb); }
+          else { umma_commit_s(ea + 8u * a); umma_commit_s(ebb); }
         }
         __syncwarp();
         PROF_ADD(3);
@@ -947,13 +953,20 @@ static inline int pa_ring(int) { return PA_RS; }
 static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_DW * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
 // The Uq ring depth must be a multiple of the stage interleave (4 / MT): consecutive uses of one slot are then
 // consumed by the same issuer, which keeps every waiter within one mbarrier phase of its barrier.
-// The TMA producer refills a slot only after the MMAs that read it have completed, so the ring depth is the
-// look-ahead that hides the TMA round trip: as deep as shared memory allows.
-static inline int pb_ring(int nc) {
+// Uq ring: `bs` tile slots in batches of 2^bzsh tiles that share one barrier pair.  Either a batch spans at least
+// one stage of every issuer (2^bzsh >= SI = 4 / MT), or there is no batching and bs is a multiple of SI (a slot is
+// then always consumed by the same issuer); both keep every waiter within one mbarrier phase of its barrier.
+static inline int pb_ring(int nc, int mt, int* bzsh) {
+  const int si = PB_G / mt;
+  const int budget = 232448 - 2048;
+  const char* env = getenv("PYRHE_TC_DEBUG_RING");       // "4": the unbatched four-slot ring
+  if (!(env && atoi(env) == 4)) {
+    if (pb_smem_bytes(nc, 8) <= budget) { *bzsh = 2; return 8; }                  // two batches of four tiles
+    if (si <= 2 && pb_smem_bytes(nc, 4) <= budget) { *bzsh = 1; return 4; }       // two batches of two tiles
+  }
+  *bzsh = 0;
   int bs = PB_BS;
-  while (bs > 4 && pb_smem_bytes(nc, bs) > 232448 - 2048) bs -= 4;
-  const char* env = getenv("PYRHE_TC_DEBUG_RING");
-  if (env && atoi(env) >= 4 && atoi(env) <= bs) bs = atoi(env) / 4 * 4;
+  while (bs > 4 && pb_smem_bytes(nc, bs) > budget) bs -= 4;
   return bs;
 }
 
@@ -992,8 +1005,8 @@ int rhe_tc_create(rhe_ctx* c) {
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa, pa_ring(s->NBa))));
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb))));
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb))));
+  { int sh; RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb, 1, &sh)))); }
+  { int sh; RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb, 2, &sh)))); }
   return RHE_OK;
 }
 
@@ -1126,15 +1139,16 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
     RHE_LAUNCH_CHECK(c);
   }
   const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
-  const int bs = pb_ring(s->NCb), smem = pb_smem_bytes(s->NCb, bs);
+  int bzsh = 0;
+  const int bs = pb_ring(s->NCb, s->MT, &bzsh), smem = pb_smem_bytes(s->NCb, bs);
   if (s->MT == 2)
     k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, bzsh, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
   else
     k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
                                                           meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
+                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, bzsh, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }

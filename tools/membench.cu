@@ -76,6 +76,27 @@ __global__ void k_mode_a(const uint8_t* __restrict__ bed, size_t pitch, int row_
   if (acc == 0x12345678u) out[0] = acc;
 }
 
+// mode W (wide pass-A pattern): CTA (y, tile) owns 128 SNP rows; per step it reads W bytes of every row, LPR = W / 128
+// threads per row each taking one 128-byte line (eight 16-byte loads), steps interleaved across the `splits` CTAs.
+__global__ void k_mode_w(const uint8_t* __restrict__ bed, size_t pitch, int row_bytes, int W, uint32_t* out) {
+  const int lpr = W / 128;
+  const int r = threadIdx.x / lpr, c = threadIdx.x % lpr;
+  const int splits = gridDim.x, y = blockIdx.x;
+  const int total = row_bytes / W;
+  const int n_step = total > y ? (total - y + splits - 1) / splits : 0;
+  const uint8_t* base = bed + (size_t)(blockIdx.y * 128 + r) * pitch + c * 128;
+  uint32_t acc = 0;
+  uint4 v[8];
+  for (int s = 0; s < n_step; ++s) {
+    const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)(y + s * splits) * W);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ldg_nc(p + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= v[i].x ^ v[i].y ^ v[i].z ^ v[i].w;
+  }
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
 template <typename F>
 static void timeit(const char* name, double bytes, F launch) {
   cudaEvent_t e0, e1;
@@ -113,7 +134,7 @@ int main() {
     snprintf(name, sizeof name, "B: window %3d B/row/CTA, D=6, %d thr", W, threads);
     timeit(name, bytes, [&]() { k_mode_b<6><<<row_bytes / W, threads>>>(next(), pitch, m, W, out); });
   }
-  for (int W : {128, 256, 512}) {
+  for (int W : {128, 256}) {
     for (int inter = 0; inter < 2; ++inter) {
       for (int splits : {4, 11, 22}) {
         const int threads = W / 32 * 128;
@@ -122,6 +143,12 @@ int main() {
       }
     }
   }
-  // streaming reference: one warp per row
+  for (int W : {128, 256, 512, 1024}) {
+    for (int splits : {11, 22}) {
+      const int threads = 128 * (W / 128);
+      snprintf(name, sizeof name, "W: %4d B/row/step (line per thread), splits %2d", W, splits);
+      timeit(name, bytes, [&]() { k_mode_w<<<dim3(splits, m / 128), threads>>>(next(), pitch, row_bytes, W, out); });
+    }
+  }
   return 0;
 }
