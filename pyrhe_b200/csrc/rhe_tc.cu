@@ -48,6 +48,7 @@ struct TcState {
   int Bp = 0;           // pass-B columns rounded up to 2
   int NCb = 0;          // pass B MMA N per (bin, M-tile) = round16(L * Bp)
   int MT = 2;           // 128-individual M-tiles per pass-B CTA
+  int G = 4;            // pass-B decode groups per CTA: 4 (one CTA per SM) or 2 (two co-resident CTAs per SM)
   int8_t* rq = nullptr;       // [NBa][Np]   limb l of column c at row l * R1p + c, permuted individual order
   double* col_dq = nullptr;   // [R1]        power-of-two dequantisation factor of every RHS column
   int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights of the current block
@@ -573,15 +574,14 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
 // Four groups of four decode warps: group g = (par, q) expands M-tile q of the stages st = par (mod 4 / MT)
 // into shared-memory A slot g.  Stage st belongs to one bin (bins are padded to 128 rows); bin k, M-tile q
 // accumulates in TMEM columns [(k * MT + q) * NC, +NC).
-#define PB_G 4
-#define PB_DW (4 * PB_G)
-#define PB_THREADS (32 * (PB_DW + 1 + PB_G))   // decode warps, one TMA warp, one MMA-issue warp per group
+#define PB_G 4                    // decode groups of the one-CTA-per-SM variant (the two-CTA variant runs 2)
+#define PB_THREADS_OF(G) (32 * (4 * (G) + 1 + (G)))   // decode warps, one TMA warp, one MMA-issue warp per group
 #define PB_BS 16                  // maximum depth of the smem ring of Uq tiles (TMA); the launch picks bs <= PB_BS
-#define PB_PKG 3                  // per-warp cp.async ring depth (in the group's own stages)
+#define PB_PKG 3                  // per-warp cp.async ring depth (in the group's own stages): PB_PKG - 1 stages in flight
 #define PB_AS 2                   // shared-memory A slots per decode group (decode of tile u+1 overlaps the MMAs of tile u)
 
 #define PB_MAX_STAGES 512
-#define PB_MAX_KB 1024            // K * B entries of the per-bin mean term staged in shared memory
+#define PB_MAX_KB 512             // K * B entries of the per-bin mean term staged in shared memory
 struct PbSmem {
   uint64_t full_a[PB_G * PB_AS], empty_a[PB_G * PB_AS], full_b[PB_BS], empty_b[PB_BS], acc_full;
   uint32_t tmem_base;
@@ -659,8 +659,10 @@ __device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq
   }
 }
 
-template <int MT>
-__global__ void __launch_bounds__(PB_THREADS, 1)
+// G = 4 decode groups and one CTA per SM, or G = 2 and two co-resident CTAs per SM (then one CTA's prologue and
+// epilogue -- the write of its [bins x vectors x 128 individuals] results -- run underneath the other's main loop).
+template <int MT, int G>
+__global__ void __launch_bounds__(PB_THREADS_OF(G), G == 2 ? 2 : 1)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
             const int32_t* __restrict__ pos_meta, const int32_t* __restrict__ stage_info,
             const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
@@ -668,11 +670,12 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
             uint32_t tmem_cols, int a_major, int kcap, int bs, int bzsh, int dbg) {
   if (dbg & 16) n_stage = 0;
-  constexpr int SI = PB_G / MT;                      // stage interleave between groups
+  constexpr int PB_DW = 4 * G, PB_THREADS = PB_THREADS_OF(G);
+  constexpr int SI = G / MT;                         // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tileA = smem;
-  uint8_t* tileB = tileA + PB_G * PB_AS * TC_TILE_A;
+  uint8_t* tileB = tileA + G * PB_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
   uint8_t* packed = tileB + bs * tileB_bytes;     // [decode warp][PB_PKG][2 halves][32 rows][16 B]
   PbSmem* sm = reinterpret_cast<PbSmem*>(packed + PB_DW * PB_PKG * 1024);
@@ -682,9 +685,9 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   const int i0 = blockIdx.x * (MT * 128);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PB_G * PB_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
+    for (int s = 0; s < G * PB_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
     for (int s = 0; s < (bs >> bzsh); ++s) { mbar_init(&sm->full_b[s], 1); mbar_init(&sm->empty_b[s], MT << bzsh); }   // one pair per batch of 2^bzsh Uq tiles
-    mbar_init(&sm->acc_full, PB_G);
+    mbar_init(&sm->acc_full, G);
     fence_barrier_init();
   }
   if (warp == PB_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
@@ -699,7 +702,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   const uint32_t tmem = sm->tmem_base;
   if (warp < PB_DW && !(dbg & 32)) {                   // zero the accumulators: quadrant per warp, columns split by group
     const uint32_t used = (uint32_t)(K * MT * NC);
-    for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < used; c += 32 * PB_G)
+    for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < used; c += 32 * G)
       tmem_zero32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c);
   }
   tc_fence_before();
@@ -723,38 +726,43 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const uint32_t my_slot = ring + (uint32_t)lane * 16;                               // owner view: [half][row][16 B]
     const uint32_t cp_dst = ring + (uint32_t)(lane & 1) * 512 + (uint32_t)(lane >> 1) * 16;   // copier view, h = 0
     const uint8_t* cp_base = base + (lane & 1) * 16;
-    auto issue = [&](int meta, int slot) {
+    auto issue = [&](int meta, uint32_t slot) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int mrow = __shfl_sync(0xffffffffu, meta, 16 * h + (lane >> 1));
         if (mrow >= 0 && !(dbg & 1))
-          cp_async16(cp_dst + (uint32_t)(slot * 1024 + h * 256), cp_base + (size_t)(mrow & 0xFFFFFF) * pitch);
+          cp_async16(cp_dst + slot * 1024u + (uint32_t)(h * 256), cp_base + (size_t)(mrow & 0xFFFFFF) * pitch);
       }
       cp_async_commit();
     };
+    constexpr int AHEAD = PB_PKG - 1;                    // stages of packed bytes in flight (memory-level parallelism)
+    static_assert(AHEAD >= 2 && AHEAD <= 4, "the meta ring is loaded five stages ahead");
 #pragma unroll
     for (int j = 0; j < 5; ++j) M[j] = meta_of(j);
     M[5] = -1;
-    issue(M[0], 0);
-    issue(M[1], 1);
+#pragma unroll
+    for (int j = 0; j < AHEAD; ++j) issue(M[j], (uint32_t)j);
+    uint32_t rd_slot = 0, wr_slot = AHEAD;               // ring slots of stage u and stage u + AHEAD
     const uint32_t tile0 = tileA_s + g * PB_AS * TC_TILE_A;
     uint64_t* const full0 = &sm->full_a[g * PB_AS];
     uint64_t* const empty0 = &sm->empty_a[g * PB_AS];
     PROF_T0();
-    static_assert(PB_AS == 2 && PB_PKG == 3, "slot parity / ring indices below");
+    static_assert(PB_AS == 2, "slot parity below");
     for (int u0 = 0; u0 < n_own; u0 += 6) {
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         const int u = u0 + r;
         if (u < n_own) {                                 // warp-uniform
           M[(r + 5) % 6] = meta_of(u + 5);
-          issue(M[(r + 2) % 6], (r + 2) % 3);            // stage u + 2
+          issue(M[(r + AHEAD) % 6], wr_slot);            // stage u + AHEAD
+          wr_slot = wr_slot + 1 == PB_PKG ? 0u : wr_slot + 1;
           const int meta = M[r];
           const uint32_t tab = meta >= 0 ? tc_value_table(((uint32_t)meta >> 24) & 3u, (meta >> 26) & 1) : 0u;
           const int a = r & 1;                           // u0 is even: slot = u % 2, use index u / 2
-          cp_async_wait<2>();                            // stage u has landed (u + 1, u + 2 may be in flight)
+          cp_async_wait<AHEAD>();                        // stage u has landed (the AHEAD later ones may be in flight)
           __syncwarp();
-          const uint4 lo = lds128(my_slot + (r % 3) * 1024), hi = lds128(my_slot + (r % 3) * 1024 + 512);
+          const uint4 lo = lds128(my_slot + rd_slot * 1024u), hi = lds128(my_slot + rd_slot * 1024u + 512);
+          rd_slot = rd_slot + 1 == PB_PKG ? 0u : rd_slot + 1;
           PROF_ADD(0);
           if (!(dbg & 128)) mbar_wait(empty0 + a, ((u >> 1) & 1) ^ 1);
           PROF_ADD(1);
@@ -950,23 +958,22 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 static inline int pa_smem_bytes(int nb, int) { return PA_RS * 4 * nb * 128 + PA_GS * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
 static inline int pa_ring(int) { return PA_RS; }
-static inline int pb_smem_bytes(int nc, int bs) { return PB_G * PB_AS * TC_TILE_A + bs * nc * 128 + PB_DW * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
-// The Uq ring depth must be a multiple of the stage interleave (4 / MT): consecutive uses of one slot are then
-// consumed by the same issuer, which keeps every waiter within one mbarrier phase of its barrier.
+static inline int pb_smem_bytes(int nc, int bs, int G = PB_G) { return G * PB_AS * TC_TILE_A + bs * nc * 128 + 4 * G * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
 // Uq ring: `bs` tile slots in batches of 2^bzsh tiles that share one barrier pair.  Either a batch spans at least
-// one stage of every issuer (2^bzsh >= SI = 4 / MT), or there is no batching and bs is a multiple of SI (a slot is
+// one stage of every issuer (2^bzsh >= SI = G / MT), or there is no batching and bs is a multiple of SI (a slot is
 // then always consumed by the same issuer); both keep every waiter within one mbarrier phase of its barrier.
-static inline int pb_ring(int nc, int mt, int* bzsh) {
-  const int si = PB_G / mt;
-  const int budget = 232448 - 2048;
-  const char* env = getenv("PYRHE_TC_DEBUG_RING");       // "4": the unbatched four-slot ring
-  if (!(env && atoi(env) == 4)) {
-    if (pb_smem_bytes(nc, 8) <= budget) { *bzsh = 2; return 8; }                  // two batches of four tiles
-    if (si <= 2 && pb_smem_bytes(nc, 4) <= budget) { *bzsh = 1; return 4; }       // two batches of two tiles
+static inline int pb_budget(int G) { return G == 2 ? 233472 / 2 - 1024 : 232448 - 2048; }
+static inline int pb_ring(int nc, int mt, int G, int* bzsh) {
+  const int si = G / mt;
+  const int budget = pb_budget(G);
+  const char* env = getenv("PYRHE_TC_DEBUG_RING");       // "1": the unbatched ring
+  if (!(env && atoi(env) == 1)) {
+    if (si <= 4 && pb_smem_bytes(nc, 8, G) <= budget) { *bzsh = 2; return 8; }    // two batches of four tiles
+    if (si <= 2 && pb_smem_bytes(nc, 4, G) <= budget) { *bzsh = 1; return 4; }    // two batches of two tiles
   }
   *bzsh = 0;
-  int bs = PB_BS;
-  while (bs > 4 && pb_smem_bytes(nc, bs) > budget) bs -= 4;
+  int bs = PB_BS / si * si;
+  while (bs > si && pb_smem_bytes(nc, bs, G) > budget) bs -= si;
   return bs;
 }
 
@@ -982,7 +989,15 @@ int rhe_tc_create(rhe_ctx* c) {
   s->Bp = round_up(g.n_vec, 2);
   s->NCb = round_up(c->n_groups * s->L * s->Bp, 16);   // weight groups (RHS sets) are stacked along N
   s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
-  if (pb_smem_bytes(s->NCb, 4) > 232448 || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
+  {
+    // Optional variant (PYRHE_B200_PASSB_GROUPS=2): two half-size CTAs per SM (one M-tile, two decode groups, 256 TMEM
+    // columns each), so that the epilogue of one overlaps the main loop of the other.  Measured equal to the default
+    // on config 5 (0.69 vs 0.68 ms per block), so it stays opt-in.
+    const char* envG = getenv("PYRHE_B200_PASSB_GROUPS");
+    const bool fits2 = g.n_bins * s->NCb <= 256 && pb_smem_bytes(s->NCb, 2, 2) <= pb_budget(2);
+    if (fits2 && envG && atoi(envG) == 2) { s->G = 2; s->MT = 1; }
+  }
+  if (pb_smem_bytes(s->NCb, s->G / s->MT, s->G) > pb_budget(s->G) || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     delete s;
     return RHE_ERR_UNSUPPORTED;
@@ -1005,8 +1020,13 @@ int rhe_tc_create(rhe_ctx* c) {
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa, pa_ring(s->NBa))));
-  { int sh; RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb, 1, &sh)))); }
-  { int sh; RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes(s->NCb, pb_ring(s->NCb, 2, &sh)))); }
+  {
+    int sh;
+    const int smem = pb_smem_bytes(s->NCb, pb_ring(s->NCb, s->MT, s->G, &sh), s->G);
+    if (s->G == 2) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else if (s->MT == 2) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
   return RHE_OK;
 }
 
@@ -1140,15 +1160,19 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   }
   const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
   int bzsh = 0;
-  const int bs = pb_ring(s->NCb, s->MT, &bzsh), smem = pb_smem_bytes(s->NCb, bs);
-  if (s->MT == 2)
-    k_tc_pass_b<2><<<c->Np / 256, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
-                                                          meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, bzsh, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
-  else
-    k_tc_pass_b<1><<<c->Np / 128, PB_THREADS, smem, st>>>(s->tm_uq, bed, g.pitch_bytes, c->Np, n_modes * n_pos / 128, s->pos_meta,
-                                                          meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, s->NCb,
-                                                          s->F, s->wmax, c->cs, c->rowscale, g.n_sets == 2 ? c->Np : 0, P_out, S_accum, cols, getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1, getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4, bs, bzsh, getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0);
+  const int bs = pb_ring(s->NCb, s->MT, s->G, &bzsh), smem = pb_smem_bytes(s->NCb, bs, s->G);
+  const int a_major = getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1;
+  const int kcap = getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4;
+  const int dbg = getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0;
+  const int n_stage = n_modes * n_pos / 128, rs_stride = g.n_sets == 2 ? c->Np : 0;
+#define PB_LAUNCH(MT_, G_)                                                                                                   \
+  k_tc_pass_b<MT_, G_><<<c->Np / (128 * MT_), PB_THREADS_OF(G_), smem, st>>>(                                                \
+      s->tm_uq, bed, g.pitch_bytes, c->Np, n_stage, s->pos_meta, meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp,  \
+      s->L, s->NCb, s->F, s->wmax, c->cs, c->rowscale, rs_stride, P_out, S_accum, cols, a_major, kcap, bs, bzsh, dbg)
+  if (s->G == 2) PB_LAUNCH(1, 2);
+  else if (s->MT == 2) PB_LAUNCH(2, 4);
+  else PB_LAUNCH(1, 4);
+#undef PB_LAUNCH
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }

@@ -210,3 +210,18 @@ def test_edge_shapes_match_cpu_oracle(shape, path):
     T, q = assemble_all(plan, ht, pieces, J)
     np.testing.assert_allclose(T, ref["T"], rtol=1e-5, atol=1e-6 * np.abs(ref["T"]).max())
     np.testing.assert_allclose(q, ref["q"], rtol=1e-5, atol=1e-6 * np.abs(ref["q"]).max())
+
+
+def test_pass_b_two_cta_variant_matches_default(monkeypatch):
+    """PYRHE_B200_PASSB_GROUPS=2 (two half-size pass-B CTAs per SM) gives the same pieces as the default layout."""
+    p = oracle_problem("rhe_cov_binary")
+    plan = plan_for(p)
+    eng, _, _ = make_engine(p, plan, kernel_path=TC)
+    a = eng.run()
+    eng.close()
+    monkeypatch.setenv("PYRHE_B200_PASSB_GROUPS", "2")
+    eng, _, _ = make_engine(p, plan, kernel_path=TC)
+    b = eng.run()
+    eng.close()
+    np.testing.assert_allclose(a["XX"], b["XX"], rtol=1e-6)
+    np.testing.assert_allclose(a["G_blk"], b["G_blk"], rtol=1e-10, atol=1e-9)
