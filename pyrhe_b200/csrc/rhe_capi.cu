@@ -122,53 +122,63 @@ __global__ void k_snp_params(const int32_t* __restrict__ counts, int m, int n_ke
   f2[s] = (double)n2 / (double)n_kept;
 }
 
-// Fused front end of rhe_block_accumulate: masked popcounts (one warp per SNP row), the imputation fill and
-// moments of the SNP, and the zeroing of everything this block accumulates into (t_raw rows, cs, gram, wmax).
+// Fused front end of rhe_block_accumulate: masked popcounts, the imputation fill and moments of the SNP, and the
+// zeroing of everything this block accumulates into (t_raw rows, cs, gram, wmax).  ST_SPLIT warps share one SNP row
+// (a quarter of the row each, combined through shared memory): with one warp per row the 10^4 rows of a block are
+// only ~1.4 waves of resident warps and the half-empty last wave costs a quarter of the pass.
+#define ST_SPLIT 4
+#define ST_ROWS (8 / ST_SPLIT)
 __global__ void __launch_bounds__(256)
 k_stats_params(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t* __restrict__ keep2, int n_kept,
                int binary, const double* __restrict__ uniforms, int32_t* __restrict__ counts,
                uint8_t* __restrict__ fill, double* __restrict__ mu, double* __restrict__ f2,
                double* __restrict__ t_raw, int t_cols, int n_ops, double* __restrict__ cs, int n_cs,
                double* __restrict__ gram, int n_gram, unsigned int* __restrict__ wmax, int n_wmax) {
+  __shared__ int part[8][3];
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < n_cs; i += 256) cs[i] = 0.0;
     for (int i = threadIdx.x; i < n_wmax; i += 256) wmax[i] = 0u;
   }
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n_gram; i += gridDim.x * 256) gram[i] = 0.0;
-  const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (s >= m) return;
-  const int lane = threadIdx.x & 31;
-  for (int op = 0; op < n_ops; ++op)
-    for (int c = lane; c < t_cols; c += 32) t_raw[((size_t)op * m + s) * t_cols + c] = 0.0;
-  const uint32_t* row = reinterpret_cast<const uint32_t*>(bed + (size_t)s * pitch);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * ST_ROWS + warp / ST_SPLIT, piece = warp % ST_SPLIT;
+  const bool live = s < m;
   int bits = 0, n2 = 0, nm = 0;
-  {
-    const uint4* row4 = reinterpret_cast<const uint4*>(row);
+  if (live) {
+    if (piece == 0)
+      for (int op = 0; op < n_ops; ++op)
+        for (int c = lane; c < t_cols; c += 32) t_raw[((size_t)op * m + s) * t_cols + c] = 0.0;
+    const uint4* row4 = reinterpret_cast<const uint4*>(bed + (size_t)s * pitch);
     const uint4* keep4 = reinterpret_cast<const uint4*>(keep2);
-    const int n4 = pitch / 16;                      // pitch is a multiple of 128 bytes
+    const int n4 = pitch / 16;                        // pitch is a multiple of 128 bytes
+    const int per = (n4 + ST_SPLIT - 1) / ST_SPLIT;
+    const int w0 = piece * per, w1 = min(n4, w0 + per);
     if (n_ops == 2) {
 #pragma unroll 4
-      for (int w = lane; w < n4; w += 32) {
+      for (int w = w0 + lane; w < w1; w += 32) {
         const uint4 x = rhe_ldg_stream(row4 + w), k = __ldg(keep4 + w);
         rhe_popc_word2<true>(x.x, k.x, bits, nm, n2); rhe_popc_word2<true>(x.y, k.y, bits, nm, n2);
         rhe_popc_word2<true>(x.z, k.z, bits, nm, n2); rhe_popc_word2<true>(x.w, k.w, bits, nm, n2);
       }
     } else {
 #pragma unroll 4
-      for (int w = lane; w < n4; w += 32) {
+      for (int w = w0 + lane; w < w1; w += 32) {
         const uint4 x = rhe_ldg_stream(row4 + w), k = __ldg(keep4 + w);
         rhe_popc_word2<false>(x.x, k.x, bits, nm, n2); rhe_popc_word2<false>(x.y, k.y, bits, nm, n2);
         rhe_popc_word2<false>(x.z, k.z, bits, nm, n2); rhe_popc_word2<false>(x.w, k.w, bits, nm, n2);
       }
     }
+    for (int o = 16; o; o >>= 1) {
+      bits += __shfl_xor_sync(0xffffffffu, bits, o);
+      n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+      nm += __shfl_xor_sync(0xffffffffu, nm, o);
+    }
   }
-  for (int o = 16; o; o >>= 1) {
-    bits += __shfl_xor_sync(0xffffffffu, bits, o);
-    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-    nm += __shfl_xor_sync(0xffffffffu, nm, o);
-  }
-  const int ssum = bits - nm;                        // n1 + 2 n2 over kept individuals
-  if (lane == 0) {
+  if (lane == 0) { part[warp][0] = bits; part[warp][1] = n2; part[warp][2] = nm; }
+  __syncthreads();
+  if (live && piece == 0 && lane == 0) {
+    for (int q = 1; q < ST_SPLIT; ++q) { bits += part[warp + q][0]; n2 += part[warp + q][1]; nm += part[warp + q][2]; }
+    const int ssum = bits - nm;                        // n1 + 2 n2 over kept individuals
     // n1 / n0 are filled in only when n2 was counted (RHE-DOM); the exact four-way counts come from k_stats
     reinterpret_cast<int4*>(counts)[s] = make_int4(n_kept - (ssum - n2) - nm, ssum - 2 * n2, n2, nm);
     int f = 0;
@@ -756,7 +766,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
     s_off_dev = e.dev;
   }
   unsigned int* wmax = g.kernel_path == RHE_PATH_TCGEN05 ? rhe_tc_wmax(c) : nullptr;
-  k_stats_params<<<rhe_div_up(m, 8), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
+  k_stats_params<<<rhe_div_up(m, ST_ROWS), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
                                                    c->counts, c->fill, c->mu, c->f2, c->t_raw, c->R1, g.n_ops, c->cs,
                                                    c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? c->n_groups * B : 0);
   RHE_LAUNCH_CHECK(c);
