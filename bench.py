@@ -113,7 +113,7 @@ def reference_arm(args, wl, rank):
         "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "projected_full_job_s": wl["N"] / 4 * wl["M"] / 1e9 / gbs,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -310,11 +310,22 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "sigma_check": [float(v) for v in sigma[-1]],
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: dict):
+    """The one JSON line goes to the process's original stdout; everything else a library prints while the
+    benchmark runs (NCCL's version banner, for one) has been redirected to stderr by then."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # C-level stdout of this process (and of its children) -> stderr
     main()
