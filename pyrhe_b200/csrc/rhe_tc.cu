@@ -677,7 +677,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   uint8_t* tileA = smem;
   uint8_t* tileB = tileA + G * PB_AS * TC_TILE_A;
   const int tileB_bytes = NC * 128;
-  uint8_t* packed = tileB + bs * tileB_bytes;     // [decode warp][PB_PKG][2 halves][32 rows][16 B]
+  uint8_t* packed = tileB + bs * tileB_bytes;     // [decode warp][PB_PKG][32 rows][32 B]
   PbSmem* sm = reinterpret_cast<PbSmem*>(packed + PB_DW * PB_PKG * 1024);
   const uint32_t tileA_s = smem_u32(tileA);
 
@@ -723,15 +723,19 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     int M[6];
     auto meta_of = [&](int u) { return u < n_own ? __ldg(pos_meta + (par + SI * u) * 128 + t) : -1; };
     const uint32_t ring = smem_u32(packed) + (uint32_t)warp * (PB_PKG * 1024);
-    const uint32_t my_slot = ring + (uint32_t)lane * 16;                               // owner view: [half][row][16 B]
-    const uint32_t cp_dst = ring + (uint32_t)(lane & 1) * 512 + (uint32_t)(lane >> 1) * 16;   // copier view, h = 0
+    // slot layout [32 rows][32 B]: the two halves of a sector stay adjacent (the sector lands as one shared-memory
+    // wavefront instead of two) and swap places in every other group of four rows (conflict-free 16-byte owner reads)
+    const uint32_t my_lo = ring + (uint32_t)lane * 32 + (((uint32_t)lane >> 2) & 1u) * 16;    // owner view, half 0
+    const uint32_t my_hi = my_lo ^ 16u;
+    const uint32_t cp_row = (uint32_t)(lane >> 1);                                              // copier view, h = 0
+    const uint32_t cp_dst = ring + cp_row * 32 + ((((uint32_t)lane & 1u) ^ ((cp_row >> 2) & 1u)) * 16);
     const uint8_t* cp_base = base + (lane & 1) * 16;
     auto issue = [&](int meta, uint32_t slot) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int mrow = __shfl_sync(0xffffffffu, meta, 16 * h + (lane >> 1));
         if (mrow >= 0 && !(dbg & 1))
-          cp_async16(cp_dst + slot * 1024u + (uint32_t)(h * 256), cp_base + (size_t)(mrow & 0xFFFFFF) * pitch);
+          cp_async16(cp_dst + slot * 1024u + (uint32_t)(h * 512), cp_base + (size_t)(mrow & 0xFFFFFF) * pitch);
       }
       cp_async_commit();
     };
@@ -761,7 +765,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
           const int a = r & 1;                           // u0 is even: slot = u % 2, use index u / 2
           cp_async_wait<AHEAD>();                        // stage u has landed (the AHEAD later ones may be in flight)
           __syncwarp();
-          const uint4 lo = lds128(my_slot + rd_slot * 1024u), hi = lds128(my_slot + rd_slot * 1024u + 512);
+          const uint4 lo = lds128(my_lo + rd_slot * 1024u), hi = lds128(my_hi + rd_slot * 1024u);
           rd_slot = rd_slot + 1 == PB_PKG ? 0u : rd_slot + 1;
           PROF_ADD(0);
           if (!(dbg & 128)) mbar_wait(empty0 + a, ((u >> 1) & 1) ^ 1);
