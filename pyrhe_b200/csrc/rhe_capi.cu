@@ -578,6 +578,88 @@ static void launch_loo_small(const float* S, const float* P, int64_t len, double
   k_loo_gram_small<E><<<grid, 256, 0, st>>>(S, P, len, out);
 }
 
+// Leave-one-out Gram on the FP64 tensor cores: out[a][c] += sum_x (S_a - P_a)(x) (S_c - P_c)(x) for up to
+// 8 NT estimates.  One mma.m8n8k4.f64 forms all 64 pair products of an 8-row tile over four positions; for a Gram
+// the A fragment (row = lane / 4, k = lane % 4) and the B fragment (k = lane % 4, column = lane / 4) of a tile are the
+// same register.  Lane (e, c) reads the positions 16 it + 4 c .. + 3 of row e as one float4, so k-step j of an
+// iteration covers the positions {4 c + j}.  Differences are formed in fp64 from the fp32 inputs (exact); ~40
+// registers per thread leave the whole SM to loads in flight.  Memory bound: reads S and P once.
+template <int NT>
+__global__ void __launch_bounds__(256)
+k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int E, int64_t len, double* __restrict__ out) {
+  constexpr int NPAIR = NT * (NT + 1) / 2;
+  double acc[NPAIR][2];
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) acc[p][0] = acc[p][1] = 0.0;
+  const int lane = threadIdx.x & 31, e = lane >> 2, c = lane & 3;
+  const int64_t n16 = len >> 4;                      // len is a multiple of 16 (B * Np, Np a multiple of 512)
+  const int64_t warp_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int UN = 1;                                // 16-position chunks in flight per warp (more did not help)
+  for (int64_t it0 = warp_id; it0 < n16; it0 += n_warps * UN) {
+    float4 v[UN][NT], w[UN][NT];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t it = it0 + (int64_t)u * n_warps;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int row = 8 * t + e;
+        v[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[u][t] = v[u][t];
+        if (row < E && it < n16) {
+          const size_t o = (size_t)row * len + (size_t)it * 16 + 4 * c;
+          v[u][t] = __ldg(reinterpret_cast<const float4*>(S + o));      // S is re-read for every block: keep it cacheable
+          if (P) w[u][t] = __ldcs(reinterpret_cast<const float4*>(P + o));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      double d[NT][4];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        d[t][0] = (double)v[u][t].x - (double)w[u][t].x; d[t][1] = (double)v[u][t].y - (double)w[u][t].y;
+        d[t][2] = (double)v[u][t].z - (double)w[u][t].z; d[t][3] = (double)v[u][t].w - (double)w[u][t].w;
+      }
+      int p = 0;
+#pragma unroll
+      for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < NT; ++tj) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(acc[p][0]), "+d"(acc[p][1]) : "d"(d[ti][j]), "d"(d[tj][j]));
+          ++p;
+        }
+    }
+  }
+  // C fragment: row = lane / 4, columns 2 (lane % 4), + 1 of the (ti, tj) tile; block reduction, then one atomic per entry
+  __shared__ double red[NPAIR][64];
+  for (int i = threadIdx.x; i < NPAIR * 64; i += blockDim.x) (&red[0][0])[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) {
+    atomicAdd(&red[p][e * 8 + 2 * c], acc[p][0]);
+    atomicAdd(&red[p][e * 8 + 2 * c + 1], acc[p][1]);
+  }
+  __syncthreads();
+  int p = 0;
+  for (int ti = 0; ti < NT; ++ti)
+    for (int tj = ti; tj < NT; ++tj, ++p)
+      for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        const int a = 8 * ti + (i >> 3), b = 8 * tj + (i & 7);
+        if (a < E && b < E) {
+          atomicAdd(out + a * E + b, red[p][i]);
+          if (ti != tj) atomicAdd(out + b * E + a, red[p][i]);
+        }
+      }
+}
+
+template <int NT>
+static void launch_loo_mma(const float* S, const float* P, int E, int64_t len, double* out, cudaStream_t st) {
+  k_loo_gram_mma<NT><<<148 * 8, 256, 0, st>>>(S, P, E, len, out);
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 
@@ -863,6 +945,13 @@ extern "C" int rhe_loo_gram(rhe_ctx* c, const float* S, const float* P, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   RHE_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_est * n_est, st));
   // register-resident kernels for up to 8 estimates (8-byte loads: even length, always true for B * Np)
+  if (len % 16 == 0 && n_est <= 24 && !getenv("PYRHE_B200_LOO_SIMT")) {      // FP64 tensor-core Gram
+    if (n_est <= 8) launch_loo_mma<1>(S, P, n_est, len, out, st);
+    else if (n_est <= 16) launch_loo_mma<2>(S, P, n_est, len, out, st);
+    else launch_loo_mma<3>(S, P, n_est, len, out, st);
+    RHE_LAUNCH_CHECK(c);
+    return RHE_OK;
+  }
   switch (len % 2 == 0 ? n_est : 0) {
     case 1: launch_loo_small<1>(S, P, len, out, st); break;
     case 2: launch_loo_small<2>(S, P, len, out, st); break;
