@@ -142,7 +142,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pyrhe_b200 import _lib
-    from pyrhe_b200.assemble import PathPlan, normal_equations_batch
+    from pyrhe_b200.assemble import PathPlan, normal_equations_batch, loo_grams
     from pyrhe_b200.engine import RheEngine
     from pyrhe_b200.hostmath import host_terms
     from pyrhe_b200 import synth
@@ -188,9 +188,8 @@ def main():
     torch.cuda.synchronize(dev)
 
     def tail(pieces):
-        G_tot = pieces["G_blk"].sum(axis=0)
-        G_loo = np.concatenate([G_tot[None] - pieces["G_blk"], G_tot[None]], axis=0)
-        T, q = normal_equations_batch(plan, ht, pieces["XX"], G_loo, pieces["M"])
+        tail.buf = loo_grams(pieces["G_blk"], getattr(tail, "buf", None))
+        T, q = normal_equations_batch(plan, ht, pieces["XX"], tail.buf, pieces["M"])
         try:
             return np.linalg.solve(T, q[..., None])[..., 0]
         except np.linalg.LinAlgError:        # only with the kernel debug switches (PYRHE_TC_DEBUG_*) that skip work

@@ -116,6 +116,11 @@ int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
 int rhe_loo_gram(rhe_ctx* ctx, const float* S_dev, const float* P_dev, int32_t n_est,
                  int64_t len, double* out_dev, void* stream);
 
+/* The same for n_blocks partials laid out at P_dev + b * p_stride floats, results at out_dev + b * out_stride
+ * doubles: up to four blocks share one read of S per launch (the pass is memory bound). */
+int rhe_loo_gram_multi(rhe_ctx* ctx, const float* S_dev, const float* P_dev, int64_t p_stride, int32_t n_blocks,
+                       int32_t n_est, int64_t len, double* out_dev, int64_t out_stride, void* stream);
+
 /* Synthetic PLINK rows generated on the device: SNP s has A2 frequency
  * p_s ~ U(0.05, 0.5), genotypes ~ Binomial(2, p_s) i.i.d., code 01 (missing) with probability
  * missing_rate; counter-based hash of (seed, first_snp + row, byte) so any row range can be

@@ -40,6 +40,8 @@ SIGNATURES = {
     "rhe_block_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rhe_loo_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "rhe_loo_gram_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
+                                     C.c_void_p, C.c_int64, C.c_void_p]),
     "rhe_launch_count": (C.c_int64, [C.c_void_p]),
     "rhe_synth_genotypes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_float,
                                       C.c_void_p]),

@@ -159,6 +159,17 @@ def trace_sums_row(T: np.ndarray, M_row: np.ndarray, N: int, E: int) -> np.ndarr
     return out
 
 
+def loo_grams(G_blk: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """[J, ...] per-block pieces -> [J + 1, ...]: total minus block j for j < J, the total in slot J.  `out` lets a
+    caller that runs this every step reuse one buffer (a fresh 1.6 MB array costs more than the arithmetic)."""
+    J = G_blk.shape[0]
+    if out is None or out.shape != (J + 1,) + G_blk.shape[1:]:
+        out = np.empty((J + 1,) + G_blk.shape[1:], dtype=np.float64)
+    np.sum(G_blk, axis=0, out=out[J])
+    np.subtract(out[J][None], G_blk, out=out[:J])
+    return out
+
+
 def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo: np.ndarray, M_tab: np.ndarray,
                            trait: int = 0, nxe_quirk: bool = True):
     """Vectorised `normal_equations` over all jackknife samples (the production path).

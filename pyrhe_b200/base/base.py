@@ -24,7 +24,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from .. import stats
-from ..assemble import PathPlan, normal_equations, trace_sums_row
+from ..assemble import PathPlan, loo_grams, normal_equations, normal_equations_batch, trace_sums_row
 from ..hostmath import block_ranges, host_terms
 from ..util.file_processing import (generate_annot, read_annot, read_bim, read_cov, read_fam, read_pheno)
 from ..util.logger import Logger
@@ -269,9 +269,19 @@ class Base(LegacyBlockOps, ABC):
         trace_sums = (np.zeros((self.num_jack + 1, self.num_estimates, self.num_estimates))
                       if self.get_trace else None)
         sigmas, trace_cols = [], []
+        batched = type(self).setup_lhs_rhs_jackknife is Base.setup_lhs_rhs_jackknife
+        if batched:       # all J + 1 systems assembled in one vectorised pass (an extender's override is honoured below)
+            pc = self._pieces
+            T_all, q_all = normal_equations_batch(self._plan_cached, self._host_terms, pc["XX"], loo_grams(pc["G_blk"]),
+                                                  self.M, trait=self._trait_index())
         for j in range(self.num_jack + 1):
             jj = 1 if (self.num_jack == 1 and j == 0) else j          # base.py:654-655
-            T, q = self.setup_lhs_rhs_jackknife(jj, trace_sums)
+            if batched:
+                T, q = T_all[jj], q_all[jj]
+                if trace_sums is not None:
+                    trace_sums[jj] = trace_sums_row(T, self.M[jj], self.num_indv, self.num_estimates)
+            else:
+                T, q = self.setup_lhs_rhs_jackknife(jj, trace_sums)
             sigmas.append(stats.solve(T, q, method))
             trace_cols.append(T[:, self.num_estimates].copy())
         if self.get_trace:

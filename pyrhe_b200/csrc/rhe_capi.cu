@@ -584,41 +584,44 @@ static void launch_loo_small(const float* S, const float* P, int64_t len, double
 // same register.  Lane (e, c) reads the positions 16 it + 4 c .. + 3 of row e as one float4, so k-step j of an
 // iteration covers the positions {4 c + j}.  Differences are formed in fp64 from the fp32 inputs (exact); ~40
 // registers per thread leave the whole SM to loads in flight.  Memory bound: reads S and P once.
-template <int NT>
+// NBLK block partials P, P + p_stride, ... share one read of S (outputs out, out + out_stride, ...).
+template <int NT, int NBLK>
 __global__ void __launch_bounds__(256)
-k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int E, int64_t len, double* __restrict__ out) {
+k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int64_t p_stride, int E, int64_t len,
+               double* __restrict__ out, int64_t out_stride) {
   constexpr int NPAIR = NT * (NT + 1) / 2;
-  double acc[NPAIR][2];
+  double acc[NBLK][NPAIR][2];
 #pragma unroll
-  for (int p = 0; p < NPAIR; ++p) acc[p][0] = acc[p][1] = 0.0;
+  for (int b = 0; b < NBLK; ++b)
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) acc[b][p][0] = acc[b][p][1] = 0.0;
   const int lane = threadIdx.x & 31, e = lane >> 2, c = lane & 3;
   const int64_t n16 = len >> 4;                      // len is a multiple of 16 (B * Np, Np a multiple of 512)
   const int64_t warp_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  constexpr int UN = 1;                                // 16-position chunks in flight per warp (more did not help)
-  for (int64_t it0 = warp_id; it0 < n16; it0 += n_warps * UN) {
-    float4 v[UN][NT], w[UN][NT];
+  for (int64_t it = warp_id; it < n16; it += n_warps) {
+    float4 v[NT], w[NBLK][NT];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int64_t it = it0 + (int64_t)u * n_warps;
+    for (int t = 0; t < NT; ++t) {
+      const int row = 8 * t + e;
+      v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const int row = 8 * t + e;
-        v[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        w[u][t] = v[u][t];
-        if (row < E && it < n16) {
-          const size_t o = (size_t)row * len + (size_t)it * 16 + 4 * c;
-          v[u][t] = __ldg(reinterpret_cast<const float4*>(S + o));      // S is re-read for every block: keep it cacheable
-          if (P) w[u][t] = __ldcs(reinterpret_cast<const float4*>(P + o));
+      for (int b = 0; b < NBLK; ++b) w[b][t] = v[t];
+      if (row < E) {
+        const size_t o = (size_t)row * len + (size_t)it * 16 + 4 * c;
+        v[t] = __ldg(reinterpret_cast<const float4*>(S + o));      // S is re-read by every launch: keep it cacheable
+        if (P) {
+#pragma unroll
+          for (int b = 0; b < NBLK; ++b) w[b][t] = __ldcs(reinterpret_cast<const float4*>(P + (size_t)b * p_stride + o));
         }
       }
     }
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
+    for (int b = 0; b < NBLK; ++b) {
       double d[NT][4];
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        d[t][0] = (double)v[u][t].x - (double)w[u][t].x; d[t][1] = (double)v[u][t].y - (double)w[u][t].y;
-        d[t][2] = (double)v[u][t].z - (double)w[u][t].z; d[t][3] = (double)v[u][t].w - (double)w[u][t].w;
+        d[t][0] = (double)v[t].x - (double)w[b][t].x; d[t][1] = (double)v[t].y - (double)w[b][t].y;
+        d[t][2] = (double)v[t].z - (double)w[b][t].z; d[t][3] = (double)v[t].w - (double)w[b][t].w;
       }
       int p = 0;
 #pragma unroll
@@ -628,36 +631,48 @@ k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int E, 
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                         : "+d"(acc[p][0]), "+d"(acc[p][1]) : "d"(d[ti][j]), "d"(d[tj][j]));
+                         : "+d"(acc[b][p][0]), "+d"(acc[b][p][1]) : "d"(d[ti][j]), "d"(d[tj][j]));
           ++p;
         }
     }
   }
   // C fragment: row = lane / 4, columns 2 (lane % 4), + 1 of the (ti, tj) tile; block reduction, then one atomic per entry
   __shared__ double red[NPAIR][64];
-  for (int i = threadIdx.x; i < NPAIR * 64; i += blockDim.x) (&red[0][0])[i] = 0.0;
-  __syncthreads();
 #pragma unroll
-  for (int p = 0; p < NPAIR; ++p) {
-    atomicAdd(&red[p][e * 8 + 2 * c], acc[p][0]);
-    atomicAdd(&red[p][e * 8 + 2 * c + 1], acc[p][1]);
-  }
-  __syncthreads();
-  int p = 0;
-  for (int ti = 0; ti < NT; ++ti)
-    for (int tj = ti; tj < NT; ++tj, ++p)
-      for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-        const int a = 8 * ti + (i >> 3), b = 8 * tj + (i & 7);
-        if (a < E && b < E) {
-          atomicAdd(out + a * E + b, red[p][i]);
-          if (ti != tj) atomicAdd(out + b * E + a, red[p][i]);
+  for (int b = 0; b < NBLK; ++b) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPAIR * 64; i += blockDim.x) (&red[0][0])[i] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+      atomicAdd(&red[p][e * 8 + 2 * c], acc[b][p][0]);
+      atomicAdd(&red[p][e * 8 + 2 * c + 1], acc[b][p][1]);
+    }
+    __syncthreads();
+    double* ob = out + (size_t)b * out_stride;
+    int p = 0;
+    for (int ti = 0; ti < NT; ++ti)
+      for (int tj = ti; tj < NT; ++tj, ++p)
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+          const int a = 8 * ti + (i >> 3), bb = 8 * tj + (i & 7);
+          if (a < E && bb < E) {
+            atomicAdd(ob + a * E + bb, red[p][i]);
+            if (ti != tj) atomicAdd(ob + bb * E + a, red[p][i]);
+          }
         }
-      }
+  }
 }
 
 template <int NT>
-static void launch_loo_mma(const float* S, const float* P, int E, int64_t len, double* out, cudaStream_t st) {
-  k_loo_gram_mma<NT><<<148 * 8, 256, 0, st>>>(S, P, E, len, out);
+static void launch_loo_mma(const float* S, const float* P, int64_t p_stride, int n_blk, int E, int64_t len, double* out,
+                           int64_t out_stride, cudaStream_t st) {
+  const int grid = 148 * 8;
+  switch (n_blk) {
+    case 4: k_loo_gram_mma<NT, 4><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
+    case 3: k_loo_gram_mma<NT, 3><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
+    case 2: k_loo_gram_mma<NT, 2><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
+    default: k_loo_gram_mma<NT, 1><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -903,6 +918,30 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
   return RHE_OK;
 }
 
+extern "C" int rhe_loo_gram_multi(rhe_ctx* c, const float* S, const float* P, int64_t p_stride, int32_t n_blocks,
+                                  int32_t n_est, int64_t len, double* out, int64_t out_stride, void* stream) {
+  if (!c || !S || !P || !out) { rhe_set_error("rhe_loo_gram_multi: NULL argument"); return RHE_ERR_INVALID; }
+  if (n_blocks < 1 || p_stride < 0 || out_stride < (int64_t)n_est * n_est) { rhe_set_error("rhe_loo_gram_multi: bad block count / strides"); return RHE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool mma = len % 16 == 0 && n_est >= 1 && n_est <= 16 && p_stride % 4 == 0 && !getenv("PYRHE_B200_LOO_SIMT");
+  for (int b0 = 0; b0 < n_blocks;) {
+    const int nb = mma ? (n_blocks - b0 < 4 ? n_blocks - b0 : 4) : 1;
+    const float* Pb = P + (size_t)b0 * p_stride;
+    double* ob = out + (size_t)b0 * out_stride;
+    if (nb == 1) {
+      int rc = rhe_loo_gram(c, S, Pb, n_est, len, ob, stream);
+      if (rc) return rc;
+    } else {
+      for (int b = 0; b < nb; ++b) RHE_CUDA(cudaMemsetAsync(ob + (size_t)b * out_stride, 0, sizeof(double) * n_est * n_est, st));
+      if (n_est <= 8) launch_loo_mma<1>(S, Pb, p_stride, nb, n_est, len, ob, out_stride, st);
+      else launch_loo_mma<2>(S, Pb, p_stride, nb, n_est, len, ob, out_stride, st);
+      RHE_LAUNCH_CHECK(c);
+    }
+    b0 += nb;
+  }
+  return RHE_OK;
+}
+
 extern "C" int rhe_synth_genotypes(uint8_t* bed, int64_t n_rows, int64_t pitch, int32_t n_indv, int64_t first_snp,
                                    uint64_t seed, float missing_rate, void* stream) {
   if (!bed || n_rows < 0 || pitch <= 0 || n_indv <= 0 || (int64_t)(n_indv + 3) / 4 > pitch) {
@@ -946,9 +985,9 @@ extern "C" int rhe_loo_gram(rhe_ctx* c, const float* S, const float* P, int32_t 
   RHE_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_est * n_est, st));
   // register-resident kernels for up to 8 estimates (8-byte loads: even length, always true for B * Np)
   if (len % 16 == 0 && n_est <= 24 && !getenv("PYRHE_B200_LOO_SIMT")) {      // FP64 tensor-core Gram
-    if (n_est <= 8) launch_loo_mma<1>(S, P, n_est, len, out, st);
-    else if (n_est <= 16) launch_loo_mma<2>(S, P, n_est, len, out, st);
-    else launch_loo_mma<3>(S, P, n_est, len, out, st);
+    if (n_est <= 8) launch_loo_mma<1>(S, P, 0, 1, n_est, len, out, 0, st);
+    else if (n_est <= 16) launch_loo_mma<2>(S, P, 0, 1, n_est, len, out, 0, st);
+    else launch_loo_mma<3>(S, P, 0, 1, n_est, len, out, 0, st);
     RHE_LAUNCH_CHECK(c);
     return RHE_OK;
   }

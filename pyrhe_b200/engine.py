@@ -259,7 +259,14 @@ class RheEngine:
                 S[E_reg].copy_(self.nxe_S)
             length = B * Np
             scratch = None
-            for jl, j in enumerate(self.own):
+            if self.store_partials and len(self.own) > 0:
+                # stored partials are contiguous, and so are the XX slots of this rank's (contiguous) blocks: up to
+                # four blocks per launch share one read of S
+                j0 = self.own[0]
+                _lib.check(self.lib.rhe_loo_gram_multi(
+                    self._ctx, _lib.ptr(S), _lib.ptr(P_all), E * B * Np, len(self.own), E, length,
+                    _lib.ptr(XX[j0]), E * E, self._stream()))
+            for jl, j in enumerate(self.own if not self.store_partials else []):
                 if self.store_partials:
                     Pj = P_all[jl]
                 else:                                               # streaming policy: recompute the block
