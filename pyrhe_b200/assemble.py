@@ -197,10 +197,12 @@ def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo:
                 Hq = H.copy()
                 Hq[:, E_reg, :, :-1] = 0
                 WtLU[:, E_reg, :, :-1] = 0
-        QH = np.einsum("cd,sedb->secb", ht.Q, H)
-        QHq = QH if Hq is H else np.einsum("cd,sedb->secb", ht.Q, Hq)
-        r1 = np.einsum("sacb,secb->sae", H, QH)
-        r2 = np.einsum("sacb,secb->sae", WtLU, QHq)
+        # batched matmuls (the einsum forms of the same contractions are ~6x slower in numpy)
+        QH = ht.Q @ H                                                   # [S, E, C, B]
+        QHq = QH if Hq is H else ht.Q @ Hq
+        flat = lambda a: a.reshape(S, E, C * B)
+        r1 = flat(H) @ flat(QH).transpose(0, 2, 1)                      # sum_cb H[s,a,c,b] QH[s,e,c,b]
+        r2 = flat(WtLU) @ flat(QHq).transpose(0, 2, 1)
         V += r2 - 2 * r1
     V /= B
     np.divide(V, MM, out=T[:, :E, :E], where=MM != 0)
