@@ -52,7 +52,7 @@ struct TcState {
   int8_t* rq = nullptr;       // [NBa][Np]   limb l of column c at row l * R1p + c, permuted individual order
   double* col_dq = nullptr;   // [R1]        power-of-two dequantisation factor of every RHS column
   int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights of the current block
-  int32_t* pos_meta = nullptr;  // [cap_pos]      SNP row | fill << 24 of the current block
+  int32_t* pos_meta = nullptr;  // [SI][chunks][128][4] per-group decode metadata (SNP row | fill << 24 | mode << 26) of the current block
   unsigned int* wmax = nullptr; // [n_groups][B] max |weight| per weight group and column (float bits)
   int cap_pos = 0;
   std::vector<TcBlockMeta> blocks;
@@ -664,7 +664,7 @@ __device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq
 template <int MT, int G>
 __global__ void __launch_bounds__(PB_THREADS_OF(G), G == 2 ? 2 : 1)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
-            const int32_t* __restrict__ pos_meta, const int32_t* __restrict__ stage_info,
+            const int32_t* __restrict__ meta_v, int n_chunk, const int32_t* __restrict__ stage_info,
             const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
@@ -714,14 +714,17 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const int par = g / MT, q = g % MT;
     const uint8_t* base = bed + (i0 >> 2) + q * 32;
     const int n_own = n_stage > par ? (n_stage - par + SI - 1) / SI : 0;   // stages st = par + SI * u
-    // M[j % 6] = pos_meta of stage j (SNP row | fill << 24 | mode << 26, or -1 for padding), a register ring
-    // statically indexed by unrolling six stages and loaded five stages ahead.  The packed bytes travel through a
-    // per-warp cp.async ring, two stages ahead: lane pair (2 i, 2 i + 1) copies the two 16-byte halves of row
-    // 16 h + i of the warp's 32 rows (h = 0, 1), so every request is a whole 32-byte sector, and the row's owner
-    // thread reads it back after the warp has synchronised.  The row address of the pair comes from the owner's
-    // meta by shuffle.
-    int M[6];
-    auto meta_of = [&](int u) { return u < n_own ? __ldg(pos_meta + (par + SI * u) * 128 + t) : -1; };
+    // Decode metadata (SNP row | fill << 24 | mode << 26, or -1 for padding) comes from the per-group layout
+    // meta_v[par][chunk][t] = int4 of four consecutive own stages: ONE 16-byte load per four stages, issued two
+    // chunks ahead (per-stage 4-byte loads share hardware scoreboards with the newest load and stall on it every
+    // stage).  The packed bytes travel through a per-warp cp.async ring, PB_PKG - 1 stages ahead: lane pair
+    // (2 i, 2 i + 1) copies the two 16-byte halves of row 16 h + i of the warp's 32 rows (h = 0, 1), so every request
+    // is a whole 32-byte sector, and the row's owner thread reads it back after the warp has synchronised.  The row
+    // address of the pair comes from the owner's meta by shuffle.
+    const int4* mv = reinterpret_cast<const int4*>(meta_v) + (size_t)par * n_chunk * 128 + t;
+    const int4 none = make_int4(-1, -1, -1, -1);
+    auto chunk_of = [&](int c) { return c < n_chunk ? __ldg(mv + (size_t)c * 128) : none; };
+    auto comp = [](const int4& m, int r) { return r == 0 ? m.x : r == 1 ? m.y : r == 2 ? m.z : m.w; };
     const uint32_t ring = smem_u32(packed) + (uint32_t)warp * (PB_PKG * 1024);
     // slot layout [32 rows][32 B]: the two halves of a sector stay adjacent (the sector lands as one shared-memory
     // wavefront instead of two) and swap places in every other group of four rows (conflict-free 16-byte owner reads)
@@ -739,30 +742,29 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       }
       cp_async_commit();
     };
-    constexpr int AHEAD = PB_PKG - 1;                    // stages of packed bytes in flight (memory-level parallelism)
-    static_assert(AHEAD >= 2 && AHEAD <= 4, "the meta ring is loaded five stages ahead");
-#pragma unroll
-    for (int j = 0; j < 5; ++j) M[j] = meta_of(j);
-    M[5] = -1;
-#pragma unroll
-    for (int j = 0; j < AHEAD; ++j) issue(M[j], (uint32_t)j);
+    constexpr int AHEAD = 2;                             // stages of packed bytes in flight
+    static_assert(PB_PKG == AHEAD + 1, "ring depth");
+    int4 cur = chunk_of(0), nxt = chunk_of(1);
+    issue(n_own > 0 ? cur.x : -1, 0u);
+    issue(n_own > 1 ? cur.y : -1, 1u);
     uint32_t rd_slot = 0, wr_slot = AHEAD;               // ring slots of stage u and stage u + AHEAD
     const uint32_t tile0 = tileA_s + g * PB_AS * TC_TILE_A;
     uint64_t* const full0 = &sm->full_a[g * PB_AS];
     uint64_t* const empty0 = &sm->empty_a[g * PB_AS];
     PROF_T0();
     static_assert(PB_AS == 2, "slot parity below");
-    for (int u0 = 0; u0 < n_own; u0 += 6) {
+    for (int c = 0; 4 * c < n_own; ++c) {
+      const int4 nn = chunk_of(c + 2);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const int u = u0 + r;
+      for (int r = 0; r < 4; ++r) {
+        const int u = 4 * c + r;
         if (u < n_own) {                                 // warp-uniform
-          M[(r + 5) % 6] = meta_of(u + 5);
-          issue(M[(r + AHEAD) % 6], wr_slot);            // stage u + AHEAD
+          const int m_iss = u + AHEAD < n_own ? (r < 2 ? comp(cur, r + 2) : comp(nxt, r - 2)) : -1;
+          issue(m_iss, wr_slot);                         // stage u + AHEAD
           wr_slot = wr_slot + 1 == PB_PKG ? 0u : wr_slot + 1;
-          const int meta = M[r];
+          const int meta = comp(cur, r);
           const uint32_t tab = meta >= 0 ? tc_value_table(((uint32_t)meta >> 24) & 3u, (meta >> 26) & 1) : 0u;
-          const int a = r & 1;                           // u0 is even: slot = u % 2, use index u / 2
+          const int a = r & 1;                           // 4 c is even: slot = u % 2, use index u / 2
           cp_async_wait<AHEAD>();                        // stage u has landed (the AHEAD later ones may be in flight)
           __syncwarp();
           const uint4 lo = lds128(my_lo + rd_slot * 1024u), hi = lds128(my_hi + rd_slot * 1024u);
@@ -778,6 +780,8 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
           PROF_ADD(4);
         }
       }
+      cur = nxt;
+      nxt = nn;
     }
     // ---- epilogue: TMEM lane = position inside M-tile q; group (par, q) takes the bins k = par (mod SI)
     mbar_wait(&sm->acc_full, 0);
@@ -930,12 +934,17 @@ __global__ void k_tc_wmax(const float* __restrict__ w1, int m, int B, unsigned i
 __global__ void k_tc_quant_w(const float* __restrict__ w1, const float* __restrict__ w2, const int32_t* __restrict__ pos_rows,
                              int n_pos, int cap_pos, int m, int WG, int n_modes, int B, int Bp, int L, int F,
                              const unsigned int* __restrict__ wmax, int8_t* __restrict__ uq,
-                             const uint8_t* __restrict__ fill, int32_t* __restrict__ pos_meta) {
+                             const uint8_t* __restrict__ fill, int32_t* __restrict__ meta_v, int SI, int n_chunk) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pos * B * WG * n_modes) return;
   const int p = idx % n_pos, b = (idx / n_pos) % B, wg = (idx / (n_pos * B)) % WG, mode = idx / (n_pos * B * WG);
   const int row = pos_rows[p];
-  if (b == 0 && wg == 0) pos_meta[mode * n_pos + p] = row >= 0 ? (row | ((int)fill[row] << 24) | (mode << 26)) : -1;
+  if (b == 0 && wg == 0) {
+    // stage st = gp / 128 belongs to decode group par = st % SI as its own stage u = st / SI: meta_v[par][u / 4][t][u % 4]
+    const int gp = mode * n_pos + p, st = gp >> 7, t = gp & 127, par = st % SI, u = st / SI;
+    meta_v[((((size_t)par * n_chunk + (u >> 2)) * 128 + t) << 2) + (u & 3)] =
+        row >= 0 ? (row | ((int)fill[row] << 24) | (mode << 26)) : -1;
+  }
   const int e = (int)((wmax[wg * B + b] >> 23) & 255u) - 126;   // one fixed-point scale per (weight group, column)
   long long q = 0ll;
   if (row >= 0) {
@@ -1150,16 +1159,18 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
     if (s->uq) cudaFree(s->uq);
     if (s->pos_meta) cudaFree(s->pos_meta);
     s->cap_pos = round_up(n_modes * (n_pos + n_pos / 8), 128);
-    RHE_CUDA(cudaMalloc((void**)&s->pos_meta, sizeof(int32_t) * s->cap_pos));
+    RHE_CUDA(cudaMalloc((void**)&s->pos_meta, sizeof(int32_t) * (s->cap_pos + 8 * 512)));   // + one padded chunk per group
     RHE_CUDA(cudaMalloc((void**)&s->uq, (size_t)s->NCb * s->cap_pos));
     RHE_CUDA(cudaMemset(s->uq, 0, (size_t)s->NCb * s->cap_pos));
     rc = tc_encode_2d(s, &s->tm_uq, s->uq, (uint64_t)s->cap_pos, (uint64_t)s->NCb, (uint32_t)s->NCb);
     if (rc) return rc;
   }
+  const int n_stage = n_modes * n_pos / 128, SI = s->G / s->MT;
+  const int n_chunk = rhe_div_up(rhe_div_up(n_stage, SI), 4);       // chunks of four own stages per decode group
   if (n_pos > 0) {
     k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B * c->n_groups * n_modes, 256), 256, 0, st>>>(
         c->w1, c->w2, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, n_modes, B, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill,
-        s->pos_meta);
+        s->pos_meta, SI, n_chunk);
     RHE_LAUNCH_CHECK(c);
   }
   const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
@@ -1168,10 +1179,10 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   const int a_major = getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1;
   const int kcap = getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4;
   const int dbg = getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0;
-  const int n_stage = n_modes * n_pos / 128, rs_stride = g.n_sets == 2 ? c->Np : 0;
+  const int rs_stride = g.n_sets == 2 ? c->Np : 0;
 #define PB_LAUNCH(MT_, G_)                                                                                                   \
   k_tc_pass_b<MT_, G_><<<c->Np / (128 * MT_), PB_THREADS_OF(G_), smem, st>>>(                                                \
-      s->tm_uq, bed, g.pitch_bytes, c->Np, n_stage, s->pos_meta, meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp,  \
+      s->tm_uq, bed, g.pitch_bytes, c->Np, n_stage, s->pos_meta, n_chunk, meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp,  \
       s->L, s->NCb, s->F, s->wmax, c->cs, c->rowscale, rs_stride, P_out, S_accum, cols, a_major, kcap, bs, bzsh, dbg)
   if (s->G == 2) PB_LAUNCH(1, 2);
   else if (s->MT == 2) PB_LAUNCH(2, 4);
