@@ -90,5 +90,8 @@ def tcgen05_supported(plan, limbs: int = None) -> bool:
     nba = -(-(L * r1p) // 16) * 16
     bp = -(-plan.B // 2) * 2
     ncb = -(-(plan.n_groups * L * bp) // 16) * 16
-    return (nba <= 256 and plan.K * ncb <= 512 and plan.K <= 255 and plan.n_groups * plan.K * plan.B <= 1024
-            and plan.n_groups * plan.B <= 64)
+    if plan.K * ncb <= 512:
+        kg = plan.K                                   # all bins in one pass-B launch
+    else:
+        kg = 512 // (2 * ncb) if 2 * ncb <= 512 else (512 // ncb if ncb <= 512 else 0)   # bin groups
+    return (nba <= 256 and 1 <= kg <= 255 and plan.n_groups * kg * plan.B <= 512 and plan.n_groups * plan.B <= 64)

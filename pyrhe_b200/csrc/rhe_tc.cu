@@ -34,10 +34,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct TcBlockMeta {
   const int32_t* key = nullptr;   // the caller's bin_rows pointer identifies the block
   int m = 0;
+  int k0 = 0, kn = 0;             // the bins [k0, k0 + kn) of this bin group
   int n_pos = 0;                  // bin-sorted positions, every bin padded to a multiple of 128 rows
   int32_t* pos_rows = nullptr;    // [n_pos]       block-local SNP row (-1 = padding)
   int32_t* stage_info = nullptr;  // [n_pos / 128] bin | first-stage-of-bin << 8 | K-steps << 16
-  int32_t* bin_count = nullptr;   // [K]           rows per bin
+  int32_t* bin_count = nullptr;   // [kn]          rows per bin of the group
 };
 
 struct TcState {
@@ -49,6 +50,7 @@ struct TcState {
   int NCb = 0;          // pass B MMA N per (bin, M-tile) = round16(L * Bp)
   int MT = 2;           // 128-individual M-tiles per pass-B CTA
   int G = 4;            // pass-B decode groups per CTA: 4 (one CTA per SM) or 2 (two co-resident CTAs per SM)
+  int KG = 0;           // bins per pass-B launch: the accumulators of KG bins x MT tiles fill the 512 TMEM columns
   int8_t* rq = nullptr;       // [NBa][Np]   limb l of column c at row l * R1p + c, permuted individual order
   double* col_dq = nullptr;   // [R1]        power-of-two dequantisation factor of every RHS column
   int8_t* uq = nullptr;         // [NCb][cap_pos] quantised pass-B weights of the current block
@@ -622,18 +624,19 @@ __device__ __forceinline__ void tmem_combine(uint32_t taddr, int stride, double 
 // remainder of a row in pairs, so nothing is read beyond the limb rows of the (bin, tile) accumulator.
 template <int L>
 __device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq_s, const double* cs_s, uint32_t trow, int i,
-                                            int par, int SI, int q, int MT, int K, int WG, int B, int Bp, int NC, int Np,
+                                            int par, int SI, int q, int MT, int K, int K_total, int k0, int WG, int B, int Bp,
+                                            int NC, int Np,
                                             const float* __restrict__ rowscale, int rs_stride,
                                             float* __restrict__ P_out, float* __restrict__ S_accum) {
   for (int k = par; k < K; k += SI) {
     const bool has = cnt[k] > 0;
     const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
     for (int wg = 0; wg < WG; ++wg) {                // weight group = RHS set (GxE) or operand (dominance) -> estimate wg * K + k
-      const int e = wg * K + k;
+      const int e = wg * K_total + k0 + k;           // estimate index; k is local to this launch's bin group
       const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
       const size_t o0 = (size_t)e * B * Np + i;
       const double* dq = dq_s + wg * B;
-      const double* cs = cs_s + e * B;
+      const double* cs = cs_s + (wg * K + k) * B;
       auto emit = [&](int b, double val) {
         const float xf = has ? (float)(rs * (val * dq[b] - cs[b])) : 0.f;
         const size_t o = o0 + (size_t)b * Np;
@@ -665,7 +668,7 @@ template <int MT, int G>
 __global__ void __launch_bounds__(PB_THREADS_OF(G), G == 2 ? 2 : 1)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
             const int32_t* __restrict__ meta_v, int n_chunk, const int32_t* __restrict__ stage_info,
-            const int32_t* __restrict__ bin_count, int K, int WG, int B, int Bp, int L, int NC,
+            const int32_t* __restrict__ bin_count, int K, int K_total, int k0, int WG, int B, int Bp, int L, int NC,
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
             uint32_t tmem_cols, int a_major, int kcap, int bs, int bzsh, int dbg) {
@@ -692,7 +695,10 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   }
   if (warp == PB_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
   for (int i = threadIdx.x; i < n_stage; i += PB_THREADS) sm->info[i] = stage_info[i];
-  for (int i = threadIdx.x; i < WG * K * B; i += PB_THREADS) sm->cs[i] = cs[i];
+  for (int i = threadIdx.x; i < WG * K * B; i += PB_THREADS) {   // mean terms of this group's bins [k0, k0 + K)
+    const int wg = i / (K * B), rem = i - wg * (K * B);
+    sm->cs[i] = cs[(size_t)(wg * K_total + k0) * B + rem];
+  }
   for (int i = threadIdx.x; i < K; i += PB_THREADS) sm->cnt[i] = bin_count[i];
   // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
   for (int i = threadIdx.x; i < WG * B; i += PB_THREADS) sm->dq[i] = ldexp(1.0, (int)((wmax[i] >> 23) & 255u) - 126 - F);
@@ -790,9 +796,9 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
     if (!(dbg & 4)) switch (L) {
-      case 2: pb_epilogue<2>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
-      case 3: pb_epilogue<3>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
-      default: pb_epilogue<4>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
+      case 2: pb_epilogue<2>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
+      case 3: pb_epilogue<3>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
+      default: pb_epilogue<4>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
     }
     PROF_ADD(6);
     PROF_FLUSH(0);
@@ -913,10 +919,10 @@ k_tc_quant_rhs(const float* __restrict__ rhs, int Np, int R1p, int L, int F, int
   }
 }
 
-__global__ void k_tc_positions(const int32_t* __restrict__ bin_rows, const int32_t* __restrict__ bin_off,
+__global__ void k_tc_positions(const int32_t* __restrict__ bin_rows, const int32_t* __restrict__ bin_off, int k0,
                                const int32_t* __restrict__ pstart, int32_t* __restrict__ pos_rows) {
-  const int k = blockIdx.y;
-  const int n = bin_off[k + 1] - bin_off[k], p0 = pstart[k], span = pstart[k + 1] - p0;
+  const int kl = blockIdx.y, k = k0 + kl;            // local / global bin
+  const int n = bin_off[k + 1] - bin_off[k], p0 = pstart[kl], span = pstart[kl + 1] - p0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < span; i += gridDim.x * blockDim.x)
     pos_rows[p0 + i] = i < n ? bin_rows[bin_off[k] + i] : -1;
 }
@@ -1001,16 +1007,21 @@ int rhe_tc_create(rhe_ctx* c) {
   s->NBa = round_up(s->L * s->R1p, 16);
   s->Bp = round_up(g.n_vec, 2);
   s->NCb = round_up(c->n_groups * s->L * s->Bp, 16);   // weight groups (RHS sets) are stacked along N
-  s->MT = g.n_bins * 2 * s->NCb <= 512 ? 2 : 1;
+  // M-tiles per CTA and bins per launch: everything in one launch when the accumulators fit (two tiles if possible),
+  // otherwise bin groups of two-tile CTAs.
+  if (g.n_bins * 2 * s->NCb <= 512) { s->MT = 2; s->KG = g.n_bins; }
+  else if (g.n_bins * s->NCb <= 512) { s->MT = 1; s->KG = g.n_bins; }
+  else if (2 * s->NCb <= 512) { s->MT = 2; s->KG = 512 / (2 * s->NCb); }
+  else { s->MT = 1; s->KG = s->NCb <= 512 ? 512 / s->NCb : 0; }
   {
     // Optional variant (PYRHE_B200_PASSB_GROUPS=2): two half-size CTAs per SM (one M-tile, two decode groups, 256 TMEM
     // columns each), so that the epilogue of one overlaps the main loop of the other.  Measured equal to the default
     // on config 5 (0.69 vs 0.68 ms per block), so it stays opt-in.
     const char* envG = getenv("PYRHE_B200_PASSB_GROUPS");
     const bool fits2 = g.n_bins * s->NCb <= 256 && pb_smem_bytes(s->NCb, 2, 2) <= pb_budget(2);
-    if (fits2 && envG && atoi(envG) == 2) { s->G = 2; s->MT = 1; }
+    if (fits2 && envG && atoi(envG) == 2) { s->G = 2; s->MT = 1; s->KG = g.n_bins; }
   }
-  if (pb_smem_bytes(s->NCb, s->G / s->MT, s->G) > pb_budget(s->G) || s->NBa > 256 || g.n_bins * s->MT * s->NCb > 512 || g.n_bins > 255 || c->n_groups * g.n_bins * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
+  if (pb_smem_bytes(s->NCb, s->G / s->MT, s->G) > pb_budget(s->G) || s->NBa > 256 || s->KG < 1 || s->KG > 255 || c->n_groups * s->KG * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
     rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
     delete s;
     return RHE_ERR_UNSUPPORTED;
@@ -1101,25 +1112,27 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   return RHE_OK;
 }
 
-// Bin-sorted positions of a block: built once per block (keyed by the caller's bin_rows pointer).
+// Bin-sorted positions of the bins [k0, k0 + kn) of a block: built once per (block, bin group), keyed by the
+// caller's bin_rows pointer.  Bins are numbered locally (0 .. kn - 1) inside the group.
 static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows, const int32_t* bin_off_dev,
-                         const int32_t* bin_off_host, cudaStream_t st, TcBlockMeta** out) {
+                         const int32_t* bin_off_host, int k0, int kn, cudaStream_t st, TcBlockMeta** out) {
   for (TcBlockMeta& b : s->blocks)
-    if (b.key == bin_rows && b.m == m) { *out = &b; return RHE_OK; }
-  const int K = c->cfg.n_bins;
-  std::vector<int32_t> pstart(K + 1, 0), counts(K), info;
-  for (int k = 0; k < K; ++k) {
-    counts[k] = bin_off_host[k + 1] - bin_off_host[k];
-    pstart[k + 1] = pstart[k] + round_up(counts[k], 128);
-    for (int done = 0; done < counts[k]; done += 128) {
-      const int left = counts[k] - done;
-      info.push_back(k | ((done == 0) << 8) | (((left < 128 ? left : 128) + 31) / 32) << 16);
+    if (b.key == bin_rows && b.m == m && b.k0 == k0 && b.kn == kn) { *out = &b; return RHE_OK; }
+  std::vector<int32_t> pstart(kn + 1, 0), counts(kn), info;
+  for (int kl = 0; kl < kn; ++kl) {
+    counts[kl] = bin_off_host[k0 + kl + 1] - bin_off_host[k0 + kl];
+    pstart[kl + 1] = pstart[kl] + round_up(counts[kl], 128);
+    for (int done = 0; done < counts[kl]; done += 128) {
+      const int left = counts[kl] - done;
+      info.push_back(kl | ((done == 0) << 8) | (((left < 128 ? left : 128) + 31) / 32) << 16);
     }
   }
   TcBlockMeta b;
   b.key = bin_rows;
   b.m = m;
-  b.n_pos = pstart[K];
+  b.k0 = k0;
+  b.kn = kn;
+  b.n_pos = pstart[kn];
   const int n_alloc = b.n_pos > 0 ? b.n_pos : 128;
   RHE_CUDA(cudaMalloc((void**)&b.pos_rows, sizeof(int32_t) * n_alloc));
   const int n_modes = c->cfg.n_ops;                  // RHE-DOM runs the position list twice (count, then [g == 2] operand)
@@ -1128,14 +1141,14 @@ static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows,
     for (int mo = 1; mo < n_modes; ++mo) for (size_t i = 0; i < one; ++i) info.push_back(info[i]);
   }
   RHE_CUDA(cudaMalloc((void**)&b.stage_info, sizeof(int32_t) * (n_alloc / 128) * n_modes));
-  RHE_CUDA(cudaMalloc((void**)&b.bin_count, sizeof(int32_t) * K));
+  RHE_CUDA(cudaMalloc((void**)&b.bin_count, sizeof(int32_t) * kn));
   int32_t* d_pstart = nullptr;
-  RHE_CUDA(cudaMalloc((void**)&d_pstart, sizeof(int32_t) * (K + 1)));
-  RHE_CUDA(cudaMemcpyAsync(d_pstart, pstart.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st));
-  RHE_CUDA(cudaMemcpyAsync(b.bin_count, counts.data(), sizeof(int32_t) * K, cudaMemcpyHostToDevice, st));
+  RHE_CUDA(cudaMalloc((void**)&d_pstart, sizeof(int32_t) * (kn + 1)));
+  RHE_CUDA(cudaMemcpyAsync(d_pstart, pstart.data(), sizeof(int32_t) * (kn + 1), cudaMemcpyHostToDevice, st));
+  RHE_CUDA(cudaMemcpyAsync(b.bin_count, counts.data(), sizeof(int32_t) * kn, cudaMemcpyHostToDevice, st));
   if (!info.empty())
     RHE_CUDA(cudaMemcpyAsync(b.stage_info, info.data(), sizeof(int32_t) * info.size(), cudaMemcpyHostToDevice, st));
-  k_tc_positions<<<dim3(rhe_div_up(m, 256), K), 256, 0, st>>>(bin_rows, bin_off_dev, d_pstart, b.pos_rows);
+  k_tc_positions<<<dim3(rhe_div_up(m, 256), kn), 256, 0, st>>>(bin_rows, bin_off_dev, k0, d_pstart, b.pos_rows);
   RHE_LAUNCH_CHECK(c);
   RHE_CUDA(cudaStreamSynchronize(st));     // the host staging vectors die here (first sight of the block only)
   cudaFree(d_pstart);
@@ -1144,13 +1157,14 @@ static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows,
   return RHE_OK;
 }
 
-int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows, const int32_t* bin_off,
-                  const int32_t* bin_off_host, float* P_out, float* S_accum, cudaStream_t st) {
-  TcState* s = (TcState*)c->tc;
+// One launch per bin group of at most KG bins (the accumulators of KG bins x MT tiles fill the TMEM allocation); every
+// group walks only the bin-sorted rows of its own bins, so the block is still read once in total.
+static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, const int32_t* bin_rows, const int32_t* bin_off,
+                           const int32_t* bin_off_host, int k0, int kn, float* P_out, float* S_accum, cudaStream_t st) {
   const rhe_config& g = c->cfg;
   const int K = g.n_bins, B = g.n_vec;
   TcBlockMeta* meta = nullptr;
-  int rc = tc_block_meta(c, s, m, bin_rows, bin_off, bin_off_host, st, &meta);
+  int rc = tc_block_meta(c, s, m, bin_rows, bin_off, bin_off_host, k0, kn, st, &meta);
   if (rc) return rc;
   const int n_pos = meta->n_pos, n_modes = g.n_ops;
   if (n_modes * n_pos / 128 > PB_MAX_STAGES) { rhe_set_error("RHE_PATH_TCGEN05: block has %d bin-sorted positions (max %d)", n_pos, PB_MAX_STAGES * 128); return RHE_ERR_UNSUPPORTED; }
@@ -1173,7 +1187,7 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
         s->pos_meta, SI, n_chunk);
     RHE_LAUNCH_CHECK(c);
   }
-  const uint32_t cols = pow2_cols(K * s->MT * s->NCb);
+  const uint32_t cols = pow2_cols(kn * s->MT * s->NCb);
   int bzsh = 0;
   const int bs = pb_ring(s->NCb, s->MT, s->G, &bzsh), smem = pb_smem_bytes(s->NCb, bs, s->G);
   const int a_major = getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1;
@@ -1182,12 +1196,25 @@ int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows
   const int rs_stride = g.n_sets == 2 ? c->Np : 0;
 #define PB_LAUNCH(MT_, G_)                                                                                                   \
   k_tc_pass_b<MT_, G_><<<c->Np / (128 * MT_), PB_THREADS_OF(G_), smem, st>>>(                                                \
-      s->tm_uq, bed, g.pitch_bytes, c->Np, n_stage, s->pos_meta, n_chunk, meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp,  \
-      s->L, s->NCb, s->F, s->wmax, c->cs, c->rowscale, rs_stride, P_out, S_accum, cols, a_major, kcap, bs, bzsh, dbg)
+      s->tm_uq, bed, g.pitch_bytes, c->Np, n_stage, s->pos_meta, n_chunk, meta->stage_info, meta->bin_count, kn, K, k0,      \
+      c->n_groups, B, s->Bp, s->L, s->NCb, s->F, s->wmax, c->cs, c->rowscale, rs_stride, P_out, S_accum, cols, a_major,      \
+      kcap, bs, bzsh, dbg)
   if (s->G == 2) PB_LAUNCH(1, 2);
   else if (s->MT == 2) PB_LAUNCH(2, 4);
   else PB_LAUNCH(1, 4);
 #undef PB_LAUNCH
   RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
+int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows, const int32_t* bin_off,
+                  const int32_t* bin_off_host, float* P_out, float* S_accum, cudaStream_t st) {
+  TcState* s = (TcState*)c->tc;
+  const int K = c->cfg.n_bins;
+  for (int k0 = 0; k0 < K; k0 += s->KG) {
+    const int kn = K - k0 < s->KG ? K - k0 : s->KG;
+    int rc = tc_pass_b_group(c, s, bed, m, bin_rows, bin_off, bin_off_host, k0, kn, P_out, S_accum, st);
+    if (rc) return rc;
+  }
   return RHE_OK;
 }

@@ -180,28 +180,51 @@ class RheEngine:
             self.upload_block(j, np.ascontiguousarray(packed[a:b]))
         torch.cuda.current_stream(self.device).synchronize()
 
-    def load_genotypes_async(self, packed: np.ndarray):
-        """Start uploading this rank's blocks on a side stream from a background thread (the ctypes call releases
-        the GIL, so host staging of block j+1 overlaps the kernels of block j).  Pass the returned handle to
+    def load_genotypes_async(self, packed: np.ndarray, n_workers: int = 4, ring: int = 3):
+        """Pipelined ingest: `.bed` rows (numpy array or memmap) -> pinned staging ring -> device.
+
+        A pool of `n_workers` threads copies row ranges of block j from `packed` (page cache / disk) into one of `ring`
+        pinned slots (numpy copies release the GIL, so the reads fault in parallel); the uploader thread then queues
+        one asynchronous 2-D copy per block on a side stream and records an event.  Staging of block j+1 therefore
+        overlaps the PCIe copy of block j and the kernels of block j-1.  Pass the returned handle to
         `run(upload=...)`; block j is consumed as soon as its own copy has finished."""
         import threading
+        from concurrent.futures import ThreadPoolExecutor
         if self.bed is None:
             self.alloc_genotypes()
         copy_stream = torch.cuda.Stream(self.device)
         ready = {j: threading.Event() for j in self.own}
         events = {}
         errors = []
+        max_m = max((self.ranges[j][1] - self.ranges[j][0] for j in self.own), default=0)
+        ring = max(1, min(ring, len(self.own)))
+        n_workers = max(1, n_workers)
 
         def worker():
             try:
                 with torch.cuda.device(self.device):
-                    for j in self.own:
-                        a, b = self.ranges[j]
-                        self.upload_block(j, np.ascontiguousarray(packed[a:b]), stream=copy_stream)
-                        ev = torch.cuda.Event()
-                        ev.record(copy_stream)
-                        events[j] = ev
-                        ready[j].set()
+                    slots = [torch.empty((max_m, self.row_bytes), dtype=torch.uint8).pin_memory() for _ in range(ring)]
+                    views = [sl.numpy() for sl in slots]
+                    slot_free = [None] * ring                      # event of the last H2D copy that read the slot
+                    with ThreadPoolExecutor(n_workers) as pool:
+                        for n, j in enumerate(self.own):
+                            a, b = self.ranges[j]
+                            m = b - a
+                            k = n % ring
+                            if slot_free[k] is not None:
+                                slot_free[k].synchronize()
+                            step = -(-m // n_workers)
+                            futs = [pool.submit(np.copyto, views[k][r0:min(m, r0 + step)], packed[a + r0:a + min(m, r0 + step)])
+                                    for r0 in range(0, m, step)]
+                            for f in futs:
+                                f.result()
+                            self.upload_block(j, slots[k][:m], stream=copy_stream)
+                            ev = torch.cuda.Event()
+                            ev.record(copy_stream)
+                            events[j] = ev
+                            slot_free[k] = ev
+                            ready[j].set()
+                    copy_stream.synchronize()                      # the pinned slots die with this thread
             except Exception as exc:          # surfaced by run()
                 errors.append(exc)
                 for e in ready.values():

@@ -177,6 +177,8 @@ EDGE_SHAPES = [
     (1000, 96,  4, 2, 4, 1, 0.01, (),            "binary", "rhe"),       # 24 SNPs per block: far fewer rows than one 128-row stage
     (777,  640, 2, 4, 5, 3, 0.02, (100, 101),    "mean",   "rhe_dom"),   # dominance operand with covariates
     (640,  512, 2, 3, 4, 2, 0.01, (),            "binary", "genie"),     # G + GxE + NxE
+    (600, 1280, 20, 10, 4, 2, 0.01, (),          "binary", "rhe"),       # 20 bins: three pass-B launches of <= 8 bins (TMEM columns)
+    (520,  960, 11, 9, 3, 0, 0.00, (3,),         "mean",   "rhe_dom"),   # 11 bins x 2 weight groups: bin groups of 4
 ]
 
 
