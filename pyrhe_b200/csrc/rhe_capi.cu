@@ -344,10 +344,24 @@ k_bin_gram(int m, int Rs, int B, int K, const int32_t* __restrict__ bin_rows,
     if (p < Rs * Rs) {
       int c1 = p / Rs, c2 = p % Rs;
       if (c2 < c1) continue;
-      for (int i = lo; i < hi; ++i) {
+      // four independent gather chains (row index -> row) in flight: the loop is pure load latency
+      double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int i = lo;
+      for (; i + 4 <= hi; i += 4) {
+        const double* r0 = T + (size_t)bin_rows[i] * Rs;
+        const double* r1 = T + (size_t)bin_rows[i + 1] * Rs;
+        const double* r2 = T + (size_t)bin_rows[i + 2] * Rs;
+        const double* r3 = T + (size_t)bin_rows[i + 3] * Rs;
+        acc += r0[c1] * r0[c2];
+        a1 += r1[c1] * r1[c2];
+        a2 += r2[c1] * r2[c2];
+        a3 += r3[c1] * r3[c2];
+      }
+      for (; i < hi; ++i) {
         const double* row = T + (size_t)bin_rows[i] * Rs;
         acc += row[c1] * row[c2];
       }
+      acc += a1 + a2 + a3;
       if (lo < hi) {
         atomicAdd(gram + ((size_t)e * Rs + c1) * Rs + c2, acc);
         if (c1 != c2) atomicAdd(gram + ((size_t)e * Rs + c2) * Rs + c1, acc);
@@ -894,7 +908,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
                                                            c->mu, c->f2, c->t_std, c->w1, c->w2, c->shiftv, wmax);
     RHE_LAUNCH_CHECK(c);
   }
-  k_bin_gram<<<dim3(c->E_reg, 32), 256, 0, st>>>(m, Rs, B, K, bin_rows, s_off_dev, c->t_std, c->shiftv, gram_out, c->cs);
+  k_bin_gram<<<dim3(c->E_reg, 64), 256, 0, st>>>(m, Rs, B, K, bin_rows, s_off_dev, c->t_std, c->shiftv, gram_out, c->cs);
   RHE_LAUNCH_CHECK(c);
   if (c->timing) RHE_CUDA(cudaEventRecord(tev[3], st));
   // ---- pass B
