@@ -582,12 +582,10 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
 #define PB_PKG 3                  // per-warp cp.async ring depth (in the group's own stages): PB_PKG - 1 stages in flight
 #define PB_AS 2                   // shared-memory A slots per decode group (decode of tile u+1 overlaps the MMAs of tile u)
 
-#define PB_MAX_STAGES 512
 #define PB_MAX_KB 512             // K * B entries of the per-bin mean term staged in shared memory
 struct PbSmem {
   uint64_t full_a[PB_G * PB_AS], empty_a[PB_G * PB_AS], full_b[PB_BS], empty_b[PB_BS], acc_full;
   uint32_t tmem_base;
-  int32_t info[PB_MAX_STAGES];    // stage_info of the block
   double cs[PB_MAX_KB];           // per-(bin, column) mean term
   double dq[64];                  // per-column dequantisation factor 2^(e - F)
   int32_t cnt[256];               // rows per bin
@@ -694,7 +692,6 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     fence_barrier_init();
   }
   if (warp == PB_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
-  for (int i = threadIdx.x; i < n_stage; i += PB_THREADS) sm->info[i] = stage_info[i];
   for (int i = threadIdx.x; i < WG * K * B; i += PB_THREADS) {   // mean terms of this group's bins [k0, k0 + K)
     const int wg = i / (K * B), rem = i - wg * (K * B);
     sm->cs[i] = cs[(size_t)(wg * K_total + k0) * B + rem];
@@ -836,18 +833,17 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
       const uint32_t idesc = idesc_i8(128, NC, a_major);   // A is MN-major: 128 individuals contiguous per SNP row
       const uint32_t fb = smem_u32(&sm->full_b[0]), eb = smem_u32(&sm->empty_b[0]);
       const uint32_t fa = smem_u32(&sm->full_a[g * PB_AS]), ea = smem_u32(&sm->empty_a[g * PB_AS]);
-      const uint32_t info_s = smem_u32(&sm->info[0]);
       const uint64_t adesc0 = smem_desc_sw128(tileA_s + g * PB_AS * TC_TILE_A, TC_TILE_A, 1024);
       const uint64_t bdesc0 = smem_desc_sw128(smem_u32(tileB), 16, 1024);
       const uint32_t dq = tmem + (uint32_t)(q * NC);
       PROF_T0();
       int b = par;                                     // par < SI <= bs
       uint32_t ph_b = 0, a = 0, ph_a = 0;
-      uint32_t info = par < n_stage ? lds32(info_s + 4u * par) : 0u;
+      uint32_t info = par < n_stage ? (uint32_t)__ldg(stage_info + par) : 0u;      // one stage ahead, straight from L2
       for (int st = par; st < n_stage; st += SI) {
         const uint32_t k = info & 255u;
         const int ksteps = min((int)(info >> 16), kcap);
-        if (st + SI < n_stage) info = lds32(info_s + 4u * (uint32_t)(st + SI));
+        if (st + SI < n_stage) info = (uint32_t)__ldg(stage_info + st + SI);
         PROF_ADD(0);
         mbar_wait_s(fb + 8u * (uint32_t)(b >> bzsh), ph_b);
         PROF_ADD(1);
@@ -1167,7 +1163,6 @@ static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, co
   int rc = tc_block_meta(c, s, m, bin_rows, bin_off, bin_off_host, k0, kn, st, &meta);
   if (rc) return rc;
   const int n_pos = meta->n_pos, n_modes = g.n_ops;
-  if (n_modes * n_pos / 128 > PB_MAX_STAGES) { rhe_set_error("RHE_PATH_TCGEN05: block has %d bin-sorted positions (max %d)", n_pos, PB_MAX_STAGES * 128); return RHE_ERR_UNSUPPORTED; }
   if (n_modes * n_pos > s->cap_pos) {
     RHE_CUDA(cudaStreamSynchronize(st));
     if (s->uq) cudaFree(s->uq);
