@@ -56,6 +56,37 @@ __global__ void k_probe(const __grid_constant__ CUtensorMap map, const int* rows
   if (lane == 0) { cycles[0] = t1; cycles[1] = t2; }
 }
 
+// NW warps issue 32 gather4 each per round into their own 128 x W tile and barrier: does the rate scale with warps?
+__global__ void k_rate(const __grid_constant__ CUtensorMap map, const int* rows, int W, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const uint32_t bar_s = smem_u32(&bar[warp]);
+  if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int r0 = rows[4 * lane], r1 = rows[4 * lane + 1], r2 = rows[4 * lane + 2], r3 = rows[4 * lane + 3];
+  const uint32_t tile = smem_u32(smem) + warp * 128 * W + lane * 4 * W;
+  const int rounds = 41;
+  long long t0 = 0;
+  for (int rd = 0; rd < rounds; ++rd) {
+    if (rd == 1) { __syncthreads(); t0 = clock64(); }
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(128 * W) : "memory");
+    __syncwarp();
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(tile), "l"(&map), "r"(bar_s), "r"((rd % 8) * 128 + warp * 16), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 22) && !ok; ++spin)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar_s), "r"(rd & 1) : "memory");
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) cycles[0] = (clock64() - t0) / (rounds - 1);
+  (void)nw;
+}
+
 int main() {
   const int M = 4096, pitch = 1024;           // rows x bytes
   std::vector<uint8_t> h((size_t)M * pitch);
@@ -117,6 +148,25 @@ int main() {
         printf("W=%3d box_rows=%d swizzle=%d: mismatches=%d (oob row: %d)  issue %lld cyc, complete %lld cyc\n", W, box_rows, sw, bad,
                bad_oob, cyc[0], cyc[1]);
       }
+    }
+  }
+  for (int W : {64, 128}) {
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {(cuuint32_t)W, 1};
+    cuuint32_t estr[2] = {1, 1};
+    enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    for (int nw : {1, 2, 4, 8}) {
+      cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 128 * 128);
+      k_rate<<<1, 32 * nw, nw * 128 * W>>>(map, d_rows, W, d_cyc);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+      printf("rate: W=%3d, %d warps x 32 gather4 per round: %lld cycles per round = %.1f cycles per gather4 (SM-wide) %s\n", W, nw, cyc,
+             (double)cyc / (32.0 * nw), e == cudaSuccess ? "" : cudaGetErrorString(e));
     }
   }
   return 0;
