@@ -7,16 +7,17 @@
 // 8-bit limbs stacked along N, so the int32 accumulation is EXACT and the result is independent of how
 // the work is split.
 //
-// Packed rows are streamed with thread-private cp.async rings (a decode thread owns one SNP row and only
-// ever reads back what it fetched itself, so no block-level barrier guards the ring).  A 32-bit packed word
-// expands to sixteen int8 values with 3 logic ops and 4 byte-permutes.
-//   pass A: the expanded A operand goes straight from registers into TENSOR MEMORY (tcgen05.st) and the MMA
-//           reads A from TMEM (K-major), so the big operand never touches shared memory; only the small Rq
-//           tile (TMA, 128B swizzle) does.
+// A decode thread owns one SNP row; a 32-bit packed word expands to sixteen int8 values with 2 logic ops,
+// 4 byte-permutes and 3 multiply-high shifts.  Warps are specialised (decode groups, TMA producers, one MMA-issue
+// warp per decode group); every role loop is warp-uniform with elect.sync around the issue.
+//   pass A: packed super-stages (128 rows x 128 B) arrive as 2-D TMA boxes; the expanded A operand goes straight
+//           from registers into TENSOR MEMORY (tcgen05.st) and the MMA reads A from TMEM (K-major), so the big
+//           operand never touches shared memory as bytes; only the small Rq tiles (TMA, 128B swizzle) do.
 //   pass B: needs the same bytes as an MN-major operand (128 individuals contiguous per SNP row), which TMEM
 //           cannot provide, so the tile is written to shared memory (128B swizzle) and read by the MMA through an
-//           MN-major descriptor.  One CTA owns MT x 128 individuals and ALL bins: bin k accumulates in its
-//           own TMEM columns, rows are gathered by bin, and the mainloop runs over the whole block.
+//           MN-major descriptor.  Rows are gathered by bin through per-warp cp.async rings.  One CTA owns
+//           MT x 128 individuals and the bins of one bin group (all bins when their accumulators fit the 512 TMEM
+//           columns): bin k accumulates in its own TMEM columns and the mainloop runs over the group's rows.
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -379,7 +380,7 @@ struct PaSmem {
 __global__ void __launch_bounds__(PA_THREADS, 2)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ CUtensorMap tm_bed, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
-            double* __restrict__ t_raw, uint32_t tmem_cols, uint32_t col_a, int mode, int bsa, int dbg) {
+            double* __restrict__ t_raw, uint32_t tmem_cols, uint32_t col_a, int mode, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* packed = smem;                            // [PA_GS][128 rows][128 B], 128-byte swizzle
@@ -528,8 +529,8 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
   } else {
     // ---- MMA issue: one warp per decode group (one elected lane issues), so no single thread serialises the block.
     // Every MMA accumulates (the accumulator was zeroed), hence the issuers need no mutual ordering.  Group g takes
-    // the sub-tiles j = g, g + PA_G, ...: ring slot j % bsa (bsa is a multiple of PA_G, so a slot always belongs to
-    // the same group), TMEM A slot alternating between 2 g and 2 g + 1.
+    // the sub-tiles j = g, g + PA_G, ...: the Rq tile j & 3 of super-stage slot (j >> 2) % PA_RS, TMEM A slot
+    // alternating between 2 g and 2 g + 1.
     {
       const int g = warp - (PA_DW + 2);
       const uint32_t idesc = idesc_i8(128, NB, 0);
@@ -971,8 +972,7 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
-static inline int pa_smem_bytes(int nb, int) { return PA_RS * 4 * nb * 128 + PA_GS * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
-static inline int pa_ring(int) { return PA_RS; }
+static inline int pa_smem_bytes(int nb) { return PA_RS * 4 * nb * 128 + PA_GS * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
 static inline int pb_smem_bytes(int nc, int bs, int G = PB_G) { return G * PB_AS * TC_TILE_A + bs * nc * 128 + 4 * G * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
 // Uq ring: `bs` tile slots in batches of 2^bzsh tiles that share one barrier pair.  Either a batch spans at least
 // one stage of every issuer (2^bzsh >= SI = G / MT), or there is no batching and bs is a multiple of SI (a slot is
@@ -1039,7 +1039,7 @@ int rhe_tc_create(rhe_ctx* c) {
   if (e != cudaSuccess) { rhe_set_error("tensor-core workspace allocation failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
   int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
   if (rc) return rc;
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa, pa_ring(s->NBa))));
+  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa)));
   {
     int sh;
     const int smem = pb_smem_bytes(s->NCb, pb_ring(s->NCb, s->MT, s->G, &sh), s->G);
@@ -1090,19 +1090,18 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   }
   if (splits > c->Np / 512) splits = c->Np / 512 > 0 ? c->Np / 512 : 1;
   const uint32_t col_a = (uint32_t)round_up(s->NBa, 32);
-  const int bsa = pa_ring(s->NBa);
   CUtensorMap tm_bed;                                  // the block's packed rows as a 2-D byte tensor [m][pitch]
   int rc = tc_encode_2d(s, &tm_bed, const_cast<uint8_t*>(bed), (uint64_t)c->cfg.pitch_bytes, (uint64_t)m, 128);
   if (rc) return rc;
   const int dbg = getenv("PYRHE_TC_DEBUG_SKIPA") ? atoi(getenv("PYRHE_TC_DEBUG_SKIPA")) : 0;
-  k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa, bsa), st>>>(
+  k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
       s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw,
-      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0, bsa, dbg);
+      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0, dbg);
   RHE_LAUNCH_CHECK(c);
   if (c->cfg.n_ops == 2) {   // RHE-DOM: the same pass over the [g == 2] indicator operand
-    k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa, bsa), st>>>(
+    k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
         s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq,
-        c->t_raw + (size_t)m * c->R1, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1, bsa, 0);
+        c->t_raw + (size_t)m * c->R1, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1, 0);
     RHE_LAUNCH_CHECK(c);
   }
   return RHE_OK;
