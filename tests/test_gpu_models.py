@@ -122,3 +122,38 @@ def test_extender_block_ops_match_oracle():
     yxxy = model._compute_yXXy(X, model.pheno)
     assert np.isfinite(yxxy).all() and yxxy.shape == (1, 1)
     model._finalize()
+
+
+def test_cli_flags_and_config_file(tmp_path):
+    """run_rhe.py (the reference's entry point, run_rhe.py:161-193): flags and a --config file give the numbers of
+    the model API, and write the log and the .tr / .MN trace summaries."""
+    import subprocess
+    import sys
+    from pyrhe_b200 import synth
+    from pyrhe_b200.models import StreamingRHE
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = synth.make_dataset(str(tmp_path / "data"), "cli", N=400, M=640, K=2, seed=3, n_cov=2)
+    common = dict(num_jack=4, num_random_vec=5, seed=0)
+    ref = StreamingRHE(model="rhe", geno_file=paths["geno_file"], annot_file=paths["annot_file"],
+                       pheno_file=paths["pheno_file"], cov_file=paths["cov_file"], device="cuda", **common)(trait=0)
+    out1 = tmp_path / "flags.out"
+    cmd = [sys.executable, os.path.join(root, "run_rhe.py"), "--model", "rhe", "--streaming", "-g", paths["geno_file"],
+           "-annot", paths["annot_file"], "-p", paths["pheno_file"], "-c", paths["cov_file"], "-k", "5", "-jn", "4",
+           "-s", "0", "--device", "cuda", "-o", str(out1), "--trace", "--trace_dir", str(tmp_path)]
+    subprocess.run(cmd, check=True, cwd=str(tmp_path), capture_output=True, timeout=600)
+    text = out1.read_text()
+    assert "Active essential options:" in text and "Runtime:" in text
+    base = os.path.basename(paths["pheno_file"])
+    assert (tmp_path / f"run_{base}.tr").exists() and (tmp_path / f"run_{base}.MN").exists()
+
+    def total_h2(t):
+        return float(re.search(r"Total h2 : (\S+) SE", t).group(1))
+    assert total_h2(text) == pytest.approx(float(np.asarray(ref["h2_total"])[-1]), rel=1e-9)
+    cfg = tmp_path / "cfg.txt"
+    out2 = tmp_path / "config.out"
+    cfg.write_text("[PyRHE_Config]\nmodel = rhe\nstreaming = True\ngenotype = %s\nannotation = %s\nphenotype = %s\n"
+                   "covariate = %s\nnum_vec = 5\nnum_block = 4\nseed = 0\ndevice = cuda\noutput = %s\n"
+                   % (paths["geno_file"], paths["annot_file"], paths["pheno_file"], paths["cov_file"], out2))
+    subprocess.run([sys.executable, os.path.join(root, "run_rhe.py"), "--config", str(cfg)], check=True,
+                   cwd=str(tmp_path), capture_output=True, timeout=600)
+    assert total_h2(out2.read_text()) == pytest.approx(total_h2(text), rel=1e-12)
