@@ -83,3 +83,8 @@ def test_batched_assembly_equals_scalar_specification(name):
     Tb, qb = normal_equations_batch(plan, ht, pieces["XX"], G_loo, pieces["M"])
     np.testing.assert_allclose(Tb, T, rtol=1e-12, atol=1e-12 * np.abs(T).max())
     np.testing.assert_allclose(qb, q, rtol=1e-12, atol=1e-12 * np.abs(q).max())
+    # the reusable-buffer helper the production tail uses gives the same leave-one-out pieces
+    from pyrhe_b200.assemble import loo_grams
+    buf = loo_grams(pieces["G_blk"])
+    np.testing.assert_allclose(buf, G_loo, rtol=1e-13, atol=1e-13 * np.abs(G_loo).max())
+    assert loo_grams(pieces["G_blk"], buf) is buf
