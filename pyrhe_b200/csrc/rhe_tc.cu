@@ -109,6 +109,11 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t addr, uint32_t parity) {
   }
   asm volatile("trap;");
 }
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double r;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t r;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
@@ -634,10 +639,11 @@ __device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq
       const int e = wg * K_total + k0 + k;           // estimate index; k is local to this launch's bin group
       const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
       const size_t o0 = (size_t)e * B * Np + i;
-      const double* dq = dq_s + wg * B;
-      const double* cs = cs_s + (wg * K + k) * B;
+      // explicit shared-space loads: through the generic pointers these are LD.E with twice the latency
+      const uint32_t dq = smem_u32(dq_s + wg * B);
+      const uint32_t cs = smem_u32(cs_s + (wg * K + k) * B);
       auto emit = [&](int b, double val) {
-        const float xf = has ? (float)(rs * (val * dq[b] - cs[b])) : 0.f;
+        const float xf = has ? (float)(rs * (val * lds_f64(dq + 8u * (uint32_t)b) - lds_f64(cs + 8u * (uint32_t)b))) : 0.f;
         const size_t o = o0 + (size_t)b * Np;
         if (P_out) P_out[o] = xf;
         if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
