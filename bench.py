@@ -7,10 +7,15 @@
 A "step" is one full RHE jackknife over synthetic genotypes of the named shape: every jackknife
 block of every rank through the block kernels, the all-reduce of the totals, the leave-one-out
 Grams, the D2H of the Gram pieces, host assembly of the J+1 normal equations and their solves.
-`value` = packed .bed bytes (ceil(N0/4) * M) / step time with the genotypes resident in HBM;
-`e2e` = the same step with every block's rows copied from pinned host memory inside the timed
-region.  The problem size is fixed as GPUs are added ("scaling": "strong"), as BASELINE.json
-quotes the metric for one problem at 1/2/4/8 GPUs.
+`value` = packed .bed bytes (ceil(N0/4) * M) / step time with the ingested genotypes resident in HBM
+(packed rows + the per-SNP allele counts the ingest kernel takes when a block lands, DESIGN.md §2);
+`e2e` = the same job through the engine's ingest API (`stream_genotypes`: host rows -> staging threads ->
+pinned ring -> PCIe -> device, counts on arrival) with every byte crossing host memory and PCIe inside the
+timed region; `e2e_model_api` = `StreamingRHE(...)(trait=0)` on a real `.bed` file at config-2 size;
+`first_pass_ms` = the very first pass of a fresh context (what a model run actually executes), and
+`step_recount_ms` the step when every block's allele counts are re-taken inside it (three reads per block,
+the round-1 structure).  The problem size is fixed as GPUs are added ("scaling": "strong"), as
+BASELINE.json quotes the metric for one problem at 1/2/4/8 GPUs.
 """
 from __future__ import annotations
 
@@ -117,42 +122,110 @@ def reference_arm(args, wl, rank):
 
 
 # ----------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config5", choices=list(WORKLOADS))
-    ap.add_argument("--kernel_path", type=int, default=int(os.environ.get("PYRHE_B200_PATH", "1")),
-                    help="1 = int8 tcgen05 kernels (default), 0 = CUDA-core validation kernels")
-    ap.add_argument("--cpu_snps", type=int, default=200, help="SNPs per block of the CPU sample")
-    ap.add_argument("--no_cpu_baseline", action="store_true")
-    ap.add_argument("--no_e2e", action="store_true")
-    ap.add_argument("--ring_blocks", type=int, default=4, help="pinned host ring (blocks) for the e2e leg")
-    args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        reference_arm(args, wl, rank)
-        return
-
+def write_synthetic_plink(outdir, wl, dev, chunk_snps=4096):
+    """A real PLINK data set of the workload's shape on local storage: `.bed` rows generated on the device
+    (`rhe_synth_genotypes`, the generator of the resident leg) and written out, text files as the reference reads them."""
     import torch
-    import torch.distributed as dist
-    from pyrhe_b200 import _lib
-    from pyrhe_b200.assemble import PathPlan, normal_equations_batch, loo_grams
+    from pyrhe_b200 import _lib, synth
+    lib = _lib.load()
+    N, M, K, Cc = wl["N"], wl["M"], wl["K"], wl["C"]
+    rb = (N + 3) // 4
+    pitch = (rb + 127) // 128 * 128
+    prefix = os.path.join(outdir, "bench")
+    st = torch.cuda.current_stream(dev)
+    buf = torch.zeros((chunk_snps, pitch), dtype=torch.uint8, device=dev)
+    host = torch.empty((chunk_snps, rb), dtype=torch.uint8).pin_memory()
+    with open(prefix + ".bed", "wb") as f:
+        f.write(synth.BED_MAGIC)
+        for s0 in range(0, M, chunk_snps):
+            m = min(chunk_snps, M - s0)
+            _lib.check(lib.rhe_synth_genotypes(C.c_void_p(buf.data_ptr()), m, pitch, N, s0, 1234, 0.001,
+                                               C.c_void_p(st.cuda_stream)))
+            host[:m].copy_(buf[:m, :rb])
+            f.write(host[:m].numpy().tobytes())
+    rng = np.random.default_rng(1)
+    ids = np.arange(N)
+    np.savetxt(prefix + ".fam", np.stack([ids, ids, 0 * ids, 0 * ids, 0 * ids, 0 * ids - 9], 1), fmt="%d")
+    with open(prefix + ".bim", "w") as f:
+        f.write("".join(f"1\trs{i}\t0\t{i}\tA\tG\n" for i in range(M)))
+    annot = synth.random_annot(M, K, rng)
+    np.savetxt(prefix + ".annot", annot, fmt="%d")
+    y = rng.standard_normal(N)
+    with open(prefix + ".pheno", "w") as f:
+        f.write("FID IID pheno0\n")
+        f.write("".join(f"{i} {i} {v!r}\n" for i, v in enumerate(y.tolist())))
+    W = rng.standard_normal((N, Cc))
+    W[:, 0] = rng.random(N) < 0.5
+    with open(prefix + ".cov", "w") as f:
+        f.write("FID IID " + " ".join(f"cov{c}" for c in range(Cc)) + "\n")
+        np.savetxt(f, np.concatenate([ids[:, None], ids[:, None], W], 1), fmt=["%d", "%d"] + ["%.17g"] * Cc)
+    return dict(geno_file=prefix, annot_file=prefix + ".annot", pheno_file=prefix + ".pheno", cov_file=prefix + ".cov")
+
+
+def model_api_e2e(args, dev):
+    """`e2e_model_api`: the call a user makes -- `StreamingRHE(**files)(trait=0)` -- on a real `.bed` file at the size
+    of BASELINE.json's single-GPU configuration, read from local storage inside the timed region (file -> staging
+    threads -> pinned ring -> PCIe -> HBM -> kernels -> estimates).  Run twice more with the genotype ring forced
+    (`PYRHE_B200_RING_BLOCKS=4`): HBM use bounded by four block slots whatever the size of the file, once with stored
+    partials (one pass over the file) and once with the streaming policy (two passes)."""
+    import shutil
+    import tempfile
+    import torch
+    wl = dict(WORKLOADS[args.api_workload])
+    bed_bytes = float((wl["N"] + 3) // 4) * wl["M"]
+    root = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 1.5 * bed_bytes + 4e9 else None
+    if root is None and shutil.disk_usage(tempfile.gettempdir()).free < 1.5 * bed_bytes:
+        return {"unavailable": "no local storage for the synthetic .bed"}
+    outdir = tempfile.mkdtemp(prefix="pyrhe_bench_", dir=root)
+    try:
+        t0 = time.perf_counter()
+        paths = write_synthetic_plink(outdir, wl, dev)
+        t_write = time.perf_counter() - t0
+        import pyrhe.models as models
+        from pyrhe.src.util import Logger
+        out = {"workload": args.api_workload, "storage": "tmpfs (/dev/shm)" if root else "local disk (page cache after the write)",
+               "bed_bytes": bed_bytes, "write_dataset_s": t_write, "runs": []}
+        for cls_name, ring in (("StreamingRHE", None), ("RHE", 4), ("StreamingRHE", 4)):
+            if ring is None:
+                os.environ.pop("PYRHE_B200_RING_BLOCKS", None)
+            else:
+                os.environ["PYRHE_B200_RING_BLOCKS"] = str(ring)
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+            t0 = time.perf_counter()
+            model = getattr(models, cls_name)(model="rhe", num_jack=wl["J"], num_random_vec=wl["B"], seed=0,
+                                              geno_impute_method="binary", device="cuda", num_workers=1,
+                                              log=Logger(suppress=True, debug_mode=False), **paths)
+            t_ctor = time.perf_counter() - t0
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            res = model(trait=0)
+            torch.cuda.synchronize(dev)
+            t_call = time.perf_counter() - t0
+            rep = dict(getattr(model, "ingest_report", {}))
+            out["runs"].append({
+                "call": f"{cls_name}(...)(trait=0)", "forced_ring_blocks": ring, "constructor_s": t_ctor,
+                "call_s": t_call, "value": bed_bytes / t_call / 1e9, "unit": UNIT,
+                "staged_gbs": rep.get("staged_bytes", 0) / t_call / 1e9,
+                "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "ingest": rep,
+                "sigma_e": float(np.ravel(res["sigma_ests_total"])[-1])})
+            del model
+        os.environ.pop("PYRHE_B200_RING_BLOCKS", None)
+        out["value"] = out["runs"][0]["value"]
+        out["unit"] = UNIT
+        return out
+    finally:
+        shutil.rmtree(outdir, ignore_errors=True)
+
+
+def build_problem(wl, args, rank, world, dev):
+    """Synthetic inputs of one workload + an engine with this rank's blocks generated in HBM and ingested."""
+    import torch
+    from pyrhe_b200 import _lib, synth
+    from pyrhe_b200.assemble import PathPlan
     from pyrhe_b200.engine import RheEngine
     from pyrhe_b200.hostmath import host_terms
-    from pyrhe_b200 import synth
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-
     N, M, J, K, Cc, B = wl["N"], wl["M"], wl["J"], wl["K"], wl["C"], wl["B"]
     rng = np.random.default_rng(0)
     annot = synth.random_annot(M, K, rng)
@@ -186,14 +259,65 @@ def main():
         _lib.check(lib.rhe_synth_genotypes(C.c_void_p(rows.data_ptr()), m, eng.pitch, N, eng.ranges[j][0], 1234, 0.0,
                                            C.c_void_p(stream.cuda_stream)))
     torch.cuda.synchronize(dev)
+    # ingest: per-SNP allele counts, once per resident block (what `upload_block` does on arrival)
+    ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ce0.record(stream)
+    eng.count_all()
+    ce1.record(stream)
+    torch.cuda.synchronize(dev)
+    ingest_count_ms = ce0.elapsed_time(ce1) / max(len(eng.own), 1)
+    return dict(eng=eng, plan=plan, ht=ht, Z=Z, W=W, Y_res=Y_res, env=env, store=store, ingest_count_ms=ingest_count_ms)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config5", choices=list(WORKLOADS))
+    ap.add_argument("--kernel_path", type=int, default=int(os.environ.get("PYRHE_B200_PATH", "1")),
+                    help="1 = int8 tcgen05 kernels (default), 0 = CUDA-core validation kernels")
+    ap.add_argument("--cpu_snps", type=int, default=200, help="SNPs per block of the CPU sample")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--ring_blocks", type=int, default=4, help="distinct host blocks served cyclically in the e2e leg")
+    ap.add_argument("--no_other_configs", action="store_true")
+    ap.add_argument("--no_api_e2e", action="store_true")
+    ap.add_argument("--api_workload", default="config2", choices=list(WORKLOADS))
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pyrhe_b200 import _lib
+    from pyrhe_b200.assemble import PathPlan, normal_equations_batch, loo_grams
+    from pyrhe_b200.engine import RheEngine
+    from pyrhe_b200.hostmath import host_terms
+    from pyrhe_b200 import synth
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    N, M, J, K, Cc, B = wl["N"], wl["M"], wl["J"], wl["K"], wl["C"], wl["B"]
+    pb = build_problem(wl, args, rank, world, dev)
+    eng, plan, ht, Z, W, Y_res, env, store = (pb[k] for k in ("eng", "plan", "ht", "Z", "W", "Y_res", "env", "store"))
+    ingest_count_ms = pb["ingest_count_ms"]
+    stream = torch.cuda.current_stream(dev)
 
     def tail(pieces):
         tail.buf = loo_grams(pieces["G_blk"], getattr(tail, "buf", None))
         T, q = normal_equations_batch(plan, ht, pieces["XX"], tail.buf, pieces["M"])
-        try:
-            return np.linalg.solve(T, q[..., None])[..., 0]
-        except np.linalg.LinAlgError:        # only with the kernel debug switches (PYRHE_TC_DEBUG_*) that skip work
-            return np.full(q.shape, np.nan)
+        return np.linalg.solve(T, q[..., None])[..., 0]
 
     def step_resident():
         return tail(eng.run())
@@ -223,7 +347,8 @@ def main():
     # clocks are sampled (200 ms period) from the first warm-up step to the end of the timed region: at 8 GPUs the
     # timed steps alone are shorter than one sampling period
     with ClockSampler(local) as clk:
-        for _ in range(args.warmup):
+        first_pass_ms, sigma = timed(step_resident, 1)         # cold: the first pass of this context over every block
+        for _ in range(max(args.warmup - 1, 0)):
             sigma = step_resident()
         launches0 = eng.launches
         ms_total, sigma = timed(step_resident, args.steps)
@@ -231,6 +356,11 @@ def main():
     ms_step = ms_total / args.steps
     total_bytes = float((N + 3) // 4) * M
     value = total_bytes / (ms_step * 1e-3) / 1e9
+    # the round-1 structure for comparison: allele counts re-taken inside every block call (three reads per block)
+    eng.use_resident_counts = False
+    step_resident()
+    ms_recount, _ = timed(step_resident, 1)
+    eng.use_resident_counts = True
 
     # ---- roofline of the dominant kernel: per-phase CUDA-event timing over one more step
     _lib.check(lib.rhe_timing_enable(eng._ctx, 1))
@@ -239,7 +369,7 @@ def main():
     ncalls = C.c_int32()
     _lib.check(lib.rhe_timing_collect(eng._ctx, phases, C.byref(ncalls)))
     _lib.check(lib.rhe_timing_enable(eng._ctx, 0))
-    names = ["stats_impute", "pass_a", "standardize_gram", "pass_b"]
+    names = ["params", "pass_a", "standardize_gram", "pass_b"]
     ph = {n: phases[i] / max(ncalls.value, 1) for i, n in enumerate(names)}
     dom = max(("pass_a", "pass_b"), key=lambda n: ph[n])
     m_avg = sum(eng.ranges[j][1] - eng.ranges[j][0] for j in eng.own) / max(len(eng.own), 1)
@@ -250,42 +380,75 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"{dom}:{args.kernel_path}:{args.workload}")
+    block_ms = sum(ph.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ph[dom], "phases_ms_per_block": ph,
-                "fused_block_frac": alg_bytes / (sum(ph.values()) * 1e-3) / 1e9 / peak if sum(ph.values()) > 0 else 0.0}
+                "ingest_count_ms_per_block": ingest_count_ms,
+                "fused_block_frac": alg_bytes / (block_ms * 1e-3) / 1e9 / peak if block_ms > 0 else 0.0,
+                "fused_block_frac_with_ingest_count": alg_bytes / ((block_ms + ingest_count_ms) * 1e-3) / 1e9 / peak
+                if block_ms > 0 else 0.0}
 
-    # ---- end to end: every block's rows cross PCIe from pinned host memory inside the step
+    # ---- end to end through the engine's ingest API: every block's rows go host memory -> staging threads -> pinned
+    # ring -> PCIe -> device slot (+ allele counts on arrival) inside the step.  The host source holds `ring_blocks`
+    # distinct blocks that are served cyclically (125 GB of host RAM per rank is not assumed); every byte of the job
+    # still crosses the host staging copy and the link each step.
     e2e = None
+    h2d_ceiling = None
     if not args.no_e2e:
         R = max(1, min(args.ring_blocks, len(eng.own)))
-        ring = torch.empty((R, eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
+        host = np.empty((R * eng.max_m, eng.row_bytes), dtype=np.uint8)
         for r in range(R):
             rows, m = eng.block_view(eng.own[r])
-            ring[r, :m].copy_(rows[:, : eng.row_bytes])
-        copy_stream = torch.cuda.Stream(dev)
+            host[r * eng.max_m: r * eng.max_m + m] = rows[:, : eng.row_bytes].cpu().numpy()
+
+        class CyclicRows:
+            """rows [a, b) of the rank's share -> the matching rows of the R-block host sample"""
+            shape = (M, eng.row_bytes)
+
+            def __getitem__(self, sl):
+                a, b = sl.start, sl.stop
+                j = min(a // (M // J), J - 1)
+                base = ((j - eng.own[0]) % R) * eng.max_m + (a - eng.ranges[j][0])
+                return host[base: base + (b - a)]
+
         h2d_total = M * eng.row_bytes + world * eng.R.numel() * 4      # all ranks: every .bed row once + the RHS per rank
         d2h_holder = {}
+        streamer = eng.stream_genotypes(CyclicRows(), ring_blocks=eng.ring_blocks)
 
         def step_e2e():
             eng.set_rhs(Z, W, Y_res, env)
-            events = {}
-            for idx, j in enumerate(eng.own):
-                eng.upload_block(j, ring[idx % R], stream=copy_stream)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                events[j] = ev
-            pieces = eng.run(upload_events=events)
+            pieces = eng.run(upload=streamer)
             d2h_holder["n"] = pieces["XX"].nbytes + pieces["G_blk"].nbytes
             return tail(pieces)
 
         step_e2e()
-        ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 2)))
-        ms_e2e /= max(1, min(args.steps, 2))
+        n_e2e = max(1, min(args.steps, 2))
+        ms_e2e, _ = timed(step_e2e, n_e2e)
+        ms_e2e /= n_e2e
         e2e = {"value": total_bytes / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_holder["n"]),
-               "host_ring_blocks": R}
-        del ring
+               "host_sample_blocks": R, "staging_threads": streamer.n_workers,
+               "path": "RheEngine.stream_genotypes (host rows -> staging threads -> pinned ring -> H2D -> counts) + run"}
+        streamer.close()
+        # the node's pinned-H2D ceiling with all ranks copying at once (no staging, no kernels): what the link gives
+        pin = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        dst.copy_(pin, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(8):
+            dst.copy_(pin, non_blocking=True)
+        c1.record(stream)
+        barrier()
+        t = torch.tensor([8 * (1 << 30) / (c0.elapsed_time(c1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_ceiling = {"aggregate_gbs": float(t.item()), "n_gpus": world,
+                       "how": "8 x 1 GiB pinned->device copies per rank, all ranks concurrently, summed"}
+        e2e["frac_of_h2d_ceiling"] = e2e["value"] / h2d_ceiling["aggregate_gbs"]
+        del pin, dst, host
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -296,6 +459,39 @@ def main():
         cb.close()
         cpu = {"value": geno / 4 / secs / 1e9, "unit": UNIT, "cores": cb.cores, "kind": "port",
                "sample": cb.describe(), "sample_seconds": secs}
+
+    eng.close()
+    del eng, pb
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json's other GPU configurations at the current GPU count (resident step, 3 timed steps each)
+    others = {}
+    if args.workload == "config5" and not args.no_other_configs:
+        for name in ("config2", "config3", "config4"):
+            owl = dict(WORKLOADS[name])
+            opb = build_problem(owl, args, rank, world, dev)
+            oeng, oplan, oht = opb["eng"], opb["plan"], opb["ht"]
+
+            def ostep():
+                pieces = oeng.run()
+                Tq = normal_equations_batch(oplan, oht, pieces["XX"], loo_grams(pieces["G_blk"]), pieces["M"])
+                return np.linalg.solve(Tq[0], Tq[1][..., None])[..., 0]
+
+            ostep()
+            oms, osig = timed(ostep, 3)
+            oms /= 3
+            ob = float((owl["N"] + 3) // 4) * owl["M"]
+            others[name] = {"model": owl["model"], "N": owl["N"], "M": owl["M"], "ms_per_step": oms,
+                            "value": ob / (oms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+                            "kernel_path": "tcgen05" if oeng.kernel_path == 1 else "simt",
+                            "sigma_e": float(osig[-1][-1])}
+            oeng.close()
+            del oeng, opb
+            torch.cuda.empty_cache()
+
+    api = None
+    if world == 1 and not args.no_e2e and not args.no_api_e2e:
+        api = model_api_e2e(args, dev)
 
     if rank == 0:
         line = {
@@ -308,9 +504,10 @@ def main():
                        "l2": "inputs larger than L2 (packed genotypes per rank >> 126 MB)", "impute": "binary"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "sigma_check": [float(v) for v in sigma[-1]],
+            "first_pass_ms": first_pass_ms, "step_recount_ms": ms_recount, "h2d_ceiling": h2d_ceiling,
+            "e2e_model_api": api, "other_configs": others,
         }
         _emit(line)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

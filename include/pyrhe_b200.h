@@ -18,8 +18,10 @@
  * (thread local).  All device pointers are caller owned (the Python host passes
  * torch tensors' data_ptr()); the context owns only its workspaces.  One context per GPU /
  * rank; calls on one context are serialised by the caller; work is ordered on the
- * `stream` argument (a cudaStream_t passed as void*); no function synchronises the host
- * except rhe_ctx_create / rhe_ctx_destroy.
+ * `stream` argument (a cudaStream_t passed as void*).  Only the set-up and tear-down calls may allocate or
+ * synchronise the host: rhe_ctx_create / rhe_ctx_destroy, rhe_block_plan_create / rhe_block_plan_destroy and
+ * rhe_timing_collect.  The per-block calls (rhe_upload_rows, rhe_block_stats, rhe_block_accumulate, rhe_loo_gram*)
+ * only enqueue work, so the host runs ahead of the GPU and the first pass over a block costs the same as any later one.
  *
  * Data layout:
  *   packed genotypes  uint8 [n_snps][pitch_bytes]   PLINK-1 SNP-major rows, 4 genotypes/byte,
@@ -42,7 +44,7 @@
 extern "C" {
 #endif
 
-#define RHE_ABI_VERSION 1
+#define RHE_ABI_VERSION 2
 
 #define RHE_OK 0
 #define RHE_ERR_INVALID (-1)   /* bad argument */
@@ -54,6 +56,7 @@ extern "C" {
 #define RHE_PATH_TCGEN05 1     /* int8 tcgen05 tensor-core kernels with TMEM accumulators   */
 
 typedef struct rhe_ctx rhe_ctx;
+typedef struct rhe_block_plan rhe_block_plan;   /* annotation metadata of one jackknife block */
 
 typedef struct rhe_config {
   int32_t device;          /* CUDA device ordinal */
@@ -77,6 +80,10 @@ const char* rhe_last_error(void);
 int rhe_ctx_create(rhe_ctx** out, const rhe_config* cfg);
 int rhe_ctx_destroy(rhe_ctx* ctx);
 
+/* 1 when the shapes of `cfg` fit the tcgen05 kernels (TMEM columns, shared memory), else 0 with the reason in
+ * rhe_last_error(); such a configuration needs kernel_path = RHE_PATH_SIMT.  No device is touched. */
+int rhe_tc_supported(const rhe_config* cfg);
+
 /* base.py:176-178,396-401 (Z, covariates, regressed phenotype as right-hand sides). */
 int rhe_set_rhs(rhe_ctx* ctx, const float* rhs_dev, const float* rowscale_dev,
                 const uint32_t* keep2_dev, void* stream);
@@ -90,7 +97,9 @@ int rhe_upload_rows(const void* host_src, int64_t row_bytes, int64_t n_rows,
                     void* dev_dst, int64_t pitch_bytes, void* stream);
 
 /* base.py:277-289 statistics: per SNP {n0, n1, n2, n_missing} over kept individuals.
- * counts_dev int32 [n_snps][4]. */
+ * counts_dev int32 [n_snps][4].  The counts depend only on the genotypes and the keep mask, so the ingest path runs
+ * this once when a block becomes resident and hands the result to every later rhe_block_accumulate (any trait, any
+ * set of random vectors); the imputation fill itself (which needs the per-run uniforms) is re-derived per call. */
 int rhe_block_stats(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
                     int32_t* counts_dev, void* stream);
 
@@ -100,16 +109,26 @@ int rhe_block_stats(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
 int rhe_decode_block(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
                      int32_t apply_impute, int8_t* out_dev, void* stream);
 
+/* base.py:315-336 (`partition_bins`): the bin row lists of ONE jackknife block, prepared once.
+ *   bin_rows_dev     int32 [bin_offsets[K]]  block-local SNP rows of every bin, concatenated (caller owned, must
+ *                                            outlive the plan); a SNP may sit in several bins
+ *   bin_offsets_host int32 [K + 1]           (host memory, copied)
+ * May allocate device memory and synchronise; the plan is then immutable and reusable for any number of calls. */
+int rhe_block_plan_create(rhe_ctx* ctx, int32_t n_snps, const int32_t* bin_rows_dev,
+                          const int32_t* bin_offsets_host, void* stream, rhe_block_plan** out);
+int rhe_block_plan_destroy(rhe_ctx* ctx, rhe_block_plan* plan);
+
 /* rhe.py:13-22 / rhe_dom.py:43-68 / genie.py:46-82 for ONE jackknife block:
- *   bin_rows_dev     int32 [bin_offsets[K]]  block-local SNP rows of every bin, concatenated
- *   bin_offsets_host int32 [K + 1]           (host memory)
+ *   plan             from rhe_block_plan_create (its n_snps rows start at bed_dev)
+ *   counts_dev       int32 [n_snps][4] from rhe_block_stats on the same rows, or NULL (counted here: one more
+ *                    read of the block)
  *   P_out_dev        float [E_reg][B][Np] or NULL   this block's X (X^T Z)
  *   S_accum_dev      float [E_reg][B][Np] or NULL   running totals (+=)
- *   gram_out_dev     double [E_reg][Rs][Rs]         overwritten */
-int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, int32_t n_snps,
-                         const int32_t* bin_rows_dev, const int32_t* bin_offsets_host,
-                         float* P_out_dev, float* S_accum_dev, double* gram_out_dev,
-                         void* stream);
+ *   gram_out_dev     double [E_reg][Rs][Rs]         overwritten
+ * Enqueues kernels on `stream` only: no allocation, no host synchronisation. */
+int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, const rhe_block_plan* plan,
+                         const int32_t* counts_dev, float* P_out_dev, float* S_accum_dev,
+                         double* gram_out_dev, void* stream);
 
 /* base.py:578-581 after aggregate (base.py:483-486): out[a][c] = sum (S_a - P_a)(S_c - P_c)
  * over `len` floats per estimate; P_dev may be NULL (totals).  out_dev double [n_est][n_est]. */

@@ -37,8 +37,12 @@ SIGNATURES = {
     "rhe_upload_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "rhe_block_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "rhe_decode_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
-    "rhe_block_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rhe_tc_supported": (C.c_int, [C.POINTER(RheConfig)]),
+    "rhe_block_plan_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p,
+                                        C.POINTER(C.c_void_p)]),
+    "rhe_block_plan_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rhe_block_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "rhe_loo_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "rhe_loo_gram_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_void_p, C.c_int64, C.c_void_p]),
@@ -83,15 +87,22 @@ def ptr(t):
     return C.c_void_p(t.ctypes.data)
 
 
-def tcgen05_supported(plan, limbs: int = None) -> bool:
-    """Mirror of the limits rhe_tc_create enforces (TMEM columns per CTA, staged metadata sizes)."""
-    L = int(os.environ.get("PYRHE_B200_LIMBS", "3")) if limbs is None else limbs
-    r1p = -(-(plan.n_sets * plan.Rs) // 4) * 4
-    nba = -(-(L * r1p) // 16) * 16
-    bp = -(-plan.B // 2) * 2
-    ncb = -(-(plan.n_groups * L * bp) // 16) * 16
-    if plan.K * ncb <= 512:
-        kg = plan.K                                   # all bins in one pass-B launch
-    else:
-        kg = 512 // (2 * ncb) if 2 * ncb <= 512 else (512 // ncb if ncb <= 512 else 0)   # bin groups
-    return (nba <= 256 and 1 <= kg <= 255 and plan.n_groups * kg * plan.B <= 512 and plan.n_groups * plan.B <= 64)
+def plan_config(plan, **fields) -> RheConfig:
+    """rhe_config of a PathPlan (assemble.py); `fields` fill in the sizes the plan does not know."""
+    base = dict(device=0, n_indv=4, n_kept=4, pitch_bytes=128, n_cols_set=plan.Rs, n_sets=plan.n_sets, n_ops=plan.n_ops,
+                n_vec=plan.B, n_bins=plan.K, max_block_snps=1, impute_binary=1, kernel_path=PATH_TCGEN05)
+    base.update(fields)
+    return RheConfig(**base)
+
+
+def tcgen05_supported(plan) -> bool:
+    """Whether the layout of `plan` fits the tcgen05 kernels: asked of the library itself (rhe_tc_supported), which
+    applies exactly the checks rhe_ctx_create enforces (TMEM columns, shared-memory budget, M-tile selection)."""
+    cfg = plan_config(plan)
+    return bool(load().rhe_tc_supported(C.byref(cfg)))
+
+
+def tcgen05_unsupported_reason(plan) -> str:
+    cfg = plan_config(plan)
+    lib = load()
+    return "" if lib.rhe_tc_supported(C.byref(cfg)) else lib.rhe_last_error().decode()

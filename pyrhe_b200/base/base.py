@@ -29,12 +29,13 @@ from ..hostmath import block_ranges, host_terms
 from ..util.file_processing import (generate_annot, read_annot, read_bim, read_cov, read_fam, read_pheno)
 from ..util.logger import Logger
 from ..util.types import CovImputeMethod, GenoImputeMethod  # noqa: F401
+from .block_hooks import BlockHookDriver, overrides
 from .legacy_ops import LegacyBlockOps
 
 _BED_MAGIC = bytes([0x6C, 0x1B, 0x01])
 
 
-class Base(LegacyBlockOps, ABC):
+class Base(BlockHookDriver, LegacyBlockOps, ABC):
     #: False -> keep every block's XXz partial in HBM (one pass over the genotypes);
     #: True  -> the reference's two-pass "streaming" memory policy (recompute each block).
     _recompute_blocks = False
@@ -56,12 +57,13 @@ class Base(LegacyBlockOps, ABC):
         self.multiprocessing = multiprocessing
         self.kernel_path = kernel_path
 
-        # base.py:72-73 -- `seed=None` keeps the reference rule; str seeds from the CLI are coerced (Q6)
-        self.seed = int(time.process_time()) if seed is None else int(seed)
-        np.random.seed(self.seed)
-
         self.device_name, self.cuda_num = device, cuda_num
         self._init_device(device, cuda_num)
+
+        # base.py:72-73 -- `seed=None` keeps the reference rule; str seeds from the CLI are coerced (Q6).  One process
+        # per GPU: every rank must draw the same Z / annotation / imputation uniforms, so rank 0's seed wins.
+        self.seed = self._agree_on_seed(int(time.process_time()) if seed is None else int(seed))
+        np.random.seed(self.seed)
         self._check_workers(num_workers)
 
         self.geno_file = geno_file
@@ -73,7 +75,9 @@ class Base(LegacyBlockOps, ABC):
             if self.num_bin is None:
                 raise ValueError("Must specify number of bins if annot file is not provided")
             annot_file = "generated_annot"
-            generate_annot(annot_file, self.num_snp, self.num_bin)          # consumes the global RNG before Z
+            # consumes the global RNG before Z on every rank (same draws everywhere); only rank 0 writes the file
+            generate_annot(annot_file if self._rank == 0 else os.devnull, self.num_snp, self.num_bin)
+            self._barrier()
         self.num_bin, self.annot_matrix, self.len_bin = read_annot(annot_file, self.num_jack)
 
         self.pheno_file = pheno_file
@@ -121,8 +125,34 @@ class Base(LegacyBlockOps, ABC):
         self.env = None
         self._pieces = None
         self._engine = None
+        self._state = None
+        self._hook_mode = False
 
     # ------------------------------------------------------------------ construction helpers
+    def _process_group_ready(self):
+        if self._world <= 1:
+            return False
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.device)
+        return True
+
+    def _agree_on_seed(self, seed: int) -> int:
+        """Multi-GPU runs are one process per rank: broadcast rank 0's seed so that every rank generates the same
+        random vectors (an all-reduce over statistics of different Z would be silently wrong)."""
+        if not self._process_group_ready():
+            return seed
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([seed], dtype=torch.int64, device=self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        return int(t.item())
+
+    def _barrier(self):
+        if self._process_group_ready():
+            import torch.distributed as dist
+            dist.barrier()
+
     def _init_device(self, device, cuda_num):
         """base.py:195-206.  The device string is accepted for compatibility; the block kernels
         always run on CUDA (`cuda_num` or, under torchrun, LOCAL_RANK) and fail loudly otherwise."""
@@ -172,10 +202,12 @@ class Base(LegacyBlockOps, ABC):
     def run(self, method):
         ...
 
-    def pre_compute_jackknife_bin(self, j, all_gen):
-        """Reference hook (rhe.py:13-22).  The built-in models fuse this whole triple loop into
-        `rhe_block_accumulate`; it is kept so subclasses can still be introspected."""
-        raise NotImplementedError("built-in models run the fused block path (pyrhe_b200.engine)")
+    def pre_compute_jackknife_bin(self, j, all_gen, worker_num=None):
+        """The model's per-block hook (base.py:453-455; rhe.py:13-22).  The built-in models never get here: their
+        whole triple loop is fused into `rhe_block_accumulate`.  A subclass that overrides it is driven by
+        `pre_compute` exactly as the reference drives it (`base/block_hooks.py`)."""
+        raise NotImplementedError("built-in models run the fused block path (pyrhe_b200.engine); override this hook "
+                                  "in a subclass to run your own per-block statistics")
 
     def _plan(self) -> PathPlan:
         """Column / estimate layout of this model for the CUDA library."""
@@ -192,6 +224,15 @@ class Base(LegacyBlockOps, ABC):
         per = int(np.ceil(num_jobs / num_workers))
         return [(i * per, min((i + 1) * per, num_jobs)) for i in range(num_workers)]
 
+    def shared_memory(self):
+        """Names, shapes and dtypes of the state arrays (base.py:419-429)."""
+        E, J, B, N = self.get_num_estimates(), self.num_jack, self.num_random_vec, self.num_indv
+        arrays = {"XXz": ((E, J + 1, B, N), "float64"), "yXXy": ((E, J + 1), "float64"), "M": ((J + 1, E), "int64")}
+        if self.use_cov:
+            arrays.update({"UXXz": ((E, J + 1, B, N), "float64"), "XXUz": ((E, J + 1, B, N), "float64")})
+        self.shared_memory_arrays = arrays
+        return arrays
+
     def _setup_shared_memory(self):
         """base.py:439-450 (name kept): only the small M table lives on the host now."""
         self.num_estimates = self.get_num_estimates()
@@ -204,10 +245,22 @@ class Base(LegacyBlockOps, ABC):
         The Z-dependent statistics do not depend on the trait, so all phenotype columns ride
         through the same pass and later traits reuse the pieces."""
         self._setup_shared_memory()
+        self._state = None
+        self._hook_mode = self._uses_block_hooks()
+        if self._hook_mode:                       # an extender's own block hook: the reference's loop around it
+            if self._world > 1:
+                raise NotImplementedError("custom block hooks run in single-process mode (the built-in models shard "
+                                          "their fused path over GPUs)")
+            t0 = time.time()
+            if self._recompute_blocks:
+                self._hook_pre_compute_streaming()
+            else:
+                self._hook_pre_compute()
+            self.log._debug(f"Precompute total time: {time.time() - t0}")
+            return
         if self._pieces is not None:
             self.M = self._pieces["M"].copy()
             return
-        from .. import _lib
         from ..engine import RheEngine
         t0 = time.time()
         plan = self._plan()
@@ -216,21 +269,28 @@ class Base(LegacyBlockOps, ABC):
         self._host_terms, Y_res = host_terms(plan, self.all_zb, self.cov_matrix, self.pheno_cp, self._env_vector())
         self._Y_res = Y_res
         pg = None
-        if self._world > 1:
-            import torch.distributed as dist
-            if not dist.is_initialized():
-                dist.init_process_group("nccl", device_id=self.device)
-        # int8 tcgen05 kernels (RHE, RHE-DOM with its [g == 2] operand, GENIE with the env-scaled GxE set) whenever
-        # the accumulators of all bins fit one TMEM allocation; otherwise the CUDA-core kernels of the same library
-        default_path = _lib.PATH_TCGEN05 if _lib.tcgen05_supported(plan) else _lib.PATH_SIMT
-        path = self.kernel_path if self.kernel_path is not None else int(os.environ.get("PYRHE_B200_PATH", default_path))
+        self._process_group_ready()
+        # int8 tcgen05 kernels (RHE, RHE-DOM with its [g == 2] operand, GENIE with the env-scaled GxE set) whenever the
+        # layout fits them; otherwise the engine falls back to the CUDA-core kernels of the same library with a warning
+        path = self.kernel_path
+        if path is None and "PYRHE_B200_PATH" in os.environ:
+            path = int(os.environ["PYRHE_B200_PATH"])
         eng = RheEngine(plan, n_indv=self.num_indv_original, keep=keep, annot=self.annot_matrix,
                         num_jack=self.num_jack, impute=self.geno_impute_methods, seed=self.seed, device=self.device,
                         kernel_path=path, rank=self._rank, world=self._world,
                         store_partials=not self._recompute_blocks, process_group=pg)
         eng.set_rhs(self.all_zb, self.cov_matrix, Y_res, self._env_vector())
-        # ingest overlapped with compute: block j+1 is staged and copied while block j runs
-        self._pieces = eng.run(upload=eng.load_genotypes_async(self.geno_bed))
+        # bounded-memory ingest overlapped with compute: block j+1 is staged and copied while
+        # block j runs; the rank's `.bed` share stays resident only when it fits the HBM, otherwise it streams
+        # through a ring of block slots (and, for the streaming policy, streams a second time)
+        ring = os.environ.get("PYRHE_B200_RING_BLOCKS")       # force the bounded ring (default: only when it must)
+        streamer = eng.stream_genotypes(self.geno_bed, ring_blocks=int(ring) if ring else "auto")
+        try:
+            self._pieces = eng.run(upload=streamer)
+        finally:
+            streamer.close()
+        self.ingest_report = dict(ring_blocks=eng.ring_blocks, genotype_bytes=eng.genotype_bytes(),
+                                  staged_bytes=streamer.bytes_staged, passes=streamer.passes)
         self._engine = eng
         self._plan_cached = plan
         self._G_tot = self._pieces["G_blk"].sum(axis=0)
@@ -249,8 +309,22 @@ class Base(LegacyBlockOps, ABC):
     def _trait_index(self) -> int:
         return getattr(self, "_trait", 0)
 
+    def _uses_block_hooks(self) -> bool:
+        """Has a subclass supplied its own per-block hook(s) (base.py:453-455, base_streaming.py:106-108)?"""
+        from .base_streaming import StreamingBase
+        own1 = overrides(self, "pre_compute_jackknife_bin", Base, StreamingBase)
+        if not self._recompute_blocks:
+            return own1
+        own2 = overrides(self, "pre_compute_jackknife_bin_pass_2", Base, StreamingBase)
+        if own1 != own2:
+            raise TypeError("a streaming model must override both pre_compute_jackknife_bin(j, all_gen, worker_num) "
+                            "and pre_compute_jackknife_bin_pass_2(j, all_gen) (base_streaming.py:85-144)")
+        return own1
+
     def setup_lhs_rhs_jackknife(self, j, trace_sums, is_streaming=False):
         """(T, q) of jackknife sample j (j == num_jack: all SNPs) -- base.py:568-628."""
+        if self._hook_mode:
+            return self._hook_lhs_rhs(j, trace_sums, is_streaming)
         plan, pc = self._plan_cached, self._pieces
         G_loo = self._G_tot - pc["G_blk"][j] if j < self.num_jack else self._G_tot
         T, q = normal_equations(plan, self._host_terms, pc["XX"][j], G_loo, self.M[j], trait=self._trait_index())
@@ -269,7 +343,7 @@ class Base(LegacyBlockOps, ABC):
         trace_sums = (np.zeros((self.num_jack + 1, self.num_estimates, self.num_estimates))
                       if self.get_trace else None)
         sigmas, trace_cols = [], []
-        batched = type(self).setup_lhs_rhs_jackknife is Base.setup_lhs_rhs_jackknife
+        batched = type(self).setup_lhs_rhs_jackknife is Base.setup_lhs_rhs_jackknife and not self._hook_mode
         if batched:       # all J + 1 systems assembled in one vectorised pass (an extender's override is honoured below)
             pc = self._pieces
             T_all, q_all = normal_equations_batch(self._plan_cached, self._host_terms, pc["XX"], loo_grams(pc["G_blk"]),
@@ -289,6 +363,8 @@ class Base(LegacyBlockOps, ABC):
         return np.array(sigmas), np.array(trace_cols)
 
     def estimate(self, method: str = "lstsq") -> Tuple[List[List], List]:
+        if self._hook_mode and self._recompute_blocks:
+            return self._hook_estimate_streaming(method)
         sigma, _ = self._solve_all(method)
         return sigma[:-1, :], sigma[-1, :]
 

@@ -200,6 +200,40 @@ k_stats_params(const uint8_t* __restrict__ bed, int pitch, int m, const uint32_t
   }
 }
 
+// Front end of rhe_block_accumulate when the block's allele counts are already resident (rhe_block_stats at ingest):
+// imputation fill + moments from the counts (same float32 replay as k_snp_params) and the zeroing of everything the
+// block accumulates into.  No genotype byte is read.
+__global__ void __launch_bounds__(256)
+k_params_from_counts(const int32_t* __restrict__ counts, int m, int n_kept, int binary, const double* __restrict__ uniforms,
+                     uint8_t* __restrict__ fill, double* __restrict__ mu, double* __restrict__ f2,
+                     double* __restrict__ t_raw, int n_traw, double* __restrict__ cs, int n_cs,
+                     double* __restrict__ gram, int n_gram, unsigned int* __restrict__ wmax, int n_wmax) {
+  const int tid = blockIdx.x * 256 + threadIdx.x, nth = gridDim.x * 256;
+  for (int i = tid; i < n_traw; i += nth) t_raw[i] = 0.0;
+  for (int i = tid; i < n_gram; i += nth) gram[i] = 0.0;
+  for (int i = tid; i < n_cs; i += nth) cs[i] = 0.0;
+  for (int i = tid; i < n_wmax; i += nth) wmax[i] = 0u;
+  for (int s = tid; s < m; s += nth) {
+    const int4 c = reinterpret_cast<const int4*>(counts)[s];
+    int n1 = c.y, n2 = c.z, f = 0;
+    const int nm = c.w;
+    if (binary) {
+      float mean32 = (float)((double)(n1 + 2 * n2) / (double)(n_kept - nm));
+      float p = __fmul_rn(mean32, 0.5f);
+      float om = __fsub_rn(1.0f, p);
+      float d0 = __fmul_rn(om, om);
+      float d1 = __fmul_rn(__fmul_rn(2.0f, p), om);
+      float u = (float)uniforms[s];
+      f = (u < d0) ? 0 : ((u < __fadd_rn(d0, d1)) ? 1 : 2);
+    }
+    if (f == 1) n1 += nm;
+    if (f == 2) n2 += nm;
+    fill[s] = (uint8_t)f;
+    mu[s] = (double)(n1 + 2 * n2) / (double)n_kept;
+    f2[s] = (double)n2 / (double)n_kept;
+  }
+}
+
 // Test hook: decoded (optionally imputed) A2 counts, one byte per genotype.
 __global__ void k_decode(const uint8_t* __restrict__ bed, int pitch, int m,
                          const uint8_t* __restrict__ fill, int apply_impute, int8_t* __restrict__ out) {
@@ -756,7 +790,6 @@ extern "C" int rhe_ctx_destroy(rhe_ctx* c) {
   cudaDeviceSynchronize();
   if (c->tc) rhe_tc_destroy(c);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
-  for (auto& e : c->off_cache) cudaFree(e.dev);
   void* ptrs[] = {c->colsum, c->counts, c->fill, c->mu, c->f2, c->t_raw, c->t_std, c->w1, c->w2, c->shiftv, c->cs, c->bin_off};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete c;
@@ -845,12 +878,65 @@ static void launch_pass_b(rhe_ctx* c, dim3 grid, cudaStream_t st, const uint8_t*
                                      rows, off, c->fill, c->w1, c->w2, c->cs, c->rowscale, P_out, S_accum);
 }
 
-extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, const int32_t* bin_rows,
-                                    const int32_t* bin_off_host, float* P_out, float* S_accum, double* gram_out,
-                                    void* stream) {
+extern "C" int rhe_tc_supported(const rhe_config* cfg) {
+  if (validate(cfg)) return 0;
+  return rhe_tc_check(cfg, 0) == RHE_OK ? 1 : 0;
+}
+
+extern "C" int rhe_block_plan_create(rhe_ctx* c, int32_t m, const int32_t* bin_rows, const int32_t* bin_off_host,
+                                     void* stream, rhe_block_plan** out) {
+  if (!c || !bin_rows || !bin_off_host || !out) { rhe_set_error("rhe_block_plan_create: NULL argument"); return RHE_ERR_INVALID; }
+  *out = nullptr;
+  const int K = c->cfg.n_bins;
+  if (m < 1 || m > c->cfg.max_block_snps) { rhe_set_error("rhe_block_plan_create: n_snps %d outside [1, %d]", m, c->cfg.max_block_snps); return RHE_ERR_INVALID; }
+  if (bin_off_host[0] != 0) { rhe_set_error("rhe_block_plan_create: bin_offsets[0] must be 0"); return RHE_ERR_INVALID; }
+  for (int k = 0; k < K; ++k)
+    if (bin_off_host[k + 1] < bin_off_host[k] || bin_off_host[k + 1] - bin_off_host[k] > m) {
+      rhe_set_error("rhe_block_plan_create: bin %d has a bad row range", k);
+      return RHE_ERR_INVALID;
+    }
+  RHE_CUDA(cudaSetDevice(c->cfg.device));
+  rhe_block_plan* p = new (std::nothrow) rhe_block_plan();
+  if (!p) { rhe_set_error("out of host memory"); return RHE_ERR_INVALID; }
+  p->m = m;
+  p->bin_rows = bin_rows;
+  p->off_host.assign(bin_off_host, bin_off_host + K + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMalloc((void**)&p->off_dev, sizeof(int32_t) * (K + 1));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->off_dev, p->off_host.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    rhe_set_error("rhe_block_plan_create: %s", cudaGetErrorString(e));
+    rhe_block_plan_destroy(c, p);
+    return RHE_ERR_CUDA;
+  }
+  if (c->tc) {
+    int rc = rhe_tc_plan_create(c, p, st);
+    if (rc) { rhe_block_plan_destroy(c, p); return rc; }
+  }
+  e = cudaStreamSynchronize(st);     // the offsets were copied from the plan's own host vector; be done before returning
+  if (e != cudaSuccess) { rhe_set_error("rhe_block_plan_create: %s", cudaGetErrorString(e)); rhe_block_plan_destroy(c, p); return RHE_ERR_CUDA; }
+  *out = p;
+  return RHE_OK;
+}
+
+extern "C" int rhe_block_plan_destroy(rhe_ctx* c, rhe_block_plan* p) {
+  if (!p) return RHE_OK;
+  if (c) cudaSetDevice(c->cfg.device);
+  if (p->tc) rhe_tc_plan_destroy(p);
+  if (p->off_dev) cudaFree(p->off_dev);
+  delete p;
+  return RHE_OK;
+}
+
+extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, const rhe_block_plan* plan, const int32_t* counts_in,
+                                    float* P_out, float* S_accum, double* gram_out, void* stream) {
+  if (!plan) { rhe_set_error("rhe_block_accumulate: plan is NULL"); return RHE_ERR_INVALID; }
+  const int m = plan->m;
   int rc = check_block(c, bed, m, "rhe_block_accumulate");
   if (rc) return rc;
-  if (!bin_rows || !bin_off_host || !gram_out) { rhe_set_error("rhe_block_accumulate: NULL argument"); return RHE_ERR_INVALID; }
+  if (!gram_out) { rhe_set_error("rhe_block_accumulate: NULL argument"); return RHE_ERR_INVALID; }
+  const int32_t* bin_rows = plan->bin_rows;
+  const int32_t* s_off_dev = plan->off_dev;
   cudaStream_t st = (cudaStream_t)stream;
   const rhe_config& g = c->cfg;
   const int K = g.n_bins, Rs = g.n_cols_set, B = g.n_vec;
@@ -863,23 +949,16 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
     rhe_set_error("binary imputation needs rhe_set_uniforms with >= %d values", m);
     return RHE_ERR_STATE;
   }
-  // bin offsets on the device: annotation metadata, copied the first time this block is seen
-  int32_t* s_off_dev = nullptr;
-  for (auto& e : c->off_cache)
-    if (e.key == bin_rows && (int)e.host.size() == K + 1 && memcmp(e.host.data(), bin_off_host, sizeof(int32_t) * (K + 1)) == 0) s_off_dev = e.dev;
-  if (!s_off_dev) {
-    rhe_ctx::OffEntry e;
-    e.key = bin_rows;
-    e.host.assign(bin_off_host, bin_off_host + K + 1);
-    RHE_CUDA(cudaMalloc((void**)&e.dev, sizeof(int32_t) * (K + 1)));
-    RHE_CUDA(cudaMemcpy(e.dev, bin_off_host, sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice));
-    c->off_cache.push_back(e);
-    s_off_dev = e.dev;
-  }
   unsigned int* wmax = g.kernel_path == RHE_PATH_TCGEN05 ? rhe_tc_wmax(c) : nullptr;
-  k_stats_params<<<rhe_div_up(m, ST_ROWS), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
-                                                   c->counts, c->fill, c->mu, c->f2, c->t_raw, c->R1, g.n_ops, c->cs,
-                                                   c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? c->n_groups * B : 0);
+  if (counts_in) {     // allele counts resident since ingest: the block is not read here
+    k_params_from_counts<<<rhe_div_up(m, 256) < 64 ? 64 : rhe_div_up(m, 256), 256, 0, st>>>(
+        counts_in, m, g.n_kept, g.impute_binary, c->uniforms, c->fill, c->mu, c->f2, c->t_raw, g.n_ops * m * c->R1, c->cs,
+        c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? c->n_groups * B : 0);
+  } else {
+    k_stats_params<<<rhe_div_up(m, ST_ROWS), 256, 0, st>>>(bed, g.pitch_bytes, m, c->keep2, g.n_kept, g.impute_binary, c->uniforms,
+                                                     c->counts, c->fill, c->mu, c->f2, c->t_raw, c->R1, g.n_ops, c->cs,
+                                                     c->E_reg * B, gram_out, c->E_reg * Rs * Rs, wmax, wmax ? c->n_groups * B : 0);
+  }
   RHE_LAUNCH_CHECK(c);
   if (c->timing) RHE_CUDA(cudaEventRecord(tev[1], st));
 
@@ -914,7 +993,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, int32_t m, c
   // ---- pass B
   if (P_out || S_accum) {
     if (g.kernel_path == RHE_PATH_TCGEN05) {
-      rc = rhe_tc_pass_b(c, bed, m, bin_rows, s_off_dev, bin_off_host, P_out, S_accum, st);
+      rc = rhe_tc_pass_b(c, bed, plan, P_out, S_accum, st);
       if (rc) return rc;
     } else {
       int BG = B <= 4 ? 4 : B <= 8 ? 8 : B <= 12 ? 12 : 16;
@@ -937,7 +1016,7 @@ extern "C" int rhe_loo_gram_multi(rhe_ctx* c, const float* S, const float* P, in
   if (!c || !S || !P || !out) { rhe_set_error("rhe_loo_gram_multi: NULL argument"); return RHE_ERR_INVALID; }
   if (n_blocks < 1 || p_stride < 0 || out_stride < (int64_t)n_est * n_est) { rhe_set_error("rhe_loo_gram_multi: bad block count / strides"); return RHE_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  const bool mma = len % 16 == 0 && n_est >= 1 && n_est <= 16 && p_stride % 4 == 0 && !getenv("PYRHE_B200_LOO_SIMT");
+  const bool mma = len % 16 == 0 && n_est >= 1 && n_est <= 16 && p_stride % 4 == 0 && !RHE_DBG_ENV("PYRHE_B200_LOO_SIMT", 0);
   for (int b0 = 0; b0 < n_blocks;) {
     const int nb = mma ? (n_blocks - b0 < 4 ? n_blocks - b0 : 4) : 1;
     const float* Pb = P + (size_t)b0 * p_stride;
@@ -998,7 +1077,7 @@ extern "C" int rhe_loo_gram(rhe_ctx* c, const float* S, const float* P, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   RHE_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_est * n_est, st));
   // register-resident kernels for up to 8 estimates (8-byte loads: even length, always true for B * Np)
-  if (len % 16 == 0 && n_est <= 24 && !getenv("PYRHE_B200_LOO_SIMT")) {      // FP64 tensor-core Gram
+  if (len % 16 == 0 && n_est <= 24 && !RHE_DBG_ENV("PYRHE_B200_LOO_SIMT", 0)) {      // FP64 tensor-core Gram
     if (n_est <= 8) launch_loo_mma<1>(S, P, 0, 1, n_est, len, out, 0, st);
     else if (n_est <= 16) launch_loo_mma<2>(S, P, 0, 1, n_est, len, out, 0, st);
     else launch_loo_mma<3>(S, P, 0, 1, n_est, len, out, 0, st);

@@ -34,9 +34,16 @@ struct rhe_ctx {
   int64_t launches = 0;
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // 5 events per timed rhe_block_accumulate call
-  // device copies of the per-block bin offsets, keyed by the caller's bin_rows pointer (annotation metadata)
-  struct OffEntry { const int32_t* key; std::vector<int32_t> host; int32_t* dev; };
-  std::vector<OffEntry> off_cache;
+};
+
+// Annotation-derived metadata of one jackknife block (rhe_block_plan_create): everything rhe_block_accumulate needs
+// besides the genotypes is resident before the block is first seen, so the hot call neither allocates nor synchronises.
+struct rhe_block_plan {
+  int m = 0;                          // SNPs in the block
+  const int32_t* bin_rows = nullptr;  // caller-owned device list of block-local SNP rows, bins concatenated
+  std::vector<int32_t> off_host;      // [K + 1]
+  int32_t* off_dev = nullptr;         // [K + 1]
+  void* tc = nullptr;                 // tensor-core path: bin-sorted positions per bin group (rhe_tc.cu)
 };
 
 void rhe_set_error(const char* fmt, ...);
@@ -76,6 +83,18 @@ void rhe_tc_destroy(rhe_ctx* ctx);
 int rhe_tc_set_rhs(rhe_ctx* ctx, cudaStream_t st);
 int rhe_tc_pass_a(rhe_ctx* ctx, const uint8_t* bed, int m, cudaStream_t st);
 unsigned int* rhe_tc_wmax(rhe_ctx* ctx);   // per-column max |pass-B weight| (float bits), or NULL
-int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, int m, const int32_t* bin_rows,
-                  const int32_t* bin_off, const int32_t* bin_off_host, float* P_out, float* S_accum,
+int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, const rhe_block_plan* plan, float* P_out, float* S_accum,
                   cudaStream_t st);
+int rhe_tc_plan_create(rhe_ctx* ctx, rhe_block_plan* plan, cudaStream_t st);   // may allocate and synchronise
+void rhe_tc_plan_destroy(rhe_block_plan* plan);
+int rhe_tc_check(const rhe_config* cfg, int quiet);                            // RHE_OK when the shapes fit the tcgen05 kernels
+
+// Work-skipping ablation switches (PYRHE_TC_DEBUG_*) exist only in the profiling build (-DRHE_TC_DEBUG,
+// libpyrhe_b200_prof.so); in the shipped library the tests compile to constants and the variables are never read.
+#ifdef RHE_TC_DEBUG
+#define RHE_DBG(mask) (dbg & (mask))
+#define RHE_DBG_ENV(name, dflt) (getenv(name) ? atoi(getenv(name)) : (dflt))
+#else
+#define RHE_DBG(mask) 0
+#define RHE_DBG_ENV(name, dflt) (dflt)
+#endif

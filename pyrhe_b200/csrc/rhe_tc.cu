@@ -30,16 +30,18 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// Annotation-derived metadata of one jackknife block (depends only on the bin row lists, so it is built the
-// first time a block is seen and reused by later traits / steps).
+// Annotation-derived metadata of one (jackknife block, bin group): depends only on the bin row lists, so it is built
+// by rhe_block_plan_create and owned by the plan.
 struct TcBlockMeta {
-  const int32_t* key = nullptr;   // the caller's bin_rows pointer identifies the block
-  int m = 0;
   int k0 = 0, kn = 0;             // the bins [k0, k0 + kn) of this bin group
   int n_pos = 0;                  // bin-sorted positions, every bin padded to a multiple of 128 rows
   int32_t* pos_rows = nullptr;    // [n_pos]       block-local SNP row (-1 = padding)
   int32_t* stage_info = nullptr;  // [n_pos / 128] bin | first-stage-of-bin << 8 | K-steps << 16
   int32_t* bin_count = nullptr;   // [kn]          rows per bin of the group
+};
+
+struct TcPlan {
+  std::vector<TcBlockMeta> groups;   // one per bin group of at most KG bins
 };
 
 struct TcState {
@@ -58,7 +60,6 @@ struct TcState {
   int32_t* pos_meta = nullptr;  // [SI][chunks][128][4] per-group decode metadata (SNP row | fill << 24 | mode << 26) of the current block
   unsigned int* wmax = nullptr; // [n_groups][B] max |weight| per weight group and column (float bits)
   int cap_pos = 0;
-  std::vector<TcBlockMeta> blocks;
   CUtensorMap tm_rq, tm_uq;
   PFN_encodeTiled encode = nullptr;
 };
@@ -448,7 +449,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
       tc_fence_after();
       PROF_ADD(1);
       const uint32_t dst = lane_base + col_a + 32u * slot_a;
-      if (dbg & 8) {
+      if (RHE_DBG(8)) {
         __syncwarp();
         if (lane == 0) { mbar_arrive(&sm->empty_g[k % PA_GS]); mbar_arrive(&sm->full_a[slot_a]); }
         return;
@@ -503,7 +504,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
         const uint32_t sl = (uint32_t)k & 1u;
         mbar_wait_s(eb + 8u * sl, (((uint32_t)k >> 1) & 1u) ^ 1u);
         if (elect_one()) {
-          if (dbg & 1) mbar_arrive_s(fb + 8u * sl);
+          if (RHE_DBG(1)) mbar_arrive_s(fb + 8u * sl);
           else {
             const int x = (y + splits * k) * 512;
             mbar_expect_tx_s(fb + 8u * sl, 4u * (uint32_t)tileB_bytes);
@@ -522,7 +523,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
         const uint32_t sg = (uint32_t)(k % PA_GS);
         mbar_wait_s(eg + 8u * sg, ((uint32_t)(k / PA_GS) & 1u) ^ 1u);
         if (elect_one()) {
-          if (dbg & 4) mbar_arrive_s(fg + 8u * sg);
+          if (RHE_DBG(4)) mbar_arrive_s(fg + 8u * sg);
           else {
             mbar_expect_tx_s(fg + 8u * sg, PA_PACKED);
             tma_load_2d_s(packed_s + sg * PA_PACKED, &tm_bed, fg + 8u * sg, (y + splits * k) * 128, snp0);
@@ -555,12 +556,12 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
         const uint64_t bdesc = bdesc0 + (uint64_t)((sl * 4u + (j & 3u)) * (uint32_t)(tileB_bytes >> 4));
         const uint32_t acol = tmem + col_a + 32u * (2u * (uint32_t)g + q);
         if (elect_one()) {
-          if (!(dbg & 2)) {
+          if (!(RHE_DBG(2))) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)   // K = 32 individuals per instruction: 8 TMEM columns / 32 bytes of the Rq row
               umma_i8_ts(tmem, acol + 8u * i, bdesc + (uint64_t)(i * 2), idesc, 1u);
           }
-          if (dbg & 16) { mbar_arrive_s(ea + 8u * q); mbar_arrive_s(eb + 8u * sl); }
+          if (RHE_DBG(16)) { mbar_arrive_s(ea + 8u * q); mbar_arrive_s(eb + 8u * sl); }
           else { umma_commit_s(ea + 8u * q); umma_commit_s(eb + 8u * sl); }
         }
         __syncwarp();
@@ -677,7 +678,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
             int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
             uint32_t tmem_cols, int a_major, int kcap, int bs, int bzsh, int dbg) {
-  if (dbg & 16) n_stage = 0;
+  if (RHE_DBG(16)) n_stage = 0;
   constexpr int PB_DW = 4 * G, PB_THREADS = PB_THREADS_OF(G);
   constexpr int SI = G / MT;                         // stage interleave between groups
   extern __shared__ uint8_t smem_raw[];
@@ -705,12 +706,17 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   }
   for (int i = threadIdx.x; i < K; i += PB_THREADS) sm->cnt[i] = bin_count[i];
   // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
-  for (int i = threadIdx.x; i < WG * B; i += PB_THREADS) sm->dq[i] = ldexp(1.0, (int)((wmax[i] >> 23) & 255u) - 126 - F);
+  // A non-finite weight (a monomorphic SNP: base.py:291-296 divides by sqrt(mu (1 - mu / 2)) = 0) has no fixed-point
+  // image; it poisons its whole column exactly as the NaN does in the reference's products.
+  for (int i = threadIdx.x; i < WG * B; i += PB_THREADS) {
+    const int ex = (int)((wmax[i] >> 23) & 255u);
+    sm->dq[i] = ex == 255 ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex - 126 - F);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
-  if (warp < PB_DW && !(dbg & 32)) {                   // zero the accumulators: quadrant per warp, columns split by group
+  if (warp < PB_DW && !(RHE_DBG(32))) {                   // zero the accumulators: quadrant per warp, columns split by group
     const uint32_t used = (uint32_t)(K * MT * NC);
     for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < used; c += 32 * G)
       tmem_zero32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c);
@@ -747,7 +753,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int mrow = __shfl_sync(0xffffffffu, meta, 16 * h + (lane >> 1));
-        if (mrow >= 0 && !(dbg & 1))
+        if (mrow >= 0 && !(RHE_DBG(1)))
           cp_async16(cp_dst + slot * 1024u + (uint32_t)(h * 512), cp_base + (size_t)(mrow & 0xFFFFFF) * pitch);
       }
       cp_async_commit();
@@ -780,13 +786,13 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
           const uint4 lo = lds128(my_lo + rd_slot * 1024u), hi = lds128(my_hi + rd_slot * 1024u);
           rd_slot = rd_slot + 1 == PB_PKG ? 0u : rd_slot + 1;
           PROF_ADD(0);
-          if (!(dbg & 128)) mbar_wait(empty0 + a, ((u >> 1) & 1) ^ 1);
+          if (!(RHE_DBG(128))) mbar_wait(empty0 + a, ((u >> 1) & 1) ^ 1);
           PROF_ADD(1);
-          if (!(dbg & 2)) tc_store_row(tile0 + a * TC_TILE_A, t, lo, hi, tab);
+          if (!(RHE_DBG(2))) tc_store_row(tile0 + a * TC_TILE_A, t, lo, hi, tab);
           PROF_ADD(2);
           fence_proxy_async();
           __syncwarp();                                  // every lane's rows are fenced: one arrival per warp
-          if (lane == 0 && !(dbg & 128)) mbar_arrive(full0 + a);
+          if (lane == 0 && !(RHE_DBG(128))) mbar_arrive(full0 + a);
           PROF_ADD(4);
         }
       }
@@ -799,7 +805,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     PROF_ADD(5);
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
-    if (!(dbg & 4)) switch (L) {
+    if (!(RHE_DBG(4))) switch (L) {
       case 2: pb_epilogue<2>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
       case 3: pb_epilogue<3>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
       default: pb_epilogue<4>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
@@ -819,7 +825,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
         const int n_in = min(bz, n_stage - st0);
         mbar_wait_s(eb + bar, wait_par);
         if (elect_one()) {
-          if (dbg & 8) mbar_arrive_s(fb + bar);
+          if (RHE_DBG(8)) mbar_arrive_s(fb + bar);
           else {
             mbar_expect_tx_s(fb + bar, (uint32_t)(n_in * tileB_bytes));
             for (int i = 0; i < n_in; ++i)
@@ -854,7 +860,7 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
         PROF_ADD(0);
         mbar_wait_s(fb + 8u * (uint32_t)(b >> bzsh), ph_b);
         PROF_ADD(1);
-        if (!(dbg & 128)) mbar_wait_s(fa + 8u * a, ph_a);
+        if (!(RHE_DBG(128))) mbar_wait_s(fa + 8u * a, ph_a);
         PROF_ADD(2);
         tc_fence_after();
         const uint32_t dcol = dq + k * (uint32_t)(MT * NC);
@@ -865,8 +871,8 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
           for (int j = 0; j < 4; ++j)   // K = 32 SNP rows per instruction: 32 rows x 128 B further down the tile
             if (j < ksteps) umma_i8(dcol, adesc + (uint64_t)(j * 256), bdesc + (uint64_t)(j * 2), idesc, 1u);
           const uint32_t ebb = eb + 8u * (uint32_t)(b >> bzsh);
-          if (dbg & 128) { mbar_arrive_s(ebb); }
-          else if (dbg & 64) { mbar_arrive_s(ea + 8u * a); mbar_arrive_s(ebb); }
+          if (RHE_DBG(128)) { mbar_arrive_s(ebb); }
+          else if (RHE_DBG(64)) { mbar_arrive_s(ea + 8u * a); mbar_arrive_s(ebb); }
           else { umma_commit_s(ea + 8u * a); umma_commit_s(ebb); }
         }
         __syncwarp();
@@ -987,8 +993,7 @@ static inline int pb_budget(int G) { return G == 2 ? 233472 / 2 - 1024 : 232448 
 static inline int pb_ring(int nc, int mt, int G, int* bzsh) {
   const int si = G / mt;
   const int budget = pb_budget(G);
-  const char* env = getenv("PYRHE_TC_DEBUG_RING");       // "1": the unbatched ring
-  if (!(env && atoi(env) == 1)) {
+  if (RHE_DBG_ENV("PYRHE_TC_DEBUG_RING", 0) != 1) {        // "1" (profiling build only): the unbatched ring
     if (si <= 4 && pb_smem_bytes(nc, 8, G) <= budget) { *bzsh = 2; return 8; }    // two batches of four tiles
     if (si <= 2 && pb_smem_bytes(nc, 4, G) <= budget) { *bzsh = 1; return 4; }    // two batches of two tiles
   }
@@ -998,36 +1003,74 @@ static inline int pb_ring(int nc, int mt, int G, int* bzsh) {
   return bs;
 }
 
-int rhe_tc_create(rhe_ctx* c) {
-  const rhe_config& g = c->cfg;
-  TcState* s = new TcState();
-  const char* envL = getenv("PYRHE_B200_LIMBS");
-  s->L = envL ? atoi(envL) : 3;
-  if (s->L < 2 || s->L > 4) { delete s; rhe_set_error("PYRHE_B200_LIMBS must be 2..4"); return RHE_ERR_INVALID; }
-  s->F = 8 * s->L - 2;
-  s->R1p = round_up(c->R1, 4);
-  s->NBa = round_up(s->L * s->R1p, 16);
-  s->Bp = round_up(g.n_vec, 2);
-  s->NCb = round_up(c->n_groups * s->L * s->Bp, 16);   // weight groups (RHS sets) are stacked along N
+// Shape plan of the tensor kernels for one configuration (pure host arithmetic: shared by rhe_tc_supported and
+// rhe_tc_create so that the Python side never has to mirror the limits).
+struct TcShape { int L, F, R1p, NBa, Bp, NCb, MT, G, KG; };
+
+static int tc_shape(const rhe_config& g, TcShape* o, int quiet) {
+  const int R1 = g.n_sets * g.n_cols_set, n_groups = g.n_ops * g.n_sets;
+  const char* envL = getenv("PYRHE_B200_LIMBS");        // precision knob, read once per context
+  o->L = envL ? atoi(envL) : 3;
+  if (o->L < 2 || o->L > 4) { if (!quiet) rhe_set_error("PYRHE_B200_LIMBS must be 2..4"); return RHE_ERR_INVALID; }
+  o->F = 8 * o->L - 2;
+  o->R1p = round_up(R1, 4);
+  o->NBa = round_up(o->L * o->R1p, 16);
+  o->Bp = round_up(g.n_vec, 2);
+  o->NCb = round_up(n_groups * o->L * o->Bp, 16);   // weight groups (RHS sets) are stacked along N
+  o->G = PB_G;
   // M-tiles per CTA and bins per launch: everything in one launch when the accumulators fit (two tiles if possible),
   // otherwise bin groups of two-tile CTAs.
-  if (g.n_bins * 2 * s->NCb <= 512) { s->MT = 2; s->KG = g.n_bins; }
-  else if (g.n_bins * s->NCb <= 512) { s->MT = 1; s->KG = g.n_bins; }
-  else if (2 * s->NCb <= 512) { s->MT = 2; s->KG = 512 / (2 * s->NCb); }
-  else { s->MT = 1; s->KG = s->NCb <= 512 ? 512 / s->NCb : 0; }
+  if (g.n_bins * 2 * o->NCb <= 512) { o->MT = 2; o->KG = g.n_bins; }
+  else if (g.n_bins * o->NCb <= 512) { o->MT = 1; o->KG = g.n_bins; }
+  else if (2 * o->NCb <= 512) { o->MT = 2; o->KG = 512 / (2 * o->NCb); }
+  else { o->MT = 1; o->KG = o->NCb <= 512 ? 512 / o->NCb : 0; }
   {
     // Optional variant (PYRHE_B200_PASSB_GROUPS=2): two half-size CTAs per SM (one M-tile, two decode groups, 256 TMEM
     // columns each), so that the epilogue of one overlaps the main loop of the other.  Measured equal to the default
-    // on config 5 (0.69 vs 0.68 ms per block), so it stays opt-in.
+    // on config 5, so it stays opt-in.
     const char* envG = getenv("PYRHE_B200_PASSB_GROUPS");
-    const bool fits2 = g.n_bins * s->NCb <= 256 && pb_smem_bytes(s->NCb, 2, 2) <= pb_budget(2);
-    if (fits2 && envG && atoi(envG) == 2) { s->G = 2; s->MT = 1; s->KG = g.n_bins; }
+    const bool fits2 = g.n_bins * o->NCb <= 256 && pb_smem_bytes(o->NCb, 2, 2) <= pb_budget(2);
+    if (fits2 && envG && atoi(envG) == 2) { o->G = 2; o->MT = 1; o->KG = g.n_bins; }
   }
-  if (pb_smem_bytes(s->NCb, s->G / s->MT, s->G) > pb_budget(s->G) || s->NBa > 256 || s->KG < 1 || s->KG > 255 || c->n_groups * s->KG * g.n_vec > PB_MAX_KB || c->n_groups * g.n_vec > 64) {
-    rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors exceed one TMEM allocation", c->R1, g.n_bins, g.n_vec);
-    delete s;
+  if (pb_smem_bytes(o->NCb, o->G / o->MT, o->G) > pb_budget(o->G) || o->NBa > 256 || o->KG < 1 || o->KG > 255 ||
+      n_groups * o->KG * g.n_vec > PB_MAX_KB || n_groups * g.n_vec > 64) {
+    if (!quiet)
+      rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors x %d weight groups exceed the tensor kernels' "
+                    "TMEM / shared-memory layout (pass A: %d limb columns <= 256; pass B: %d x %d <= 64 vector columns)",
+                    R1, g.n_bins, g.n_vec, n_groups, o->NBa, n_groups, g.n_vec);
     return RHE_ERR_UNSUPPORTED;
   }
+  return RHE_OK;
+}
+
+int rhe_tc_check(const rhe_config* cfg, int quiet) {
+  TcShape sh;
+  return tc_shape(*cfg, &sh, quiet);
+}
+
+// (Re)allocate the per-block pass-B staging (quantised weights, decode metadata) for `need` positions.  Called from the
+// set-up entry points only (context / plan creation): the device is idle-synchronised before buffers are replaced.
+static int tc_reserve_positions(rhe_ctx* c, TcState* s, int need) {
+  if (need <= s->cap_pos) return RHE_OK;
+  RHE_CUDA(cudaDeviceSynchronize());
+  if (s->uq) cudaFree(s->uq);
+  if (s->pos_meta) cudaFree(s->pos_meta);
+  s->uq = nullptr;
+  s->pos_meta = nullptr;
+  s->cap_pos = round_up(need, 128);
+  RHE_CUDA(cudaMalloc((void**)&s->pos_meta, sizeof(int32_t) * (s->cap_pos + 8 * 512)));   // + one padded chunk per group
+  RHE_CUDA(cudaMalloc((void**)&s->uq, (size_t)s->NCb * s->cap_pos));
+  RHE_CUDA(cudaMemset(s->uq, 0, (size_t)s->NCb * s->cap_pos));
+  return tc_encode_2d(s, &s->tm_uq, s->uq, (uint64_t)s->cap_pos, (uint64_t)s->NCb, (uint32_t)s->NCb);
+}
+
+int rhe_tc_create(rhe_ctx* c) {
+  const rhe_config& g = c->cfg;
+  TcShape sh;
+  int rc = tc_shape(g, &sh, 0);
+  if (rc) return rc;
+  TcState* s = new TcState();
+  s->L = sh.L; s->F = sh.F; s->R1p = sh.R1p; s->NBa = sh.NBa; s->Bp = sh.Bp; s->NCb = sh.NCb; s->MT = sh.MT; s->G = sh.G; s->KG = sh.KG;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
@@ -1043,12 +1086,17 @@ int rhe_tc_create(rhe_ctx* c) {
   alloc((void**)&s->col_dq, sizeof(double) * c->R1);
   alloc((void**)&s->wmax, sizeof(unsigned int) * c->n_groups * g.n_vec);
   if (e != cudaSuccess) { rhe_set_error("tensor-core workspace allocation failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
-  int rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
+  rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
+  if (rc) return rc;
+  // pass-B staging for the largest block of a one-bin-per-SNP annotation (every bin padded to 128 rows); plans with
+  // overlapping annotations grow it at plan creation
+  const int kg = s->KG < g.n_bins ? s->KG : g.n_bins;
+  rc = tc_reserve_positions(c, s, g.n_ops * (round_up(g.max_block_snps, 128) + 128 * kg));
   if (rc) return rc;
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa)));
   {
-    int sh;
-    const int smem = pb_smem_bytes(s->NCb, pb_ring(s->NCb, s->MT, s->G, &sh), s->G);
+    int shb;
+    const int smem = pb_smem_bytes(s->NCb, pb_ring(s->NCb, s->MT, s->G, &shb), s->G);
     if (s->G == 2) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else if (s->MT == 2) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1059,11 +1107,6 @@ int rhe_tc_create(rhe_ctx* c) {
 void rhe_tc_destroy(rhe_ctx* c) {
   TcState* s = (TcState*)c->tc;
   if (!s) return;
-  for (TcBlockMeta& b : s->blocks) {
-    if (b.pos_rows) cudaFree(b.pos_rows);
-    if (b.stage_info) cudaFree(b.stage_info);
-    if (b.bin_count) cudaFree(b.bin_count);
-  }
   void* ptrs[] = {s->rq, s->col_dq, s->uq, s->wmax, s->pos_meta};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete s;
@@ -1099,7 +1142,7 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   CUtensorMap tm_bed;                                  // the block's packed rows as a 2-D byte tensor [m][pitch]
   int rc = tc_encode_2d(s, &tm_bed, const_cast<uint8_t*>(bed), (uint64_t)c->cfg.pitch_bytes, (uint64_t)m, 128);
   if (rc) return rc;
-  const int dbg = getenv("PYRHE_TC_DEBUG_SKIPA") ? atoi(getenv("PYRHE_TC_DEBUG_SKIPA")) : 0;
+  const int dbg = RHE_DBG_ENV("PYRHE_TC_DEBUG_SKIPA", 0);
   k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
       s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw,
       pow2_cols((int)col_a + 32 * PA_AS), col_a, 0, dbg);
@@ -1113,12 +1156,11 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   return RHE_OK;
 }
 
-// Bin-sorted positions of the bins [k0, k0 + kn) of a block: built once per (block, bin group), keyed by the
-// caller's bin_rows pointer.  Bins are numbered locally (0 .. kn - 1) inside the group.
-static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows, const int32_t* bin_off_dev,
-                         const int32_t* bin_off_host, int k0, int kn, cudaStream_t st, TcBlockMeta** out) {
-  for (TcBlockMeta& b : s->blocks)
-    if (b.key == bin_rows && b.m == m && b.k0 == k0 && b.kn == kn) { *out = &b; return RHE_OK; }
+// Bin-sorted positions of the bins [k0, k0 + kn) of a block (bins numbered locally 0 .. kn - 1 inside the group).
+// Set-up path: allocates, copies from host staging vectors and synchronises before they die.
+static int tc_block_meta(rhe_ctx* c, const rhe_block_plan* plan, int k0, int kn, cudaStream_t st, TcBlockMeta* out) {
+  const int m = plan->m;
+  const int32_t* bin_off_host = plan->off_host.data();
   std::vector<int32_t> pstart(kn + 1, 0), counts(kn), info;
   for (int kl = 0; kl < kn; ++kl) {
     counts[kl] = bin_off_host[k0 + kl + 1] - bin_off_host[k0 + kl];
@@ -1128,9 +1170,7 @@ static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows,
       info.push_back(kl | ((done == 0) << 8) | (((left < 128 ? left : 128) + 31) / 32) << 16);
     }
   }
-  TcBlockMeta b;
-  b.key = bin_rows;
-  b.m = m;
+  TcBlockMeta& b = *out;
   b.k0 = k0;
   b.kn = kn;
   b.n_pos = pstart[kn];
@@ -1145,40 +1185,57 @@ static int tc_block_meta(rhe_ctx* c, TcState* s, int m, const int32_t* bin_rows,
   RHE_CUDA(cudaMalloc((void**)&b.bin_count, sizeof(int32_t) * kn));
   int32_t* d_pstart = nullptr;
   RHE_CUDA(cudaMalloc((void**)&d_pstart, sizeof(int32_t) * (kn + 1)));
-  RHE_CUDA(cudaMemcpyAsync(d_pstart, pstart.data(), sizeof(int32_t) * (kn + 1), cudaMemcpyHostToDevice, st));
-  RHE_CUDA(cudaMemcpyAsync(b.bin_count, counts.data(), sizeof(int32_t) * kn, cudaMemcpyHostToDevice, st));
-  if (!info.empty())
-    RHE_CUDA(cudaMemcpyAsync(b.stage_info, info.data(), sizeof(int32_t) * info.size(), cudaMemcpyHostToDevice, st));
-  k_tc_positions<<<dim3(rhe_div_up(m, 256), kn), 256, 0, st>>>(bin_rows, bin_off_dev, k0, d_pstart, b.pos_rows);
-  RHE_LAUNCH_CHECK(c);
-  RHE_CUDA(cudaStreamSynchronize(st));     // the host staging vectors die here (first sight of the block only)
+  cudaError_t e = cudaMemcpyAsync(d_pstart, pstart.data(), sizeof(int32_t) * (kn + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b.bin_count, counts.data(), sizeof(int32_t) * kn, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && !info.empty())
+    e = cudaMemcpyAsync(b.stage_info, info.data(), sizeof(int32_t) * info.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    k_tc_positions<<<dim3(rhe_div_up(m, 256), kn), 256, 0, st>>>(plan->bin_rows, plan->off_dev, k0, d_pstart, b.pos_rows);
+    c->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);     // the host staging vectors die here
   cudaFree(d_pstart);
-  s->blocks.push_back(b);
-  *out = &s->blocks.back();
+  if (e != cudaSuccess) { rhe_set_error("tc_block_meta: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
   return RHE_OK;
+}
+
+int rhe_tc_plan_create(rhe_ctx* c, rhe_block_plan* plan, cudaStream_t st) {
+  TcState* s = (TcState*)c->tc;
+  TcPlan* tp = new TcPlan();
+  plan->tc = tp;
+  const int K = c->cfg.n_bins;
+  int need = 0;
+  for (int k0 = 0; k0 < K; k0 += s->KG) {
+    const int kn = K - k0 < s->KG ? K - k0 : s->KG;
+    tp->groups.emplace_back();
+    int rc = tc_block_meta(c, plan, k0, kn, st, &tp->groups.back());
+    if (rc) return rc;
+    if (c->cfg.n_ops * tp->groups.back().n_pos > need) need = c->cfg.n_ops * tp->groups.back().n_pos;
+  }
+  return tc_reserve_positions(c, s, need);
+}
+
+void rhe_tc_plan_destroy(rhe_block_plan* plan) {
+  TcPlan* tp = (TcPlan*)plan->tc;
+  if (!tp) return;
+  for (TcBlockMeta& b : tp->groups) {
+    if (b.pos_rows) cudaFree(b.pos_rows);
+    if (b.stage_info) cudaFree(b.stage_info);
+    if (b.bin_count) cudaFree(b.bin_count);
+  }
+  delete tp;
+  plan->tc = nullptr;
 }
 
 // One launch per bin group of at most KG bins (the accumulators of KG bins x MT tiles fill the TMEM allocation); every
 // group walks only the bin-sorted rows of its own bins, so the block is still read once in total.
-static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, const int32_t* bin_rows, const int32_t* bin_off,
-                           const int32_t* bin_off_host, int k0, int kn, float* P_out, float* S_accum, cudaStream_t st) {
+static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, const TcBlockMeta* meta, float* P_out,
+                           float* S_accum, cudaStream_t st) {
   const rhe_config& g = c->cfg;
-  const int K = g.n_bins, B = g.n_vec;
-  TcBlockMeta* meta = nullptr;
-  int rc = tc_block_meta(c, s, m, bin_rows, bin_off, bin_off_host, k0, kn, st, &meta);
-  if (rc) return rc;
+  const int K = g.n_bins, B = g.n_vec, k0 = meta->k0, kn = meta->kn;
   const int n_pos = meta->n_pos, n_modes = g.n_ops;
-  if (n_modes * n_pos > s->cap_pos) {
-    RHE_CUDA(cudaStreamSynchronize(st));
-    if (s->uq) cudaFree(s->uq);
-    if (s->pos_meta) cudaFree(s->pos_meta);
-    s->cap_pos = round_up(n_modes * (n_pos + n_pos / 8), 128);
-    RHE_CUDA(cudaMalloc((void**)&s->pos_meta, sizeof(int32_t) * (s->cap_pos + 8 * 512)));   // + one padded chunk per group
-    RHE_CUDA(cudaMalloc((void**)&s->uq, (size_t)s->NCb * s->cap_pos));
-    RHE_CUDA(cudaMemset(s->uq, 0, (size_t)s->NCb * s->cap_pos));
-    rc = tc_encode_2d(s, &s->tm_uq, s->uq, (uint64_t)s->cap_pos, (uint64_t)s->NCb, (uint32_t)s->NCb);
-    if (rc) return rc;
-  }
+  if (n_modes * n_pos > s->cap_pos) { rhe_set_error("pass B staging smaller than the plan (plan of another context?)"); return RHE_ERR_STATE; }
   const int n_stage = n_modes * n_pos / 128, SI = s->G / s->MT;
   const int n_chunk = rhe_div_up(rhe_div_up(n_stage, SI), 4);       // chunks of four own stages per decode group
   if (n_pos > 0) {
@@ -1190,9 +1247,9 @@ static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, co
   const uint32_t cols = pow2_cols(kn * s->MT * s->NCb);
   int bzsh = 0;
   const int bs = pb_ring(s->NCb, s->MT, s->G, &bzsh), smem = pb_smem_bytes(s->NCb, bs, s->G);
-  const int a_major = getenv("PYRHE_TC_DEBUG_KMAJOR") ? 0 : 1;
-  const int kcap = getenv("PYRHE_TC_DEBUG_KSTEPS") ? atoi(getenv("PYRHE_TC_DEBUG_KSTEPS")) : 4;
-  const int dbg = getenv("PYRHE_TC_DEBUG_SKIP") ? atoi(getenv("PYRHE_TC_DEBUG_SKIP")) : 0;
+  const int a_major = RHE_DBG_ENV("PYRHE_TC_DEBUG_KMAJOR", 0) ? 0 : 1;
+  const int kcap = RHE_DBG_ENV("PYRHE_TC_DEBUG_KSTEPS", 4);
+  const int dbg = RHE_DBG_ENV("PYRHE_TC_DEBUG_SKIP", 0);
   const int rs_stride = g.n_sets == 2 ? c->Np : 0;
 #define PB_LAUNCH(MT_, G_)                                                                                                   \
   k_tc_pass_b<MT_, G_><<<c->Np / (128 * MT_), PB_THREADS_OF(G_), smem, st>>>(                                                \
@@ -1207,13 +1264,12 @@ static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, co
   return RHE_OK;
 }
 
-int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, int m, const int32_t* bin_rows, const int32_t* bin_off,
-                  const int32_t* bin_off_host, float* P_out, float* S_accum, cudaStream_t st) {
+int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, const rhe_block_plan* plan, float* P_out, float* S_accum, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
-  const int K = c->cfg.n_bins;
-  for (int k0 = 0; k0 < K; k0 += s->KG) {
-    const int kn = K - k0 < s->KG ? K - k0 : s->KG;
-    int rc = tc_pass_b_group(c, s, bed, m, bin_rows, bin_off, bin_off_host, k0, kn, P_out, S_accum, st);
+  const TcPlan* tp = (const TcPlan*)plan->tc;
+  if (!tp) { rhe_set_error("rhe_block_accumulate: the plan was created without the tensor-core path"); return RHE_ERR_STATE; }
+  for (const TcBlockMeta& meta : tp->groups) {
+    int rc = tc_pass_b_group(c, s, bed, plan->m, &meta, P_out, S_accum, st);
     if (rc) return rc;
   }
   return RHE_OK;

@@ -41,6 +41,143 @@ def allreduce_sum(tensors, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+class BlockStreamer:
+    """Bounded-memory, pipelined `.bed` ingest of one rank (base.py:338-345 reads one block at a time).
+
+    host rows (numpy array / memmap of the `.bed` payload) --staging threads--> pinned ring --copy stream--> device slot
+    (+ the block's allele counts, `rhe_block_stats`, on the same stream).  One background thread drives the staging
+    and queues the copies, so the caller's thread only enqueues kernels: staging of block n+1 overlaps the PCIe copy
+    of block n and the kernels of block n-1.  When the engine holds a ring of R device slots, the copy of block n
+    waits (on the device) for the kernels of block n-R, so HBM use is bounded by R blocks whatever the size of the
+    `.bed` share.  File-backed sources are read with `preadv` straight into the pinned ring (no page-fault walk over
+    a mapping); in-memory arrays are copied by the same threads.
+    """
+
+    def __init__(self, eng: "RheEngine", packed: np.ndarray, n_workers: Optional[int] = None, ring_host: int = 3):
+        import os
+        self.eng = eng
+        self.packed = packed
+        cores = os.cpu_count() or 4
+        self.n_workers = max(1, n_workers if n_workers else min(16, max(2, cores // max(eng.world, 1))))
+        self.ring_host = max(1, min(ring_host, max(len(eng.own), 1)))
+        self.copy_stream = torch.cuda.Stream(eng.device)
+        # the genotype buffer was zeroed on the caller's stream: order that memset before the first copy
+        self.copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
+        eng.bed.record_stream(self.copy_stream)
+        eng.counts.record_stream(self.copy_stream)
+        self._fd, self._file_off = None, 0
+        fname = getattr(packed, "filename", None)
+        if fname is not None and isinstance(packed, np.memmap) and packed.flags.c_contiguous \
+                and packed.shape[1] == eng.row_bytes:
+            self._fd = os.open(fname, os.O_RDONLY)
+            self._file_off = int(packed.offset)
+        with torch.cuda.device(eng.device):
+            self.slots = [torch.empty((eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
+                          for _ in range(self.ring_host)]
+        self.views = [sl.numpy() for sl in self.slots]
+        self.thread = None
+        self.errors = []
+        self.bytes_staged = 0
+        self.passes = 0
+
+    # ---- staging
+    def _read_chunk(self, dst: np.ndarray, first_row: int):
+        """Rows [first_row, first_row + len(dst)) of the payload into a contiguous piece of a pinned slot."""
+        import os
+        if self._fd is not None:
+            mv = memoryview(dst).cast("B")
+            off = self._file_off + first_row * self.eng.row_bytes
+            done = 0
+            while done < len(mv):
+                n = os.preadv(self._fd, [mv[done:]], off + done)
+                if n <= 0:
+                    raise IOError("short read from the .bed file")
+                done += n
+        else:
+            np.copyto(dst, self.packed[first_row: first_row + dst.shape[0]])
+
+    def _worker(self, order):
+        from concurrent.futures import ThreadPoolExecutor
+        eng = self.eng
+        R = eng.ring_blocks
+        try:
+            with torch.cuda.device(eng.device), ThreadPoolExecutor(self.n_workers) as pool:
+                slot_free = [None] * self.ring_host            # event of the last H2D copy that read the pinned slot
+                for n, j in enumerate(order):
+                    a, b = eng.ranges[j]
+                    m = b - a
+                    k = n % self.ring_host
+                    if slot_free[k] is not None:
+                        slot_free[k].synchronize()
+                    step = -(-m // self.n_workers)
+                    futs = [pool.submit(self._read_chunk, self.views[k][r0:min(m, r0 + step)], a + r0)
+                            for r0 in range(0, m, step)]
+                    for f in futs:
+                        f.result()
+                    self.bytes_staged += m * eng.row_bytes
+                    if R is not None and n >= R:               # the device slot still belongs to block n - R
+                        prev = order[n - R]
+                        self._released[prev].wait()
+                        if self.errors:
+                            return
+                        self.copy_stream.wait_event(self._done[prev])
+                    eng.upload_block(j, self.slots[k][:m], stream=self.copy_stream)
+                    ev = torch.cuda.Event()
+                    ev.record(self.copy_stream)
+                    self._events[j] = ev
+                    slot_free[k] = ev
+                    self._ready[j].set()
+                self.copy_stream.synchronize()
+        except Exception as exc:          # surfaced by acquire() / check()
+            self.errors.append(exc)
+            for e in self._ready.values():
+                e.set()
+
+    # ---- protocol used by RheEngine._pass
+    def start(self, order):
+        import threading
+        self.join()
+        self._ready = {j: threading.Event() for j in order}
+        self._released = {j: threading.Event() for j in order}
+        self._events, self._done = {}, {}
+        self.passes += 1
+        self.thread = threading.Thread(target=self._worker, args=(list(order),), daemon=True)
+        self.thread.start()
+
+    def acquire(self, j):
+        """Blocks the host until block j's copy (and count) has been queued; returns the event it signals."""
+        self._ready[j].wait()
+        self.check()
+        return self._events[j]
+
+    def release(self, j, stream):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self._done[j] = ev
+        self._released[j].set()
+
+    def check(self):
+        if self.errors:
+            for e in getattr(self, "_released", {}).values():
+                e.set()
+            raise self.errors[0]
+
+    def join(self):
+        if self.thread is not None:
+            self.thread.join()
+            self.thread = None
+
+    def close(self):
+        import os
+        for e in getattr(self, "_released", {}).values():
+            e.set()
+        self.join()
+        if self._fd is not None:
+            os.close(self._fd)
+            self._fd = None
+        self.slots, self.views = [], []
+
+
 class RheEngine:
     def __init__(self, plan: PathPlan, *, n_indv: int, keep: np.ndarray, annot: np.ndarray, num_jack: int,
                  impute: str = "binary", seed: int = 0, device: Optional[torch.device] = None,
@@ -50,8 +187,14 @@ class RheEngine:
             raise _lib.RheError("pyrhe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.plan = plan
-        if kernel_path is None:      # int8 tcgen05 kernels whenever the layout fits one TMEM allocation
-            kernel_path = _lib.PATH_TCGEN05 if _lib.tcgen05_supported(plan) else _lib.PATH_SIMT
+        if kernel_path is None:      # int8 tcgen05 kernels whenever the layout fits them (asked of the library)
+            kernel_path = _lib.PATH_TCGEN05
+            why = _lib.tcgen05_unsupported_reason(plan)
+            if why:
+                import warnings
+                warnings.warn("pyrhe_b200: falling back to the CUDA-core kernels (about 50x slower than the tcgen05 "
+                              f"path): {why}", RuntimeWarning, stacklevel=2)
+                kernel_path = _lib.PATH_SIMT
         self.kernel_path = kernel_path
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rank, self.world, self.pg = rank, world, process_group
@@ -103,18 +246,38 @@ class RheEngine:
             if impute == "binary":
                 self.uniforms = torch.from_numpy(impute_uniforms(seed, self.max_m)).to(self.device)
                 _lib.check(self.lib.rhe_set_uniforms(self._ctx, _lib.ptr(self.uniforms), self.max_m))
+            # annotation metadata of every own block, resident before the first block is seen: the per-block call
+            # neither allocates nor synchronises (include/pyrhe_b200.h)
+            self._plans = {}
+            for j in self.own:
+                lo, _ = self._row_slices[j]
+                handle = C.c_void_p()
+                _lib.check(self.lib.rhe_block_plan_create(
+                    self._ctx, self.ranges[j][1] - self.ranges[j][0], C.c_void_p(self.bin_rows.data_ptr() + 4 * lo),
+                    self._offs[j], self._stream(), C.byref(handle)))
+                self._plans[j] = handle
         self.bed = None
+        self.counts = None
+        self.ring_blocks = None
+        self._counted = set()
+        #: hand the ingest-time allele counts to rhe_block_accumulate (False: every call re-counts the block)
+        self.use_resident_counts = True
         self._row_off = {}
         cur = 0
         for j in self.own:
             self._row_off[j] = cur
             cur += self.ranges[j][1] - self.ranges[j][0]
         self.m_own = cur
+        self._slot_off = dict(self._row_off)
         self.nxe_S = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
         if getattr(self, "_ctx", None):
+            torch.cuda.synchronize(self.device)
+            for handle in getattr(self, "_plans", {}).values():
+                self.lib.rhe_block_plan_destroy(self._ctx, handle)
+            self._plans = {}
             self.lib.rhe_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -156,107 +319,124 @@ class RheEngine:
                 full[:, np.nonzero(self.keep)[0]] = ((np.asarray(env, np.float64) ** 2)[:, None] * Z).T
                 self.nxe_S = torch.from_numpy(full).to(self.device)
 
-    def alloc_genotypes(self):
-        """Zeroed device buffer for this rank's `.bed` rows, pitch padded to 128 bytes."""
+    # ------------------------------------------------------------------ genotype residency
+    def alloc_genotypes(self, ring_blocks: Optional[int] = None):
+        """Device buffer for `.bed` rows, pitch padded to 128 bytes, zeroed (the padding stays zero).
+
+        ring_blocks=None: every own block resident (`m_own x pitch` bytes).  ring_blocks=R: a ring of R block-sized
+        slots for the bounded-memory ingest (`stream_genotypes`), the way the reference holds one block at a time
+        (/root/reference/pyrhe/src/base/base.py:338-345, base_streaming.py:85-104): block n of the streaming order
+        lives in slot n % R until its kernels have run.  Next to the rows sit the per-SNP allele counts
+        (`rhe_block_stats`), filled when a block becomes resident."""
         with torch.cuda.device(self.device):
-            self.bed = torch.zeros((max(self.m_own, 1), self.pitch), dtype=torch.uint8, device=self.device)
+            if ring_blocks is None:
+                self.ring_blocks = None
+                rows = max(self.m_own, 1)
+                self._slot_off = dict(self._row_off)
+            else:
+                self.ring_blocks = R = max(1, min(int(ring_blocks), max(len(self.own), 1)))
+                rows = R * self.max_m
+                self._slot_off = {j: (n % R) * self.max_m for n, j in enumerate(self.own)}
+            self.bed = torch.zeros((rows, self.pitch), dtype=torch.uint8, device=self.device)
+            self.counts = torch.zeros((rows, 4), dtype=torch.int32, device=self.device)
+            self._counted = set()
         return self.bed
 
-    def upload_block(self, j: int, host_rows, stream=None):
-        """Host `.bed` rows of block j ([m_j, row_bytes] uint8 numpy / pinned torch) -> device."""
+    def genotype_bytes(self) -> int:
+        return 0 if self.bed is None else self.bed.numel() + self.counts.numel() * 4
+
+    def block_view(self, j: int):
+        m = self.ranges[j][1] - self.ranges[j][0]
+        off = self._slot_off[j]
+        return self.bed[off: off + m], m
+
+    def count_block(self, j: int, stream=None):
+        """Per-SNP allele counts of resident block j (`rhe_block_stats`): the one read of the block that depends on
+        nothing but the genotypes, done when the block lands so that no later pass repeats it."""
+        rows, m = self.block_view(j)
+        st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        cnt = self.counts[self._slot_off[j]: self._slot_off[j] + m]
+        _lib.check(self.lib.rhe_block_stats(self._ctx, C.c_void_p(rows.data_ptr()), m, _lib.ptr(cnt), st))
+        self._counted.add(j)
+
+    def count_all(self):
+        for j in self.own:
+            self.count_block(j)
+
+    def upload_block(self, j: int, host_rows, stream=None, count: bool = True):
+        """Host `.bed` rows of block j ([m_j, row_bytes] uint8 numpy / pinned torch) -> its device slot (+ counts)."""
         a, b = self.ranges[j]
         m = b - a
         st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
-        dst = self.bed[self._row_off[j]]
+        dst = self.bed[self._slot_off[j]]
         _lib.check(self.lib.rhe_upload_rows(_lib.ptr(host_rows), self.row_bytes, m, C.c_void_p(dst.data_ptr()),
                                             self.pitch, st))
+        if count:
+            self.count_block(j, stream)
 
     def load_genotypes(self, packed: np.ndarray):
-        """packed [M, row_bytes] (numpy / memmap of the .bed payload): uploads this rank's blocks."""
-        if self.bed is None:
+        """packed [M, row_bytes] (numpy / memmap of the .bed payload): uploads this rank's blocks (synchronous)."""
+        if self.bed is None or self.ring_blocks is not None:
             self.alloc_genotypes()
         for j in self.own:
             a, b = self.ranges[j]
             self.upload_block(j, np.ascontiguousarray(packed[a:b]))
         torch.cuda.current_stream(self.device).synchronize()
 
-    def load_genotypes_async(self, packed: np.ndarray, n_workers: int = 4, ring: int = 3):
+    def plan_residency(self, reserve_bytes: float = 8e9) -> Optional[int]:
+        """None when this rank's whole `.bed` share (plus the stored partials, if kept) fits the free HBM, else the
+        number of ring slots to stream through."""
+        free_b, _ = torch.cuda.mem_get_info(self.device)
+        part = len(self.own) * self.plan.E * self.plan.B * self.Np * 4 if self.store_partials else 0
+        need = self.m_own * (self.pitch + 16) + part + 3 * self.plan.E * self.plan.B * self.Np * 4
+        return None if need + reserve_bytes < free_b else 4
+
+    def stream_genotypes(self, packed: np.ndarray, n_workers: Optional[int] = None, ring_host: int = 3,
+                         ring_blocks="auto"):
         """Pipelined ingest: `.bed` rows (numpy array or memmap) -> pinned staging ring -> device.
+        Returns the `BlockStreamer` to hand to `run(upload=...)`."""
+        if ring_blocks == "auto":
+            ring_blocks = self.plan_residency()
+        if self.bed is None or self.ring_blocks != ring_blocks:
+            self.alloc_genotypes(ring_blocks)
+        return BlockStreamer(self, packed, n_workers=n_workers, ring_host=ring_host)
 
-        A pool of `n_workers` threads copies row ranges of block j from `packed` (page cache / disk) into one of `ring`
-        pinned slots (numpy copies release the GIL, so the reads fault in parallel); the uploader thread then queues
-        one asynchronous 2-D copy per block on a side stream and records an event.  Staging of block j+1 therefore
-        overlaps the PCIe copy of block j and the kernels of block j-1.  Pass the returned handle to
-        `run(upload=...)`; block j is consumed as soon as its own copy has finished."""
-        import threading
-        from concurrent.futures import ThreadPoolExecutor
-        if self.bed is None:
-            self.alloc_genotypes()
-        copy_stream = torch.cuda.Stream(self.device)
-        ready = {j: threading.Event() for j in self.own}
-        events = {}
-        errors = []
-        max_m = max((self.ranges[j][1] - self.ranges[j][0] for j in self.own), default=0)
-        ring = max(1, min(ring, len(self.own)))
-        n_workers = max(1, n_workers)
-
-        def worker():
-            try:
-                with torch.cuda.device(self.device):
-                    slots = [torch.empty((max_m, self.row_bytes), dtype=torch.uint8).pin_memory() for _ in range(ring)]
-                    views = [sl.numpy() for sl in slots]
-                    slot_free = [None] * ring                      # event of the last H2D copy that read the slot
-                    with ThreadPoolExecutor(n_workers) as pool:
-                        for n, j in enumerate(self.own):
-                            a, b = self.ranges[j]
-                            m = b - a
-                            k = n % ring
-                            if slot_free[k] is not None:
-                                slot_free[k].synchronize()
-                            step = -(-m // n_workers)
-                            futs = [pool.submit(np.copyto, views[k][r0:min(m, r0 + step)], packed[a + r0:a + min(m, r0 + step)])
-                                    for r0 in range(0, m, step)]
-                            for f in futs:
-                                f.result()
-                            self.upload_block(j, slots[k][:m], stream=copy_stream)
-                            ev = torch.cuda.Event()
-                            ev.record(copy_stream)
-                            events[j] = ev
-                            slot_free[k] = ev
-                            ready[j].set()
-                    copy_stream.synchronize()                      # the pinned slots die with this thread
-            except Exception as exc:          # surfaced by run()
-                errors.append(exc)
-                for e in ready.values():
-                    e.set()
-
-        thread = threading.Thread(target=worker, daemon=True)
-        thread.start()
-        return dict(ready=ready, events=events, errors=errors, thread=thread)
-
-    def block_view(self, j: int):
-        m = self.ranges[j][1] - self.ranges[j][0]
-        return self.bed[self._row_off[j]: self._row_off[j] + m], m
+    load_genotypes_async = stream_genotypes          # round-1 name
 
     # ------------------------------------------------------------------ the path
     def _accumulate(self, j, P_out, S_accum, gram_out):
         rows, m = self.block_view(j)
-        lo, _ = self._row_slices[j]
+        cnt = None
+        if j in self._counted and self.use_resident_counts:
+            cnt = C.c_void_p(self.counts.data_ptr() + 16 * self._slot_off[j])
         _lib.check(self.lib.rhe_block_accumulate(
-            self._ctx, C.c_void_p(rows.data_ptr()), m, C.c_void_p(self.bin_rows.data_ptr() + 4 * lo),
-            self._offs[j], _lib.ptr(P_out), _lib.ptr(S_accum), _lib.ptr(gram_out), self._stream()))
+            self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], cnt, _lib.ptr(P_out), _lib.ptr(S_accum),
+            _lib.ptr(gram_out), self._stream()))
 
-    def run(self, upload_events=None, upload=None) -> dict:
+    def _pass(self, upload, body):
+        """One sweep over the own blocks in order; with a streamer, block j is consumed as soon as its own copy has
+        landed and its device slot is handed back right after its kernels are queued."""
+        cur = torch.cuda.current_stream(self.device)
+        if upload is not None:
+            upload.start(self.own)
+        for jl, j in enumerate(self.own):
+            if upload is not None:
+                cur.wait_event(upload.acquire(j))
+            body(jl, j)
+            if upload is not None:
+                upload.release(j, cur)
+
+    def run(self, upload=None) -> dict:
         """All own blocks -> totals -> all-reduce -> leave-one-out Grams.
 
-        Returns host arrays XX [J+1, E, E] and G_blk [J, E_reg, Rs, Rs] (identical on all ranks).
-        `upload_events[j]`, when given, is a CUDA event the block's genotype upload signals; `upload` is the handle
-        of `load_genotypes_async` (events appear as the background thread records them)."""
+        Returns host arrays XX [J+1, E, E] and G_blk [J, E_reg, Rs, Rs] (identical on all ranks).  `upload` is the
+        `BlockStreamer` of `stream_genotypes`; without it the blocks must already be resident (`load_genotypes`)."""
         plan = self.plan
         E, E_reg, B, Rs, Np, J = plan.E, plan.E_reg, plan.B, plan.Rs, self.Np, self.J
         dev = self.device
+        if upload is None and self.ring_blocks is not None and self.ring_blocks < len(self.own):
+            raise _lib.RheError("genotypes live in a ring: run() needs the streamer (upload=...)")
         with torch.cuda.device(dev):
-            cur = torch.cuda.current_stream(dev)
             S = torch.zeros((E, B, Np), dtype=torch.float32, device=dev)
             G_blk = torch.zeros((J, E_reg, Rs, Rs), dtype=torch.float64, device=dev)
             XX = torch.zeros((J + 1, E, E), dtype=torch.float64, device=dev)
@@ -267,21 +447,12 @@ class RheEngine:
                 P_all = torch.empty((max(len(self.own), 1), E, B, Np), dtype=torch.float32, device=dev)
                 if E > E_reg:
                     P_all[:, E_reg:].zero_()
-            for jl, j in enumerate(self.own):
-                if upload is not None:
-                    upload["ready"][j].wait()
-                    if upload["errors"]:
-                        raise upload["errors"][0]
-                    cur.wait_event(upload["events"][j])
-                if upload_events is not None:
-                    cur.wait_event(upload_events[j])
-                self._accumulate(j, P_all[jl] if self.store_partials else None, S, G_blk[j])
+            self._pass(upload, lambda jl, j: self._accumulate(j, P_all[jl] if self.store_partials else None, S, G_blk[j]))
             if self.world > 1:
                 allreduce_sum([S, G_blk], self.pg)
             if plan.has_nxe:
                 S[E_reg].copy_(self.nxe_S)
             length = B * Np
-            scratch = None
             if self.store_partials and len(self.own) > 0:
                 # stored partials are contiguous, and so are the XX slots of this rank's (contiguous) blocks: up to
                 # four blocks per launch share one read of S
@@ -289,17 +460,18 @@ class RheEngine:
                 _lib.check(self.lib.rhe_loo_gram_multi(
                     self._ctx, _lib.ptr(S), _lib.ptr(P_all), E * B * Np, len(self.own), E, length,
                     _lib.ptr(XX[j0]), E * E, self._stream()))
-            for jl, j in enumerate(self.own if not self.store_partials else []):
-                if self.store_partials:
-                    Pj = P_all[jl]
-                else:                                               # streaming policy: recompute the block
-                    if scratch is None:
-                        scratch = torch.zeros((E, B, Np), dtype=torch.float32, device=dev)
-                        gscratch = torch.zeros((E_reg, Rs, Rs), dtype=torch.float64, device=dev)
+            elif len(self.own) > 0:
+                # streaming policy (base_streaming.py:110-144): a second sweep recomputes every block's partial and
+                # forms its leave-one-out Gram at once; in ring mode the rows are streamed from the host again
+                scratch = torch.zeros((E, B, Np), dtype=torch.float32, device=dev)
+                gscratch = torch.zeros((E_reg, Rs, Rs), dtype=torch.float64, device=dev)
+
+                def second(jl, j):
                     self._accumulate(j, scratch, None, gscratch)
-                    Pj = scratch
-                _lib.check(self.lib.rhe_loo_gram(self._ctx, _lib.ptr(S), _lib.ptr(Pj), E, length, _lib.ptr(XX[j]),
-                                                 self._stream()))
+                    _lib.check(self.lib.rhe_loo_gram(self._ctx, _lib.ptr(S), _lib.ptr(scratch), E, length,
+                                                     _lib.ptr(XX[j]), self._stream()))
+                resident = self.ring_blocks is None or self.ring_blocks >= len(self.own)
+                self._pass(None if resident else upload, second)
             if self.rank == self.world - 1:
                 _lib.check(self.lib.rhe_loo_gram(self._ctx, _lib.ptr(S), None, E, length, _lib.ptr(XX[J]),
                                                  self._stream()))
@@ -307,6 +479,8 @@ class RheEngine:
                 allreduce_sum([XX], self.pg)
             self.S, self.P_all = S, P_all
             out = dict(XX=XX.cpu().numpy(), G_blk=G_blk.cpu().numpy(), M=self.Mjk)
+            if upload is not None:
+                upload.check()
         return out
 
     def decode_rows(self, packed_rows: np.ndarray) -> np.ndarray:

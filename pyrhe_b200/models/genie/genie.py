@@ -61,6 +61,8 @@ class GENIE(Base):
         (read back from the assembled trace column)."""
         if k < self.num_bin:
             return self.num_indv
+        if self._hook_mode:       # an extender's hook filled the state arrays: the reference's own expression
+            return np.sum(self.XXz[k][b_idx] * self.all_zb.T) / (self.num_random_vec * self.M[j][k])
         T, _ = self.setup_lhs_rhs_jackknife(j, None)
         tr = T[k, self.num_estimates]
         if self.use_cov:   # undo the covariate correction base.py:612-618 applies on top

@@ -67,12 +67,13 @@ def write_pheno(path: str, Y: np.ndarray, missing_rows=()) -> None:
             f.write(f"{i} {i} " + " ".join(vals) + "\n")
 
 
-def write_cov(path: str, W: np.ndarray) -> None:
+def write_cov(path: str, W: np.ndarray, missing_cells=()) -> None:
     N, C = W.shape
+    miss = set((int(i), int(c)) for i, c in missing_cells)
     with open(path, "w") as f:
         f.write("FID IID " + " ".join(f"cov{c}" for c in range(C)) + "\n")
         for i in range(N):
-            f.write(f"{i} {i} " + " ".join(repr(float(v)) for v in W[i]) + "\n")
+            f.write(f"{i} {i} " + " ".join("NA" if (i, c) in miss else repr(float(W[i, c])) for c in range(C)) + "\n")
 
 
 def write_env(path: str, env: np.ndarray) -> None:
@@ -101,12 +102,20 @@ def random_annot(M: int, K: int, rng: np.random.Generator, overlap: float = 0.0)
 def make_dataset(outdir: str, name: str, N: int, M: int, K: int, *, seed: int = 0,
                  n_cov: int = 0, n_traits: int = 1, missing_rate: float = 0.0,
                  missing_pheno=(), with_env: bool = False, h2: float = 0.25,
-                 overlap: float = 0.0) -> dict:
-    """Write a full synthetic data set; returns the paths (keys = reference kwarg names)."""
+                 overlap: float = 0.0, maf_lo: float = 0.05, maf_hi: float = 0.5,
+                 monomorphic=(), binary_pheno: bool = False, cov_missing=()) -> dict:
+    """Write a full synthetic data set; returns the paths (keys = reference kwarg names).
+
+    The later keywords only change the data when given (the random stream of the existing cases is untouched):
+    `maf_lo/maf_hi` the allele-frequency range (rare variants), `monomorphic` SNP rows forced to count 0,
+    `binary_pheno` thresholds every trait at its median into {0, 1} (case/control, rhe.py:79-88), `cov_missing`
+    (row, column) covariate cells written as NA."""
     os.makedirs(outdir, exist_ok=True)
     rng = np.random.default_rng(seed)
     prefix = os.path.join(outdir, name)
-    counts = random_counts(N, M, rng, missing_rate)
+    counts = random_counts(N, M, rng, missing_rate, maf_lo, maf_hi)
+    for s in monomorphic:
+        counts[s] = 0
     write_bed(prefix + ".bed", counts)
     write_plink_text(prefix, N, M)
     annot = random_annot(M, K, rng, overlap)
@@ -123,11 +132,13 @@ def make_dataset(outdir: str, name: str, N: int, M: int, K: int, *, seed: int = 
         W = rng.standard_normal((N, n_cov))
         W[:, 0] = (rng.random(N) < 0.5).astype(np.float64)
         Y += (W @ rng.standard_normal((n_cov, 1))) * 0.3
-        write_cov(prefix + ".cov", W)
+        write_cov(prefix + ".cov", W, cov_missing)
         paths["cov_file"] = prefix + ".cov"
     if with_env:
         env = (rng.random(N) < 0.4).astype(np.float64)
         write_env(prefix + ".env", env)
         paths["env_file"] = prefix + ".env"
+    if binary_pheno:
+        Y = (Y > np.median(Y, axis=0)).astype(np.float64)
     write_pheno(prefix + ".pheno", Y, missing_pheno)
     return paths

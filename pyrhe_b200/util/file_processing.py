@@ -85,7 +85,12 @@ def read_cov(filename, std: bool = False, missing_indvs: list = None, cov_impute
     """(covariate matrix, all missing rows) -- file_processing.py:121-199.
 
     `one_hot_conversion` only writes `<column>_one_hot.cov` side files; the returned matrix
-    keeps the original columns."""
+    keeps the original columns.
+
+    `cov_impute_method="mean"`: NA / -9 cells are replaced by their column mean and the individual is KEPT.  The
+    reference reports those individuals as missing all the same (file_processing.py:157) while their rows stay in the
+    covariate matrix, so phenotype and covariates end up with different lengths (and under pandas >= 3 its chained
+    `fillna(inplace=True)` no longer fills at all): it cannot run such a file.  This is the intended behaviour."""
     try:
         df = pd.read_csv(filename, sep=r"\s+")
     except FileNotFoundError:
@@ -99,8 +104,9 @@ def read_cov(filename, std: bool = False, missing_indvs: list = None, cov_impute
     if cov_impute_method == "ignore":
         df = df[~is_missing]
     else:
-        df = df.replace({"NA": np.nan, "-9": np.nan})
+        df = df.replace({"NA": np.nan, "-9": np.nan, -9: np.nan}).astype(float)
         df = df.fillna(df.mean())
+        newly_missing = []
     for column in df.columns:
         n_unique = df[column].nunique()
         if n_unique <= categorical_threshold:

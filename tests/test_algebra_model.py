@@ -3,13 +3,13 @@ reference's per-jackknife T and q (golden vectors) -- no GPU needed."""
 import numpy as np
 import pytest
 
-from golden_cases import CASES
+from golden_cases import CASES, SMALL_CASES
 from helpers import load_golden, oracle_problem
 from device_model import run_model, assemble_all
 from pyrhe_b200.assemble import PathPlan
 from pyrhe_b200.hostmath import host_terms, binary_fill_values
 
-SMALL = [n for n in CASES if n != "rhe_example_shape"]
+SMALL = list(SMALL_CASES)
 
 
 def plan_for(p, Ty=1):

@@ -90,13 +90,30 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.rhe_version() == 1
+    assert lib.rhe_version() == 2
     # argument validation happens before any CUDA call
     cfg = _lib.RheConfig(device=0, n_indv=10, n_kept=10, pitch_bytes=100, n_cols_set=4, n_sets=1, n_ops=1, n_vec=2,
                          n_bins=1, max_block_snps=8, impute_binary=0, kernel_path=0)
     ctx = ctypes.c_void_p()
     assert lib.rhe_ctx_create(ctypes.byref(ctx), ctypes.byref(cfg)) == -1
     assert b"pitch_bytes" in lib.rhe_last_error()
+
+
+def test_tcgen05_capability_is_answered_by_the_library():
+    """The layout limits of the tensor kernels live in ONE place (rhe_tc_supported, also used by rhe_ctx_create): the
+    Python side asks instead of mirroring them.  Pure host arithmetic -- no device is touched."""
+    from pyrhe_b200 import _lib
+    from pyrhe_b200.assemble import PathPlan
+    assert _lib.tcgen05_supported(PathPlan(model="rhe", K=8, B=10, C=5))
+    assert _lib.tcgen05_supported(PathPlan(model="rhe_dom", K=8, B=10, C=5))
+    assert _lib.tcgen05_supported(PathPlan(model="genie", K=8, B=10, C=5))
+    assert _lib.tcgen05_supported(PathPlan(model="rhe", K=20, B=10, C=2))         # bin groups
+    # K = 2, B = 64: passes a naive TMEM-column count but not the shared-memory budget / vector-column limit
+    wide = PathPlan(model="rhe", K=2, B=64, C=0)
+    assert not _lib.tcgen05_supported(wide)
+    assert "exceed" in _lib.tcgen05_unsupported_reason(wide)
+    bad = _lib.plan_config(PathPlan(model="rhe", K=1, B=2, C=0), pitch_bytes=100)   # invalid config -> 0, not a crash
+    assert _lib.load().rhe_tc_supported(ctypes.byref(bad)) == 0
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_the_oracle():

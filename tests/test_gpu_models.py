@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from golden_cases import CASES
+from golden_cases import CASES, MODEL_CASES
 from helpers import case_dataset, load_golden
 from test_api_cpu import build_model
 
@@ -36,7 +36,7 @@ def run_case(name, streaming, tmp_path):
 
 
 @pytest.mark.parametrize("streaming", [False, True])
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(MODEL_CASES))
 def test_model_matches_reference(name, streaming, tmp_path):
     """Streaming classes are held to the NON-streaming reference."""
     g, model, log, results = run_case(name, streaming, tmp_path)

@@ -4,14 +4,14 @@ import numpy as np
 import pytest
 import scipy.linalg
 
-from golden_cases import CASES
+from golden_cases import CASES, SMALL_CASES
 from helpers import load_golden, oracle_problem
 from device_model import assemble_all
 from pyrhe_b200.assemble import PathPlan
 from pyrhe_b200.hostmath import host_terms, block_ranges
 
 pytestmark = pytest.mark.gpu
-SMALL = [n for n in CASES if n != "rhe_example_shape"]
+SMALL = list(SMALL_CASES)
 PATHS = [0]  # RHE_PATH_SIMT; the tcgen05 path is added in test_gpu_tcgen05.py
 
 

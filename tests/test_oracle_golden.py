@@ -3,10 +3,10 @@ import numpy as np
 import pytest
 import torch
 
-from golden_cases import CASES
+from golden_cases import CASES, SMALL_CASES
 from helpers import load_golden, oracle_problem
 
-SMALL = [n for n in CASES if n != "rhe_example_shape"]
+SMALL = list(SMALL_CASES)
 
 
 @pytest.fixture(autouse=True)

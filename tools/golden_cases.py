@@ -56,4 +56,57 @@ CASES = {
         data=dict(N=5000, M=10000, K=8, seed=41, n_cov=5),
         model="RHE", kwargs=dict(num_jack=100, num_random_vec=10, geno_impute_method="binary", seed=0),
         dump_state=False),
+    # ---- round 2: parity at BASELINE scale in N.  The reference itself runs these here in
+    # minutes when M is small; the committed files keep only T, q and the result dicts (no N-sized arrays).
+    # config 5 shape in N: 500k individuals, 8 bins, 5 covariates, B = 10, missing genotypes, binary imputation
+    "scale_rhe_500k": dict(
+        data=dict(N=500_000, M=800, K=8, seed=51, n_cov=5, missing_rate=0.002),
+        model="RHE", kwargs=dict(num_jack=4, num_random_vec=10, geno_impute_method="binary", seed=0),
+        dump_state=False, scale=True),
+    # configs 2 / 3 shape in N: 200k individuals, additive + dominance
+    "scale_dom_200k": dict(
+        data=dict(N=200_000, M=800, K=8, seed=52, n_cov=5, missing_rate=0.002),
+        model="RHE_DOM", kwargs=dict(num_jack=4, num_random_vec=10, geno_impute_method="binary", seed=0),
+        dump_state=False, scale=True),
+    # rare variants (UK-Biobank-style allele frequencies 1e-3 .. 0.05): stretches the per-column weight range
+    "scale_rhe_rare_100k": dict(
+        data=dict(N=100_000, M=800, K=4, seed=53, n_cov=3, missing_rate=0.001, maf_lo=0.001, maf_hi=0.05),
+        model="RHE", kwargs=dict(num_jack=4, num_random_vec=10, geno_impute_method="binary", seed=0),
+        dump_state=False, scale=True),
+    # GENIE G + GxE + NxE: the reference builds an N x N matrix for the NxE row (base.py:474), so 20k is what it can run
+    "scale_genie_20k": dict(
+        data=dict(N=20_000, M=800, K=8, seed=54, n_cov=5, with_env=True, missing_rate=0.002),
+        model="GENIE", kwargs=dict(num_jack=4, num_random_vec=10, geno_impute_method="binary", seed=0,
+                                   genie_model="G+GxE+NxE"),
+        dump_state=False, scale=True),
+    # config 4 shape in N (300k individuals): beyond what the reference can run for GENIE, so this one file comes from
+    # the CPU oracle (pinned to the reference by every other GENIE golden, including scale_genie_20k above)
+    "scale_genie_300k_oracle": dict(
+        data=dict(N=300_000, M=400, K=4, seed=55, n_cov=5, with_env=True, missing_rate=0.002),
+        model="GENIE", kwargs=dict(num_jack=2, num_random_vec=10, geno_impute_method="binary", seed=0,
+                                   genie_model="G+GxE+NxE"),
+        dump_state=False, scale=True, source="oracle"),
+    # ---- round 2: edge cases the reference handles (VERDICT r1 "untested reference edge cases")
+    # case/control phenotype with prevalences -> liability-scale lines (rhe.py:79-88; the reference calls the method by a
+    # name that does not exist, SURVEY.md §9.3 Q10: the worker aliases it to _compute_liability_h2, nothing else changes)
+    "rhe_binary_pheno": dict(
+        data=dict(N=400, M=600, K=2, seed=61, n_cov=2, binary_pheno=True),
+        model="RHE", kwargs=dict(num_jack=6, num_random_vec=5, geno_impute_method="mean", seed=8,
+                                 samp_prev=0.5, pop_prev=0.1),
+        dump_state=False),
+    # cov_impute_method="mean" (file_processing.py:139-146).  With NA cells present the reference cannot run: under
+    # pandas >= 3 its chained `fillna(inplace=True)` is a no-op (NaN reaches pinv), and under older pandas the imputed
+    # rows stay in the covariate matrix while their individuals are still dropped from the phenotype (shape mismatch,
+    # base.py:137-149).  The golden pins the keyword path on a complete file; NA cells are a product-only test.
+    "rhe_cov_mean_impute": dict(
+        data=dict(N=240, M=360, K=2, seed=62, n_cov=3),
+        model="RHE", kwargs=dict(num_jack=5, num_random_vec=4, geno_impute_method="binary", seed=10,
+                                 cov_impute_method="mean"),
+        dump_state=False),
 }
+
+# names by size class: the N-scale cases are GPU-only (tests/test_gpu_scale.py); `rhe_example_shape` is the reference's
+# example configuration (N = 5000, M = 10000, J = 100)
+SCALE_CASES = [n for n, c in CASES.items() if c.get("scale")]
+SMALL_CASES = [n for n, c in CASES.items() if not c.get("scale") and n != "rhe_example_shape"]
+MODEL_CASES = [n for n, c in CASES.items() if not c.get("scale")]

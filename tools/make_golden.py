@@ -35,7 +35,26 @@ def sha256_file(path):
     return h.hexdigest()
 
 
+def run_oracle_case(name, case, outdir):
+    """Cases the reference cannot run (GENIE at N >= 1e5 builds an N x N matrix): vectors from the CPU oracle, which
+    every reference-made golden pins.  Marked `source = "oracle"` in the file."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from oracle import rhe_oracle
+    p = helpers.oracle_problem(name, verify=False)
+    out = rhe_oracle.run(p)
+    _, paths = helpers.case_dataset(name, verify=False)
+    data = dict(T=out["T"][None], q=out["q"][None], M=out["M"], res_sigma_ests_total=out["sigma_total"][None],
+                res_sig_errs=out["sigma_se"][None], sigma_jack=out["sigma_jack"][None], source=np.array("oracle"),
+                bed_sha256=np.array(sha256_file(paths["geno_file"] + ".bed")),
+                case=np.array(json.dumps(dict(data=case["data"], model=case["model"], kwargs=case["kwargs"]))))
+    np.savez_compressed(os.path.join(outdir, name + ".npz"), **data)
+    print(f"{name} (oracle): T{data['T'].shape} sigma={out['sigma_total']}")
+
+
 def run_case(name, case, outdir):
+    if case.get("source") == "oracle":
+        return run_oracle_case(name, case, outdir)
     tmp = tempfile.mkdtemp(prefix=f"golden_{name}_")
     paths = make_dataset(tmp, name, **case["data"])
     spec = dict(model=case["model"], kwargs=case["kwargs"], paths=paths,
