@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--ring_blocks", type=int, default=4, help="distinct host blocks served cyclically in the e2e leg")
+    ap.add_argument("--e2e_source", default="pinned", choices=["pinned", "pageable"])
     ap.add_argument("--no_other_configs", action="store_true")
     ap.add_argument("--no_api_e2e", action="store_true")
     ap.add_argument("--api_workload", default="config2", choices=list(WORKLOADS))
@@ -397,20 +398,31 @@ def main():
     h2d_ceiling = None
     if not args.no_e2e:
         R = max(1, min(args.ring_blocks, len(eng.own)))
-        host = np.empty((R * eng.max_m, eng.row_bytes), dtype=np.uint8)
+        host = torch.empty((R * eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
         for r in range(R):
             rows, m = eng.block_view(eng.own[r])
-            host[r * eng.max_m: r * eng.max_m + m] = rows[:, : eng.row_bytes].cpu().numpy()
+            host[r * eng.max_m: r * eng.max_m + m].copy_(rows[:, : eng.row_bytes])
+        torch.cuda.synchronize(dev)
+        host_np = host.numpy()
 
         class CyclicRows:
-            """rows [a, b) of the rank's share -> the matching rows of the R-block host sample"""
+            """rows [a, b) of the rank's share -> the matching rows of the R-block host sample.  `--e2e_source pinned`
+            (default, the contract's "inputs in pinned host memory"): the sample is pinned and copied from where it
+            lies; `pageable`: plain host memory, every byte also crosses the staging threads' copy into the ring."""
             shape = (M, eng.row_bytes)
 
-            def __getitem__(self, sl):
-                a, b = sl.start, sl.stop
+            def _base(self, a):
                 j = min(a // (M // J), J - 1)
-                base = ((j - eng.own[0]) % R) * eng.max_m + (a - eng.ranges[j][0])
-                return host[base: base + (b - a)]
+                return ((j - eng.own[0]) % R) * eng.max_m + (a - eng.ranges[j][0])
+
+            def __getitem__(self, sl):
+                base = self._base(sl.start)
+                return host_np[base: base + (sl.stop - sl.start)]
+
+            if args.e2e_source == "pinned":
+                def pinned_rows(self, a, b):
+                    base = self._base(a)
+                    return host[base: base + (b - a)]
 
         h2d_total = M * eng.row_bytes + world * eng.R.numel() * 4      # all ranks: every .bed row once + the RHS per rank
         d2h_holder = {}
@@ -428,7 +440,8 @@ def main():
         ms_e2e /= n_e2e
         e2e = {"value": total_bytes / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_holder["n"]),
-               "host_sample_blocks": R, "staging_threads": streamer.n_workers,
+               "host_sample_blocks": R, "host_source": args.e2e_source,
+               "staging_threads": 0 if streamer.pinned_source else streamer.n_workers,
                "path": "RheEngine.stream_genotypes (host rows -> staging threads -> pinned ring -> H2D -> counts) + run"}
         streamer.close()
         # the node's pinned-H2D ceiling with all ranks copying at once (no staging, no kernels): what the link gives
@@ -448,7 +461,7 @@ def main():
         h2d_ceiling = {"aggregate_gbs": float(t.item()), "n_gpus": world,
                        "how": "8 x 1 GiB pinned->device copies per rank, all ranks concurrently, summed"}
         e2e["frac_of_h2d_ceiling"] = e2e["value"] / h2d_ceiling["aggregate_gbs"]
-        del pin, dst, host
+        del pin, dst, host, host_np
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

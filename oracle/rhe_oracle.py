@@ -29,6 +29,11 @@ import torch
 
 _CODE_TO_A2 = np.array([0.0, np.nan, 1.0, 2.0], dtype=np.float32)
 
+# Working precision of the block products.  float32 is the reference's (mat_mul.py:12 casts every operand);
+# `run(problem, f64=True)` repeats the same algorithm in float64 to measure how far the reference's own fp32
+# arithmetic sits from the exact answer (the yardstick for the parity tolerances).
+_DT = {"np": np.float32, "torch": torch.float32}
+
 
 # --------------------------------------------------------------------------- decode
 def decode_bed_rows(packed: np.ndarray, n_indv: int) -> np.ndarray:
@@ -41,7 +46,7 @@ def decode_bed_rows(packed: np.ndarray, n_indv: int) -> np.ndarray:
     codes = np.empty((m, packed.shape[1] * 4), dtype=np.uint8)
     for shift in range(4):
         codes[:, shift::4] = (packed >> (2 * shift)) & 3
-    return np.asfortranarray(_CODE_TO_A2[codes[:, :n_indv]].T)
+    return np.asfortranarray(_CODE_TO_A2.astype(_DT["np"])[codes[:, :n_indv]].T)
 
 
 def block_range(M: int, J: int, j: int):
@@ -84,7 +89,7 @@ def _t32(a):
     a = np.asarray(a)
     if not a.flags.writeable:
         a = a.copy(order="K")
-    return torch.from_numpy(a).float()
+    return torch.from_numpy(a).to(_DT["torch"])
 
 
 def mm(*mats) -> np.ndarray:
@@ -253,16 +258,16 @@ class Oracle:
             else:
                 # NxE row: X = diag(env).  The reference multiplies by a dense N x N matrix
                 # (base.py:474); with X diagonal each fp32 product reduces to env*(env*z).
-                env32 = self.p.env.astype(np.float32)
+                env32 = self.p.env.astype(_DT["np"])
                 for b in range(B):
-                    z32 = self.p.Z[:, b].astype(np.float32)
+                    z32 = self.p.Z[:, b].astype(_DT["np"])
                     self.XXz[e][J][b] = env32 * (env32 * z32)
-                v = (env32.reshape(-1, 1) * self._y_res().astype(np.float32))
+                v = (env32.reshape(-1, 1) * self._y_res().astype(_DT["np"]))
                 self.yXXy[e][J] = mm(v.T, v)[0][0]
                 if self.use_cov:                                        # Q8: only b = B-1 is filled
                     b = B - 1
                     self.UXXz[e][J][b] = self._uxxz(self.XXz[e][J][b])
-                    u32 = self.UZ[:, b].astype(np.float32)
+                    u32 = self.UZ[:, b].astype(_DT["np"])
                     self.XXUz[e][J][b] = env32 * (env32 * u32)
             for j in range(J):
                 for A in arrays:
@@ -330,10 +335,17 @@ def jackknife_se(ests: np.ndarray, J: int) -> np.ndarray:
     return np.sqrt((J - 1) * ((ests - mean) ** 2).sum(axis=0) / J)
 
 
-def run(problem: OracleProblem) -> dict:
-    o = Oracle(problem)
-    o.pre_compute()
-    T, q, sig = o.estimate()
+def run(problem: OracleProblem, f64: bool = False) -> dict:
+    """`f64=True`: the same algorithm with float64 block products (not the reference's arithmetic: a yardstick)."""
+    saved = dict(_DT)
+    if f64:
+        _DT.update(np=np.float64, torch=torch.float64)
+    try:
+        o = Oracle(problem)
+        o.pre_compute()
+        T, q, sig = o.estimate()
+    finally:
+        _DT.update(saved)
     out = dict(T=T, q=q, sigma_jack=sig[:-1], sigma_total=sig[-1],
                sigma_se=jackknife_se(sig[:-1], o.J), M=o.Mjk, XXz=o.XXz, yXXy=o.yXXy)
     if o.use_cov:

@@ -45,7 +45,9 @@ class BlockStreamer:
     """Bounded-memory, pipelined `.bed` ingest of one rank (base.py:338-345 reads one block at a time).
 
     host rows (numpy array / memmap of the `.bed` payload) --staging threads--> pinned ring --copy stream--> device slot
-    (+ the block's allele counts, `rhe_block_stats`, on the same stream).  One background thread drives the staging
+    (+ the block's allele counts, `rhe_block_stats`, on the same stream).  A source that already lives in pinned host
+    memory (it offers `pinned_rows(a, b)` -> pinned uint8 tensor [b - a, row_bytes]) is copied from where it lies,
+    without the staging hop.  One background thread drives the staging
     and queues the copies, so the caller's thread only enqueues kernels: staging of block n+1 overlaps the PCIe copy
     of block n and the kernels of block n-1.  When the engine holds a ring of R device slots, the copy of block n
     waits (on the device) for the kernels of block n-R, so HBM use is bounded by R blocks whatever the size of the
@@ -71,9 +73,12 @@ class BlockStreamer:
                 and packed.shape[1] == eng.row_bytes:
             self._fd = os.open(fname, os.O_RDONLY)
             self._file_off = int(packed.offset)
-        with torch.cuda.device(eng.device):
-            self.slots = [torch.empty((eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
-                          for _ in range(self.ring_host)]
+        self.pinned_source = hasattr(packed, "pinned_rows")
+        self.slots = []
+        if not self.pinned_source:
+            with torch.cuda.device(eng.device):
+                self.slots = [torch.empty((eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
+                              for _ in range(self.ring_host)]
         self.views = [sl.numpy() for sl in self.slots]
         self.thread = None
         self.errors = []
@@ -107,13 +112,17 @@ class BlockStreamer:
                     a, b = eng.ranges[j]
                     m = b - a
                     k = n % self.ring_host
-                    if slot_free[k] is not None:
-                        slot_free[k].synchronize()
-                    step = -(-m // self.n_workers)
-                    futs = [pool.submit(self._read_chunk, self.views[k][r0:min(m, r0 + step)], a + r0)
-                            for r0 in range(0, m, step)]
-                    for f in futs:
-                        f.result()
+                    if self.pinned_source:
+                        src = self.packed.pinned_rows(a, b)
+                    else:
+                        if slot_free[k] is not None:
+                            slot_free[k].synchronize()
+                        step = -(-m // self.n_workers)
+                        futs = [pool.submit(self._read_chunk, self.views[k][r0:min(m, r0 + step)], a + r0)
+                                for r0 in range(0, m, step)]
+                        for f in futs:
+                            f.result()
+                        src = self.slots[k][:m]
                     self.bytes_staged += m * eng.row_bytes
                     if R is not None and n >= R:               # the device slot still belongs to block n - R
                         prev = order[n - R]
@@ -121,7 +130,7 @@ class BlockStreamer:
                         if self.errors:
                             return
                         self.copy_stream.wait_event(self._done[prev])
-                    eng.upload_block(j, self.slots[k][:m], stream=self.copy_stream)
+                    eng.upload_block(j, src, stream=self.copy_stream)
                     ev = torch.cuda.Event()
                     ev.record(self.copy_stream)
                     self._events[j] = ev

@@ -75,10 +75,10 @@ def test_T_q_sigma_match_reference(name, path):
         np.testing.assert_allclose(q, g["q"][t], rtol=1e-5, atol=1e-6 * np.abs(g["q"][t]).max())
         sig = solve_all(T, q)
         vy = float(np.var(p.y))
-        np.testing.assert_allclose(sig[-1], g["res_sigma_ests_total"][t], rtol=1e-5, atol=2e-5 * vy)
+        np.testing.assert_allclose(sig[-1], g["res_sigma_ests_total"][t], rtol=1e-5, atol=1e-5 * vy)
         J = p.num_jack
         se = np.sqrt((J - 1) * ((sig[:-1] - sig[:-1].mean(0)) ** 2).sum(0) / J)
-        np.testing.assert_allclose(se, g["res_sig_errs"][t], rtol=1e-4, atol=2e-5 * vy)
+        np.testing.assert_allclose(se, g["res_sig_errs"][t], rtol=1e-4, atol=1e-5 * vy)
 
 
 @pytest.mark.parametrize("name", ["rhe_cov_binary", "dom_cov", "genie_full_cov"])

@@ -9,6 +9,10 @@ from test_gpu_parity import make_engine, plan_for, solve_all
 
 pytestmark = pytest.mark.gpu
 TC = 1
+# absolute floor of the sigma^2 / SE comparison in units of Var(y) for the N ~ 200 goldens (few hundred individuals:
+# every component is a small difference of O(N) traces, so fp32 block products move it by ~1e-6; the N-scale cases in
+# test_gpu_scale.py use the 1e-7 floor of SURVEY.md §9.2 plus the float64 yardstick)
+SIGMA_ATOL = 1e-5
 RHE_CASES = ["rhe_cov_binary", "rhe_nocov_mean", "rhe_overlap", "rhe_one_block", "rhe_example_shape",
              "genie_full_cov", "genie_full_nocov", "dom_cov", "dom_nocov"]
 
@@ -26,7 +30,19 @@ def test_tcgen05_T_q_sigma_match_reference(name):
         np.testing.assert_allclose(T, g["T"][t], rtol=1e-5, atol=1e-6 * np.abs(g["T"][t]).max())
         np.testing.assert_allclose(q, g["q"][t], rtol=1e-5, atol=1e-6 * np.abs(g["q"][t]).max())
         sig = solve_all(T, q)
-        np.testing.assert_allclose(sig[-1], g["res_sigma_ests_total"][t], rtol=1e-5, atol=2e-5 * float(np.var(p.y)))
+        vy = float(np.var(p.y))
+        ref = np.asarray(g["res_sigma_ests_total"][t])
+        J = p.num_jack
+        se = np.sqrt((J - 1) * ((sig[:-1] - sig[:-1].mean(0)) ** 2).sum(0) / J)
+        from test_gpu_scale import _record, _units
+        _record(f"{name}[trait {t}]", {
+            "source": "unmodified reference (tools/make_golden.py)", "N": int(p.Z.shape[0]), "M": int(p.annot.shape[0]),
+            "J": J, "kernel_path": "tcgen05", "var_y": vy,
+            "T_tol_units(rtol 1e-5, atol 1e-6 max|T|)": _units(T, g["T"][t], 1e-5, 1e-6 * np.abs(g["T"][t]).max()),
+            "sigma2_total_max_abs/var_y": float(np.max(np.abs(sig[-1] - ref)) / vy),
+            "se_max_abs/var_y": float(np.max(np.abs(se - g["res_sig_errs"][t])) / vy)})
+        np.testing.assert_allclose(sig[-1], ref, rtol=1e-5, atol=SIGMA_ATOL * vy)
+        np.testing.assert_allclose(se, g["res_sig_errs"][t], rtol=1e-4, atol=SIGMA_ATOL * vy)
 
 
 def test_tcgen05_vectors_match_simt_path():
