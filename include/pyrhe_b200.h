@@ -118,17 +118,30 @@ int rhe_block_plan_create(rhe_ctx* ctx, int32_t n_snps, const int32_t* bin_rows_
                           const int32_t* bin_offsets_host, void* stream, rhe_block_plan** out);
 int rhe_block_plan_destroy(rhe_ctx* ctx, rhe_block_plan* plan);
 
+/* Optional second layout of a resident block (tensor-core path): the INDIVIDUAL-MAJOR copy
+ *   gt   uint8 [Np / 128][n_pos / 512][128][128]   one contiguous 16 KB box per (128 individuals, 512 bin-sorted
+ *                                positions of the plan; every bin padded to 128 positions, the list to 512): row =
+ *                                individual, 2 bits per position, imputation applied, 16 positions per 32-bit word
+ * lets pass B (X (X^T Z), base.py:403-405) feed the tensor cores from tensor memory like pass A instead of staging every
+ * genotype through shared memory as a byte.  It doubles the genotype footprint, so the caller decides per
+ * block.  rhe_block_fast_bytes: size of the copy, 0 when the configuration / plan has no such path.
+ * rhe_block_transpose: builds it from the packed rows and their counts (ingest; depends on the imputation uniforms). */
+int64_t rhe_block_fast_bytes(const rhe_ctx* ctx, const rhe_block_plan* plan);
+int rhe_block_transpose(rhe_ctx* ctx, const uint8_t* bed_dev, const rhe_block_plan* plan,
+                        const int32_t* counts_dev, uint8_t* gt_dev, void* stream);
+
 /* rhe.py:13-22 / rhe_dom.py:43-68 / genie.py:46-82 for ONE jackknife block:
  *   plan             from rhe_block_plan_create (its n_snps rows start at bed_dev)
  *   counts_dev       int32 [n_snps][4] from rhe_block_stats on the same rows, or NULL (counted here: one more
  *                    read of the block)
+ *   gt_dev           the block's individual-major copy (rhe_block_transpose) or NULL (pass B gathers SNP rows)
  *   P_out_dev        float [E_reg][B][Np] or NULL   this block's X (X^T Z)
  *   S_accum_dev      float [E_reg][B][Np] or NULL   running totals (+=)
  *   gram_out_dev     double [E_reg][Rs][Rs]         overwritten
  * Enqueues kernels on `stream` only: no allocation, no host synchronisation. */
 int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, const rhe_block_plan* plan,
-                         const int32_t* counts_dev, float* P_out_dev, float* S_accum_dev,
-                         double* gram_out_dev, void* stream);
+                         const int32_t* counts_dev, const uint8_t* gt_dev, float* P_out_dev,
+                         float* S_accum_dev, double* gram_out_dev, void* stream);
 
 /* base.py:578-581 after aggregate (base.py:483-486): out[a][c] = sum (S_a - P_a)(S_c - P_c)
  * over `len` floats per estimate; P_dev may be NULL (totals).  out_dev double [n_est][n_est]. */

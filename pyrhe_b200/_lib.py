@@ -41,8 +41,10 @@ SIGNATURES = {
     "rhe_block_plan_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p,
                                         C.POINTER(C.c_void_p)]),
     "rhe_block_plan_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rhe_block_fast_bytes": (C.c_int64, [C.c_void_p, C.c_void_p]),
+    "rhe_block_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rhe_block_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.c_void_p, C.c_void_p]),
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "rhe_loo_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "rhe_loo_gram_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_void_p, C.c_int64, C.c_void_p]),

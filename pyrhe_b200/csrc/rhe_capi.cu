@@ -215,17 +215,9 @@ k_params_from_counts(const int32_t* __restrict__ counts, int m, int n_kept, int 
   for (int i = tid; i < n_wmax; i += nth) wmax[i] = 0u;
   for (int s = tid; s < m; s += nth) {
     const int4 c = reinterpret_cast<const int4*>(counts)[s];
-    int n1 = c.y, n2 = c.z, f = 0;
+    int n1 = c.y, n2 = c.z;
     const int nm = c.w;
-    if (binary) {
-      float mean32 = (float)((double)(n1 + 2 * n2) / (double)(n_kept - nm));
-      float p = __fmul_rn(mean32, 0.5f);
-      float om = __fsub_rn(1.0f, p);
-      float d0 = __fmul_rn(om, om);
-      float d1 = __fmul_rn(__fmul_rn(2.0f, p), om);
-      float u = (float)uniforms[s];
-      f = (u < d0) ? 0 : ((u < __fadd_rn(d0, d1)) ? 1 : 2);
-    }
+    const int f = rhe_fill_from_counts(n1, n2, nm, n_kept, binary, binary ? uniforms[s] : 0.0);
     if (f == 1) n1 += nm;
     if (f == 2) n2 += nm;
     fill[s] = (uint8_t)f;
@@ -928,13 +920,26 @@ extern "C" int rhe_block_plan_destroy(rhe_ctx* c, rhe_block_plan* p) {
   return RHE_OK;
 }
 
+extern "C" int64_t rhe_block_fast_bytes(const rhe_ctx* c, const rhe_block_plan* plan) {
+  if (!c || !plan || !c->tc) return 0;
+  return rhe_tc_gt_bytes(c, plan);
+}
+
+extern "C" int rhe_block_transpose(rhe_ctx* c, const uint8_t* bed, const rhe_block_plan* plan, const int32_t* counts,
+                                   uint8_t* gt, void* stream) {
+  if (!c || !bed || !plan || !counts || !gt) { rhe_set_error("rhe_block_transpose: NULL argument"); return RHE_ERR_INVALID; }
+  if (!c->tc) { rhe_set_error("rhe_block_transpose: the context runs the CUDA-core path"); return RHE_ERR_UNSUPPORTED; }
+  return rhe_tc_transpose(c, bed, plan, counts, gt, (cudaStream_t)stream);
+}
+
 extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, const rhe_block_plan* plan, const int32_t* counts_in,
-                                    float* P_out, float* S_accum, double* gram_out, void* stream) {
+                                    const uint8_t* gt, float* P_out, float* S_accum, double* gram_out, void* stream) {
   if (!plan) { rhe_set_error("rhe_block_accumulate: plan is NULL"); return RHE_ERR_INVALID; }
   const int m = plan->m;
   int rc = check_block(c, bed, m, "rhe_block_accumulate");
   if (rc) return rc;
   if (!gram_out) { rhe_set_error("rhe_block_accumulate: NULL argument"); return RHE_ERR_INVALID; }
+  if (gt && c->cfg.kernel_path != RHE_PATH_TCGEN05) { rhe_set_error("rhe_block_accumulate: the individual-major copy belongs to the tensor-core path"); return RHE_ERR_INVALID; }
   const int32_t* bin_rows = plan->bin_rows;
   const int32_t* s_off_dev = plan->off_dev;
   cudaStream_t st = (cudaStream_t)stream;
@@ -993,7 +998,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, const rhe_bl
   // ---- pass B
   if (P_out || S_accum) {
     if (g.kernel_path == RHE_PATH_TCGEN05) {
-      rc = rhe_tc_pass_b(c, bed, plan, P_out, S_accum, st);
+      rc = rhe_tc_pass_b(c, bed, gt, plan, P_out, S_accum, st);
       if (rc) return rc;
     } else {
       int BG = B <= 4 ? 4 : B <= 8 ? 8 : B <= 12 ? 12 : 16;

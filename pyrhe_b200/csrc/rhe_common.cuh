@@ -75,6 +75,20 @@ __device__ __forceinline__ int rhe_code_value(uint32_t code, int fill) {
   return code == 1u ? fill : (int)(code >> 1) + (int)(code == 3u);
 }
 
+// Imputation fill of one SNP from its allele counts {n0, n1, n2, n_miss}: "mean" fills 0 (base.py:287, Q4); "binary"
+// replays numpy's float32 arithmetic of base.py:265-285 bit for bit (round-to-nearest intrinsics, no FMA contraction)
+// with the uniform drawn for this block-local SNP.  Host specification: pyrhe_b200/hostmath.py:binary_fill_values.
+__device__ __forceinline__ int rhe_fill_from_counts(int n1, int n2, int nm, int n_kept, int binary, double uniform) {
+  if (!binary) return 0;
+  float mean32 = (float)((double)(n1 + 2 * n2) / (double)(n_kept - nm));
+  float p = __fmul_rn(mean32, 0.5f);
+  float om = __fsub_rn(1.0f, p);
+  float d0 = __fmul_rn(om, om);
+  float d1 = __fmul_rn(__fmul_rn(2.0f, p), om);
+  float u = (float)uniform;
+  return (u < d0) ? 0 : ((u < __fadd_rn(d0, d1)) ? 1 : 2);
+}
+
 static inline int rhe_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // tensor-core path entry points (rhe_tc.cu)
@@ -83,8 +97,11 @@ void rhe_tc_destroy(rhe_ctx* ctx);
 int rhe_tc_set_rhs(rhe_ctx* ctx, cudaStream_t st);
 int rhe_tc_pass_a(rhe_ctx* ctx, const uint8_t* bed, int m, cudaStream_t st);
 unsigned int* rhe_tc_wmax(rhe_ctx* ctx);   // per-column max |pass-B weight| (float bits), or NULL
-int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, const rhe_block_plan* plan, float* P_out, float* S_accum,
-                  cudaStream_t st);
+int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, const uint8_t* gt, const rhe_block_plan* plan, float* P_out,
+                  float* S_accum, cudaStream_t st);
+int64_t rhe_tc_gt_bytes(const rhe_ctx* ctx, const rhe_block_plan* plan);        // 0: no individual-major fast path
+int rhe_tc_transpose(rhe_ctx* ctx, const uint8_t* bed, const rhe_block_plan* plan, const int32_t* counts, uint8_t* gt,
+                     cudaStream_t st);
 int rhe_tc_plan_create(rhe_ctx* ctx, rhe_block_plan* plan, cudaStream_t st);   // may allocate and synchronise
 void rhe_tc_plan_destroy(rhe_block_plan* plan);
 int rhe_tc_check(const rhe_config* cfg, int quiet);                            // RHE_OK when the shapes fit the tcgen05 kernels

@@ -60,6 +60,7 @@ struct TcState {
   int32_t* pos_meta = nullptr;  // [SI][chunks][128][4] per-group decode metadata (SNP row | fill << 24 | mode << 26) of the current block
   unsigned int* wmax = nullptr; // [n_groups][B] max |weight| per weight group and column (float bits)
   int cap_pos = 0;
+  int n_sm = 148;               // SMs of the device (grid of the persistent kernel)
   CUtensorMap tm_rq, tm_uq;
   PFN_encodeTiled encode = nullptr;
 };
@@ -601,8 +602,11 @@ struct PbSmem {
 // W adjacent accumulator columns of the L limb rows (limb l sits `stride` columns further on) -> exact doubles
 template <int W>
 __device__ __forceinline__ void tmem_ldw(uint32_t taddr, int32_t (&v)[W]) {
-  static_assert(W == 2 || W == 8, "column chunk");
-  if constexpr (W == 2) {
+  static_assert(W == 2 || W == 4 || W == 8, "column chunk");
+  if constexpr (W == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+  } else if constexpr (W == 2) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
   } else {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -891,6 +895,417 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
   if (warp == PB_DW + 1) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
+// ------------------------------------------------------------------------------------------ pass B from TMEM (fast path)
+// The gather pass B above is bound by the shared-memory data pipe: every genotype is written to shared memory as a
+// byte and read back by the MMA.  When the block also has an INDIVIDUAL-MAJOR copy
+//     GT [Np / 128][n_ss][128][128 B]   one contiguous 16 KB box per (M-tile of 128 individuals, super-stage of 512
+//                         bin-sorted positions of the block's plan): row = individual, 2 bits per position, imputation
+//                         already applied (no missing code left), 16 positions per 32-bit word
+// the product D[i, n] = sum_s G[i, s] Uq[s, n] has the shape of pass A with the roles swapped: the TMEM lane is the
+// individual, K runs over positions, and the expanded A operand goes from registers straight into TENSOR MEMORY.
+// Only the small Uq tiles travel through shared memory.  GT is written once per resident block by k_tc_transpose
+// (ingest); it doubles the genotype footprint, so the engine keeps it for as many blocks as the HBM allows.
+//
+// Positions are bin-sorted, so a CTA (128 individuals, all positions) finishes bin k before it starts bin k + 1: the
+// accumulator of a bin lives in one of `n_acc` TMEM buffers of NC columns and is drained (scaled, written to P / S,
+// re-zeroed) by the drain warps while the next bin accumulates in the other buffer: n_acc NC + 10 A slots of TMEM
+// columns for any number of bins, and the epilogue overlaps the main loop.  The CTA is persistent: it walks the
+// M-tiles blockIdx.x, blockIdx.x + gridDim.x, ... and the sequence of sub-tiles, super-stages and bins simply
+// continues from one M-tile into the next, so rings and barriers never restart.
+// One persistent CTA per SM (992 threads, 64 registers): warps 0-19 decode (five groups of four, one TMEM lane quadrant
+// per warp), 20 TMA producer of the genotype boxes, 21 TMA producer of the Uq tiles, 22-26 MMA issue (one per decode
+// group), 27-30 drain (any four consecutive warps cover the four lane quadrants).  The decode loop is the spill-free
+// loop of pass A; the drains never touch it.  The two rings are fed independently: the genotype ring must run several
+// super-stages ahead of the decode front (about 2.5 stages are being consumed at any time and HBM latency is ~2 us), while
+// a Uq slot only frees up when its MMAs have completed.
+#define P2_G 5
+#define P2_DW (4 * P2_G)
+#define P2_W_PROD P2_DW
+#define P2_W_PRODU (P2_DW + 1)
+#define P2_W_MMA (P2_DW + 2)
+#define P2_W_DRAIN (P2_DW + 2 + P2_G)
+#define P2_THREADS (32 * (P2_W_DRAIN + 4))
+#define P2_AS (2 * P2_G)          // TMEM A slots (32 columns each): two per group
+#define P2_MAXRING 8
+
+struct P2Smem {
+  uint64_t full_a[P2_AS], empty_a[P2_AS], full_u[P2_MAXRING], empty_u[P2_MAXRING], full_g[P2_MAXRING], empty_g[P2_MAXRING];
+  uint64_t bin_full[2], acc_free[2];
+  uint32_t tmem_base;
+  double cs[PB_MAX_KB];           // per-(weight group, bin, column) mean term
+  double dq[64];                  // per-(weight group, column) dequantisation factor 2^(e - F)
+  int32_t cnt[256];               // rows per bin
+};
+
+__device__ __forceinline__ bool mbar_test_s(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ double lds_f64_nv(uint32_t addr) {     // not volatile: the scheduler may hoist and overlap these
+  double r;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
+  return r;
+}
+
+// Drain the accumulator of virtual bin v = mode * K + k for this thread's individual (TMEM lane): the same arithmetic
+// as pb_epilogue.  mode 0 writes P (and subtracts the per-bin mean term), mode 1 (the [g == 2] operand of RHE-DOM)
+// adds to what mode 0 wrote -- the same thread drains both modes of a bin, so the read-modify-write is ordered.
+// The four drain warps are the serial resource of the kernel (one bin after the other, 128 lanes x B values each), so
+// the path is kept short: all limb rows of a weight group are read with as few tcgen05.ld as possible and ONE wait,
+// the accumulator buffer is zeroed and handed back to the MMA issuers (`release`) as soon as the last values are in
+// registers, and only then come the conversions and the stores; limbs are recombined in int64 (one conversion per value).
+// One chunk of W adjacent columns of a non-empty bin.  `p` / `s` point at this individual's entry of the chunk's first
+// column in P / S (nullptr: not wanted); successive columns are `Np` floats apart.  The drain warps are the serial
+// resource of the kernel, so the code per value is kept to the conversions, the limb recombination (exact in fp64),
+// scale, mean term, row scale, one store and one RED.
+template <int L, int W, int MODE>
+__device__ __forceinline__ void p2_drain_chunk(uint32_t taddr, int stride, int nvalid, size_t Np, double rs, uint32_t dq_a,
+                                               uint32_t cs_a, float* __restrict__ p, float* __restrict__ s, int dbg) {
+  int32_t a[L][W];
+  if (RHE_DBG(2)) {
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int j = 0; j < W; ++j) a[l][j] = (int)taddr + j;
+  } else {
+#pragma unroll
+    for (int l = 0; l < L; ++l) tmem_ldw<W>(taddr + (uint32_t)(l * stride), a[l]);
+    tmem_ld_wait();
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    if (j < nvalid) {
+      double val = (double)a[L - 1][j];
+#pragma unroll
+      for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
+      const double dq = lds_f64_nv(dq_a + 8u * (uint32_t)j);
+      float xf;
+      if (MODE == 0) xf = (float)(rs * (val * dq - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
+      else xf = (float)(rs * (val * dq));             // gather kernel: float(rs (dq (D0 + D1) - cs)); here two roundings
+      if (RHE_DBG(1)) { if (xf == 1.2345f && p) *p = xf; continue; }
+      if (p) { if (MODE == 0) *p = xf; else *p += xf; p += Np; }
+      if (s && !RHE_DBG(4)) { atomicAdd(s, xf); s += Np; }            // result unused -> RED
+    }
+  }
+}
+
+// Drain the accumulator of virtual bin v = mode * K + k for this thread's individual (TMEM lane): the same arithmetic
+// as pb_epilogue.  mode 0 writes P (and subtracts the per-bin mean term), mode 1 (the [g == 2] operand of RHE-DOM)
+// adds to what mode 0 wrote -- the same thread drains both modes of a bin, so the read-modify-write is ordered.
+template <int L, int MODE>
+__device__ __forceinline__ void p2_drain(uint32_t tcol, int k, int i, int K, int WG, int B, int Bp, size_t Np,
+                                         const double* dq_s, const double* cs_s, const float (&rsv)[2],
+                                         float* __restrict__ P_out, float* __restrict__ S_accum, int dbg) {
+  for (int wg = 0; wg < WG; ++wg) {                    // four columns per tcgen05.ld, the remainder in pairs
+    const uint32_t base = tcol + (uint32_t)(wg * L * Bp);
+    const double rs = (double)(wg ? rsv[1] : rsv[0]);  // row scale of this individual: loaded once per M-tile, not per bin
+    uint32_t dq_a = smem_u32(dq_s + wg * B), cs_a = smem_u32(cs_s + (wg * K + k) * B);
+    const size_t o = (size_t)(wg * K + k) * B * Np + i;
+    float* p = P_out ? P_out + o : nullptr;
+    float* s = S_accum ? S_accum + o : nullptr;
+    int c0 = 0;
+    for (; c0 + 4 <= Bp; c0 += 4) {
+      p2_drain_chunk<L, 4, MODE>(base + (uint32_t)c0, Bp, B - c0, Np, rs, dq_a, cs_a, p, s, dbg);
+      dq_a += 32u; cs_a += 32u;
+      if (p) p += 4 * Np;
+      if (s) s += 4 * Np;
+    }
+    for (; c0 < Bp; c0 += 2) {
+      p2_drain_chunk<L, 2, MODE>(base + (uint32_t)c0, Bp, B - c0, Np, rs, dq_a, cs_a, p, s, dbg);
+      dq_a += 16u; cs_a += 16u;
+      if (p) p += 2 * Np;
+      if (s) s += 2 * Np;
+    }
+  }
+}
+
+// Sub-tile j = 128 positions of one M-tile; super-stage k = 4 sub-tiles = one TMA box of GT (128 individuals x 128 B) +
+// four Uq tiles; n_ss super-stages per mode, n_modes modes (RHE-DOM walks the positions twice: count operand, then
+// [g == 2] operand; both use the same GT bytes).  Capital letters below are indices of the CTA's whole run: J = it n_sub + j.
+template <int GS, int US>
+__global__ void __launch_bounds__(P2_THREADS, 1)
+k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ CUtensorMap tm_gt, int n_mt, int Np, int n_ss,
+             int n_modes, const int32_t* __restrict__ stage_info, const int32_t* __restrict__ bin_count, int K, int WG,
+             int B, int Bp, int L, int NC, int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
+             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
+             uint32_t tmem_cols, uint32_t col_a, int n_acc, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int acc_stride = (NC + 31) & ~31;            // TMEM columns per accumulator buffer (zeroed 32 columns at a time)
+  uint8_t* packed = smem;                            // [GS][128 individuals][128 B], 128-byte swizzle
+  uint8_t* tileU = packed + GS * PA_PACKED;          // [US][4][NC][128 B]
+  const int tileU_bytes = NC * 128;
+  P2Smem* sm = reinterpret_cast<P2Smem*>(tileU + US * 4 * tileU_bytes);
+  const uint32_t packed_s = smem_u32(packed);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+  const int n_it = n_mt > (int)blockIdx.x ? (n_mt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // own M-tiles
+  const int total_ss = n_ss * n_modes, n_sub = 4 * total_ss, V = n_modes * K;
+  const int N_sub = n_it * n_sub;                    // sub-tiles of the whole run
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P2_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
+    for (int s = 0; s < P2_MAXRING; ++s) {
+      mbar_init(&sm->full_u[s], 1); mbar_init(&sm->empty_u[s], 4);      // 4 sub-tiles
+      mbar_init(&sm->full_g[s], 1); mbar_init(&sm->empty_g[s], 16);     // 4 sub-tiles x 4 warps
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm->bin_full[s], P2_G); mbar_init(&sm->acc_free[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == P2_W_PROD) tmem_alloc(&sm->tmem_base, tmem_cols);
+  for (int i = threadIdx.x; i < WG * K * B; i += P2_THREADS) sm->cs[i] = cs[i];
+  for (int i = threadIdx.x; i < K; i += P2_THREADS) sm->cnt[i] = bin_count[i];
+  for (int i = threadIdx.x; i < WG * B; i += P2_THREADS) {
+    const int ex = (int)((wmax[i] >> 23) & 255u);       // same rule as k_tc_quant_w / the gather kernel
+    sm->dq[i] = ex == 255 ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex - 126 - F);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  if (warp < 4)                                        // zero the accumulator buffers (lane quadrant per warp)
+    for (uint32_t c = 0; c < col_a; c += 32) tmem_zero32(tmem + ((uint32_t)(warp * 32) << 16) + c);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp < P2_DW) {
+    const int t = (warp & 3) * 32 + lane, g = warp >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t row_s = packed_s + (uint32_t)t * 128;      // this thread's individual inside a staged box
+    const uint32_t sw = (uint32_t)(t & 7);                      // 128-byte swizzle: 16-byte chunk c sits at c ^ (row & 7)
+    const int n_own = N_sub > g ? (N_sub - g + P2_G - 1) / P2_G : 0;     // own sub-tiles J = g + P2_G * jj
+    // packed words of sub-tile J = 4 Kg + q: chunks 2 q, 2 q + 1 of the row in ring slot Kg % GS
+    auto fetch = [&](int J, uint4& lo, uint4& hi) {
+      const int k = J >> 2, q = J & 3, sg = k % GS;
+      mbar_wait(&sm->full_g[sg], (uint32_t)(k / GS) & 1u);
+      const uint32_t base = row_s + (uint32_t)sg * PA_PACKED;
+      lo = lds128(base + (((uint32_t)(2 * q) ^ sw) << 4));
+      hi = lds128(base + (((uint32_t)(2 * q + 1) ^ sw) << 4));
+    };
+    // Same software pipeline as pass A: the packed words of the next sub-tile are read from the ring before the current
+    // one is expanded, each sub-tile goes to TMEM as two 16-column stores, one barrier arrival per warp.
+    auto put = [&](uint32_t slot_a, uint32_t parity, const uint4& lo, const uint4& hi, int k, uint32_t tab) {
+      uint4 r[4];
+      mbar_wait(&sm->empty_a[slot_a], parity ^ 1u);
+      tc_fence_after();
+      const uint32_t dst = lane_base + col_a + 32u * slot_a;
+      r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
+      tmem_st16(dst, r);
+      uint4 r2[4];
+      r2[0] = tc_expand(hi.x, tab); r2[1] = tc_expand(hi.y, tab); r2[2] = tc_expand(hi.z, tab); r2[3] = tc_expand(hi.w, tab);
+      tmem_st16(dst + 16, r2);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();                                    // every lane's stores are complete and fenced: one arrival per warp
+      if (lane == 0) { mbar_arrive(&sm->empty_g[k % GS]); mbar_arrive(&sm->full_a[slot_a]); }
+    };
+    // the GT bytes carry no missing code (imputation is applied at ingest): a constant value table per operand
+    const uint32_t tab0 = tc_value_table(0u, 0), tab1 = tc_value_table(0u, 1);
+    const int half = n_modes == 2 ? n_sub >> 1 : n_sub;       // sub-tiles [half, n_sub) of an M-tile use the [g == 2] operand
+    int jm = g % n_sub;                                       // J mod n_sub of the current sub-tile
+    uint4 lo, hi;
+    if (n_own > 0) fetch(g, lo, hi);
+    for (int jj = 0; jj < n_own; ++jj) {
+      const int J = g + P2_G * jj;
+      uint4 nlo = lo, nhi = hi;
+      if (jj + 1 < n_own) fetch(J + P2_G, nlo, nhi);
+      put((uint32_t)(2 * g + (jj & 1)), (uint32_t)(jj >> 1) & 1u, lo, hi, J >> 2, jm >= half ? tab1 : tab0);
+      lo = nlo;
+      hi = nhi;
+      jm += P2_G;
+      while (jm >= n_sub) jm -= n_sub;
+    }
+    tc_fence_before();
+  } else if (warp == P2_W_PROD) {
+    // TMA producer 1: the genotype box of every super-stage (positions 512 kk .. of the M-tile's 128 individuals) -> ring
+    // slot Kg % GS, as far ahead of the decode front as the ring allows.
+    const uint32_t fg = smem_u32(&sm->full_g[0]), eg = smem_u32(&sm->empty_g[0]);
+    uint32_t gsl = 0, gpar = 1;
+    for (int it = 0; it < n_it; ++it) {
+      const int mt = (int)blockIdx.x + it * (int)gridDim.x;
+      int kk = 0;                                      // super-stage inside the mode
+      for (int k = 0; k < total_ss; ++k) {             // the whole warp runs the loop; one elected lane issues
+        mbar_wait_s(eg + 8u * gsl, gpar);
+        if (elect_one()) {
+          mbar_expect_tx_s(fg + 8u * gsl, PA_PACKED);
+          tma_load_2d_s(packed_s + gsl * PA_PACKED, &tm_gt, fg + 8u * gsl, 0, (mt * n_ss + kk) * 128);
+        }
+        __syncwarp();
+        if (++gsl == (uint32_t)GS) { gsl = 0; gpar ^= 1u; }
+        if (++kk == n_ss) kk = 0;
+      }
+    }
+  } else if (warp == P2_W_PRODU) {
+    // TMA producer 2: the four Uq tiles of every super-stage -> ring slot Kg % US (the same tiles for every M-tile: L2 hits)
+    const uint32_t fu = smem_u32(&sm->full_u[0]), eu = smem_u32(&sm->empty_u[0]);
+    const uint32_t tileU_s = smem_u32(tileU);
+    uint32_t usl = 0, upar = 1;
+    for (int it = 0; it < n_it; ++it) {
+      for (int k = 0; k < total_ss; ++k) {
+        mbar_wait_s(eu + 8u * usl, upar);
+        if (elect_one()) {
+          mbar_expect_tx_s(fu + 8u * usl, 4u * (uint32_t)tileU_bytes);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            tma_load_2d_s(tileU_s + (usl * 4u + (uint32_t)q) * (uint32_t)tileU_bytes, &tm_uq, fu + 8u * usl, (4 * k + q) * 128, 0);
+        }
+        __syncwarp();
+        if (++usl == (uint32_t)US) { usl = 0; upar ^= 1u; }
+      }
+    }
+  } else if (warp < P2_W_DRAIN) {
+    // ---- MMA issue: one warp per decode group.  Every issuer walks ALL virtual bins of the run in order (bin v of M-tile
+    // `it` is Vg = it V + v) -- enter (wait until the bin's accumulator buffer has been drained of the bin n_acc before
+    // it), issue its own sub-tiles of the bin, leave (commit: the buffer's bin_full barrier counts the issuers) -- so no
+    // barrier ever sees arrivals of two phases.
+    const int g = warp - P2_W_MMA;
+    const uint32_t idesc = idesc_i8(128, NC, 0);
+    const uint32_t fu = smem_u32(&sm->full_u[0]), eu = smem_u32(&sm->empty_u[0]);
+    const uint32_t fa = smem_u32(&sm->full_a[2 * g]), ea = smem_u32(&sm->empty_a[2 * g]);
+    const uint32_t bfull = smem_u32(&sm->bin_full[0]), afree = smem_u32(&sm->acc_free[0]);
+    const uint64_t bdesc0 = smem_desc_sw128(smem_u32(tileU), 16, 1024);
+    const int n_own = N_sub > g ? (N_sub - g + P2_G - 1) / P2_G : 0;
+    const int V_all = n_it * V, sh = n_acc - 1;          // n_acc is 1 or 2: Vg % n_acc = Vg & sh, Vg / n_acc = Vg >> sh
+    uint32_t ph_a = 0, q = 0;
+    int cur_v = 0;
+    auto enter = [&](int v) {                          // buffer v % n_acc must have been drained of bin v - n_acc
+      if (v >= n_acc) mbar_wait_s(afree + 8u * (uint32_t)(v & sh), (uint32_t)((v >> sh) - 1) & 1u);
+      tc_fence_after();
+    };
+    auto leave = [&](int v) {
+      if (elect_one()) umma_commit_s(bfull + 8u * (uint32_t)(v & sh));
+      __syncwarp();
+    };
+    if (V_all > 0) enter(0);
+    int jm = g % n_sub, vbase = 0;                       // J mod n_sub and it * V of the current sub-tile
+    for (int x = g; x >= n_sub; x -= n_sub) vbase += V;  // (g < n_sub unless the M-tile has a single super-stage)
+    uint32_t info_next = n_own > 0 ? (uint32_t)__ldg(stage_info + jm) : 0u;     // one sub-tile ahead, straight from L2
+    for (int jj = 0; jj < n_own; ++jj) {
+      const int J = g + P2_G * jj, k = J >> 2;
+      const uint32_t info = info_next;                           // stage_info holds n_modes copies of the per-mode list
+      const int v = vbase + (jm >= (n_modes == 2 ? n_sub >> 1 : n_sub) ? K : 0) + (int)(info & 255u);
+      const int ksteps = (int)(info >> 16);
+      jm += P2_G;
+      while (jm >= n_sub) { jm -= n_sub; vbase += V; }
+      if (jj + 1 < n_own) info_next = (uint32_t)__ldg(stage_info + jm);
+      while (cur_v < v) { leave(cur_v); ++cur_v; enter(cur_v); }
+      const uint32_t u_slot = (uint32_t)(k % US);
+      mbar_wait_s(fu + 8u * u_slot, (uint32_t)(k / US) & 1u);
+      mbar_wait_s(fa + 8u * q, ph_a);
+      tc_fence_after();
+      const uint64_t bdesc = bdesc0 + (uint64_t)((u_slot * 4u + ((uint32_t)J & 3u)) * (uint32_t)(tileU_bytes >> 4));
+      const uint32_t acol = tmem + col_a + 32u * (2u * (uint32_t)g + q);
+      const uint32_t dcol = tmem + (uint32_t)((v & sh) * acc_stride);
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)   // K = 32 positions per instruction: 8 TMEM columns / 32 bytes of the Uq row
+          if (i < ksteps) umma_i8_ts(dcol, acol + 8u * i, bdesc + (uint64_t)(i * 2), idesc, 1u);
+        umma_commit_s(ea + 8u * q);
+        umma_commit_s(eu + 8u * u_slot);
+      }
+      __syncwarp();
+      q ^= 1u;
+      if (q == 0u) ph_a ^= 1u;
+    }
+    while (cur_v < V_all) { leave(cur_v); ++cur_v; if (cur_v < V_all) enter(cur_v); }
+  } else {
+    // ---- drain warps (TMEM lane quadrant = warp & 3): bin after bin, in sequence order.  The same four warps drain every
+    // bin, so each accumulator buffer's barriers advance one phase per use and a parity wait is never ambiguous.
+    const int t = (warp & 3) * 32 + lane, sh = n_acc - 1;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t bfull = smem_u32(&sm->bin_full[0]), afree = smem_u32(&sm->acc_free[0]);
+    int Vg = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int i = ((int)blockIdx.x + it * (int)gridDim.x) * 128 + t;
+      const float rsv[2] = {rowscale[i], WG > 1 ? rowscale[(size_t)rs_stride + i] : 0.f};
+      for (int v = 0; v < V; ++v, ++Vg) {
+        const int mode = v >= K ? 1 : 0, k = v - mode * K, buf = Vg & sh;
+        mbar_wait_s(bfull + 8u * (uint32_t)buf, (uint32_t)(Vg >> sh) & 1u);
+        tc_fence_after();
+        const bool has = sm->cnt[k] > 0;
+        const uint32_t tcol = lane_base + (uint32_t)(buf * acc_stride);
+        if (has) {
+          if (mode == 0) {
+            if (L == 3) p2_drain<3, 0>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
+            else if (L == 2) p2_drain<2, 0>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
+            else p2_drain<4, 0>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
+          } else {
+            if (L == 3) p2_drain<3, 1>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
+            else if (L == 2) p2_drain<2, 1>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
+            else p2_drain<4, 1>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
+          }
+          for (int c = 0; c < acc_stride; c += 32) tmem_zero32(tcol + (uint32_t)c);
+        } else if (mode == 0 && P_out) {                 // a bin without SNPs in this block: X (X^T Z) = 0
+          for (int wg = 0; wg < WG; ++wg)
+            for (int b = 0; b < B; ++b) P_out[((size_t)(wg * K + k) * B + b) * Np + i] = 0.f;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(afree + 8u * (uint32_t)buf);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == P2_W_PROD) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
+}
+
+// Individual-major copy of one block (ingest): GT[i][p] = imputed 2-bit code of bin-sorted position p for individual i.
+// Word w of a row holds positions 16 w .. 16 w + 15 with position 16 w + x in field tc_perm16-inverse order, so that the
+// byte order tc_expand produces is the natural position order of the Uq tiles.  Tile = 128 positions x 512 individuals.
+__global__ void __launch_bounds__(256)
+k_tc_transpose(const uint8_t* __restrict__ bed, int pitch, const int32_t* __restrict__ pos_rows,
+               const int32_t* __restrict__ counts, int n_kept, int binary, const double* __restrict__ uniforms,
+               uint8_t* __restrict__ gt, int n_ss) {
+  __shared__ uint32_t tile[128][33];
+  __shared__ uint32_t outw[512][9];
+  __shared__ uint8_t fcode[128];
+  const int st = blockIdx.y, i0 = blockIdx.x * 512;
+  for (int idx = threadIdx.x; idx < 128 * 32; idx += 256) {
+    const int r = idx >> 5, w = idx & 31;
+    const int row = pos_rows[st * 128 + r];
+    tile[r][w] = row >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(bed + (size_t)row * pitch + (i0 >> 2)) + w) : 0u;
+  }
+  if (threadIdx.x < 128) {
+    const int row = pos_rows[st * 128 + threadIdx.x];
+    int code = 0;
+    if (row >= 0) {
+      const int4 c = reinterpret_cast<const int4*>(counts)[row];
+      const int f = rhe_fill_from_counts(c.y, c.z, c.w, n_kept, binary, binary ? uniforms[row] : 0.0);
+      code = f == 0 ? 0 : (f == 1 ? 2 : 3);           // A2 count -> PLINK code (00, 10, 11)
+    }
+    fcode[threadIdx.x] = (uint8_t)code;
+  }
+  __syncthreads();
+  for (int it = 0; it < 16; ++it) {
+    const int idx = threadIdx.x + 256 * it;            // lanes = consecutive individuals, warp-uniform position group
+    const int i = idx & 511, pg = idx >> 9;
+    const int wsrc = i >> 4, sh = 2 * (i & 15);
+    uint32_t out = 0;
+#pragma unroll
+    for (int f = 0; f < 16; ++f) {
+      const int p = 16 * pg + tc_invperm16(f);
+      uint32_t code = (tile[p][wsrc] >> sh) & 3u;
+      if (code == 1u) code = fcode[p];
+      out |= code << (2 * f);
+    }
+    outw[i][pg] = out;
+  }
+  __syncthreads();
+  for (int it = 0; it < 16; ++it) {
+    const int idx = threadIdx.x + 256 * it;            // 8 consecutive lanes = one individual's 32-byte sector
+    const int i = idx >> 3, pg = idx & 7;
+    // box (M-tile, super-stage) = 128 individuals x 128 B, contiguous: [mtile][ss][row][q * 32 + pg * 4]
+    const size_t box = (size_t)((i0 + i) >> 7) * n_ss + (size_t)(st >> 2);
+    *reinterpret_cast<uint32_t*>(gt + (box * 128 + (size_t)((i0 + i) & 127)) * 128 + (size_t)((st & 3) * 32 + pg * 4)) = outw[i][pg];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ quantisation kernels
 // Balanced base-256 digits of a signed integer: q = sum_l d_l 256^l, d_l in [-128, 127].
 __device__ __forceinline__ void tc_limbs(long long q, int L, int8_t* out, size_t stride) {
@@ -1003,6 +1418,10 @@ static inline int pb_ring(int nc, int mt, int G, int* bzsh) {
   return bs;
 }
 
+struct P2Shape;
+static bool p2_shape(const TcState* s, P2Shape* o);
+static int p2_smem_of(const TcState* s);
+
 // Shape plan of the tensor kernels for one configuration (pure host arithmetic: shared by rhe_tc_supported and
 // rhe_tc_create so that the Python side never has to mirror the limits).
 struct TcShape { int L, F, R1p, NBa, Bp, NCb, MT, G, KG; };
@@ -1079,6 +1498,7 @@ int rhe_tc_create(rhe_ctx* c) {
     return RHE_ERR_CUDA;
   }
   s->encode = (PFN_encodeTiled)fn;
+  cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, c->cfg.device);
   c->tc = s;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
@@ -1091,7 +1511,7 @@ int rhe_tc_create(rhe_ctx* c) {
   // pass-B staging for the largest block of a one-bin-per-SNP annotation (every bin padded to 128 rows); plans with
   // overlapping annotations grow it at plan creation
   const int kg = s->KG < g.n_bins ? s->KG : g.n_bins;
-  rc = tc_reserve_positions(c, s, g.n_ops * (round_up(g.max_block_snps, 128) + 128 * kg));
+  rc = tc_reserve_positions(c, s, g.n_ops * (round_up(g.max_block_snps, 128) + 128 * kg + 512));
   if (rc) return rc;
   RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa)));
   {
@@ -1100,6 +1520,11 @@ int rhe_tc_create(rhe_ctx* c) {
     if (s->G == 2) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else if (s->MT == 2) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  if (p2_smem_of(s) > 0) {
+    RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b2<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2_smem_of(s)));
+    RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b2<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2_smem_of(s)));
+    RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_b2<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2_smem_of(s)));
   }
   return RHE_OK;
 }
@@ -1173,9 +1598,13 @@ static int tc_block_meta(rhe_ctx* c, const rhe_block_plan* plan, int k0, int kn,
   TcBlockMeta& b = *out;
   b.k0 = k0;
   b.kn = kn;
-  b.n_pos = pstart[kn];
+  // the list ends on a super-stage boundary (512 positions = one 128-byte TMA box of the individual-major copy): up
+  // to three empty tail stages (no rows, no K-steps) that belong to the last bin
+  b.n_pos = round_up(pstart[kn], 512);
+  for (int p = pstart[kn]; p < b.n_pos; p += 128) info.push_back((kn - 1) | (0 << 8) | (0 << 16));
   const int n_alloc = b.n_pos > 0 ? b.n_pos : 128;
   RHE_CUDA(cudaMalloc((void**)&b.pos_rows, sizeof(int32_t) * n_alloc));
+  RHE_CUDA(cudaMemsetAsync(b.pos_rows, 0xFF, sizeof(int32_t) * n_alloc, st));      // -1 = padding
   const int n_modes = c->cfg.n_ops;                  // RHE-DOM runs the position list twice (count, then [g == 2] operand)
   {
     const size_t one = info.size();
@@ -1264,10 +1693,93 @@ static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, co
   return RHE_OK;
 }
 
-int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, const rhe_block_plan* plan, float* P_out, float* S_accum, cudaStream_t st) {
+// ---- individual-major fast path (k_tc_pass_b2): shapes, ingest, launch
+struct P2Shape { int n_acc, gs, us, smem; uint32_t col_a, cols; };
+
+static bool p2_shape(const TcState* s, P2Shape* o) {
+  if (s->NCb > 96) return false;
+  o->n_acc = 2;
+  o->col_a = (uint32_t)(o->n_acc * round_up(s->NCb, 32));
+  o->cols = pow2_cols((int)o->col_a + 32 * P2_AS);
+  if (o->cols > 512) return false;
+  const int budget = 232448 - 2048;                    // one CTA per SM
+  const int rings[3][2] = {{8, 4}, {6, 3}, {4, 2}};    // depth of the genotype-box ring / of the Uq super-stage ring
+  for (const auto& r : rings) {
+    const int smem = r[0] * PA_PACKED + r[1] * 4 * s->NCb * 128 + (int)sizeof(P2Smem) + 1024;
+    if (smem <= budget) { o->gs = r[0]; o->us = r[1]; o->smem = smem; return true; }
+  }
+  return false;
+}
+
+static int p2_smem_of(const TcState* s) {
+  P2Shape sh;
+  return p2_shape(s, &sh) ? sh.smem : 0;
+}
+
+// Bytes of the individual-major copy of the plan's block (0: this configuration / plan has no fast path and pass B
+// gathers from the SNP-major rows).  The copy exists only for plans whose bins form one group.
+int64_t rhe_tc_gt_bytes(const rhe_ctx* c, const rhe_block_plan* plan) {
+  const TcState* s = (const TcState*)c->tc;
+  const TcPlan* tp = (const TcPlan*)plan->tc;
+  P2Shape sh;
+  if (!s || !tp || tp->groups.size() != 1 || tp->groups[0].n_pos <= 0 || !p2_shape(s, &sh)) return 0;
+  return (int64_t)c->Np * (tp->groups[0].n_pos / 4);
+}
+
+int rhe_tc_transpose(rhe_ctx* c, const uint8_t* bed, const rhe_block_plan* plan, const int32_t* counts, uint8_t* gt, cudaStream_t st) {
+  const TcPlan* tp = (const TcPlan*)plan->tc;
+  if (rhe_tc_gt_bytes(c, plan) == 0) { rhe_set_error("rhe_block_transpose: this plan has no individual-major fast path"); return RHE_ERR_UNSUPPORTED; }
+  const TcBlockMeta& meta = tp->groups[0];
+  const rhe_config& g = c->cfg;
+  if (g.impute_binary && (!c->uniforms || c->n_uniforms < plan->m)) { rhe_set_error("binary imputation needs rhe_set_uniforms first"); return RHE_ERR_STATE; }
+  k_tc_transpose<<<dim3(c->Np / 512, meta.n_pos / 128), 256, 0, st>>>(bed, g.pitch_bytes, meta.pos_rows, counts, g.n_kept,
+                                                                     g.impute_binary, c->uniforms, gt, meta.n_pos / 512);
+  RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
+static int tc_pass_b2(rhe_ctx* c, TcState* s, const uint8_t* gt, int m, const TcBlockMeta* meta, float* P_out, float* S_accum,
+                      cudaStream_t st) {
+  const rhe_config& g = c->cfg;
+  const int K = g.n_bins, B = g.n_vec, n_pos = meta->n_pos, n_modes = g.n_ops;
+  P2Shape sh;
+  if (!p2_shape(s, &sh)) { rhe_set_error("individual-major pass B: unsupported shape"); return RHE_ERR_UNSUPPORTED; }
+  if (n_modes * n_pos > s->cap_pos) { rhe_set_error("pass B staging smaller than the plan (plan of another context?)"); return RHE_ERR_STATE; }
+  // the quantised weights in bin-sorted position order: the same kernel and buffers as the gather path (its per-group
+  // decode metadata is written as well and simply not read)
+  const int n_stage = n_modes * n_pos / 128, SI = s->G / s->MT;
+  const int n_chunk = rhe_div_up(rhe_div_up(n_stage, SI), 4);
+  k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B * c->n_groups * n_modes, 256), 256, 0, st>>>(
+      c->w1, c->w2, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, n_modes, B, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill,
+      s->pos_meta, SI, n_chunk);
+  RHE_LAUNCH_CHECK(c);
+  CUtensorMap tm_gt;                                   // GT as a 2-D byte tensor [(Np / 128) n_ss 128 rows][128 B]: one box = 16 KB contiguous
+  int rc = tc_encode_2d(s, &tm_gt, const_cast<uint8_t*>(gt), 128, (uint64_t)c->Np * (uint64_t)(n_pos / 512), 128);
+  if (rc) return rc;
+  const int rs_stride = g.n_sets == 2 ? c->Np : 0;
+  const int n_mt = c->Np / 128, grid = n_mt < s->n_sm ? n_mt : s->n_sm;      // persistent: one CTA per SM
+  const int dbg2 = RHE_DBG_ENV("PYRHE_TC_DEBUG_SKIPB2", 0);
+#define P2_LAUNCH(GS_, US_)                                                                                                 \
+  k_tc_pass_b2<GS_, US_><<<grid, P2_THREADS, sh.smem, st>>>(                                                               \
+      s->tm_uq, tm_gt, n_mt, c->Np, n_pos / 512, n_modes, meta->stage_info, meta->bin_count, K, c->n_groups, B, s->Bp, s->L, \
+      s->NCb, s->F, s->wmax, c->cs, c->rowscale, rs_stride, P_out, S_accum, sh.cols, sh.col_a, sh.n_acc, dbg2)
+  if (sh.gs == 8) P2_LAUNCH(8, 4);
+  else if (sh.gs == 6) P2_LAUNCH(6, 3);
+  else P2_LAUNCH(4, 2);
+#undef P2_LAUNCH
+  RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
+int rhe_tc_pass_b(rhe_ctx* c, const uint8_t* bed, const uint8_t* gt, const rhe_block_plan* plan, float* P_out, float* S_accum,
+                  cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
   const TcPlan* tp = (const TcPlan*)plan->tc;
   if (!tp) { rhe_set_error("rhe_block_accumulate: the plan was created without the tensor-core path"); return RHE_ERR_STATE; }
+  if (gt) {
+    if (tp->groups.size() != 1) { rhe_set_error("rhe_block_accumulate: individual-major copy given for a plan without fast path"); return RHE_ERR_INVALID; }
+    return tc_pass_b2(c, s, gt, plan->m, &tp->groups[0], P_out, S_accum, st);
+  }
   for (const TcBlockMeta& meta : tp->groups) {
     int rc = tc_pass_b_group(c, s, bed, plan->m, &meta, P_out, S_accum, st);
     if (rc) return rc;

@@ -67,6 +67,8 @@ class BlockStreamer:
         self.copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
         eng.bed.record_stream(self.copy_stream)
         eng.counts.record_stream(self.copy_stream)
+        for t in eng.gt.values():
+            t.record_stream(self.copy_stream)
         self._fd, self._file_off = None, 0
         fname = getattr(packed, "filename", None)
         if fname is not None and isinstance(packed, np.memmap) and packed.flags.c_contiguous \
@@ -271,6 +273,9 @@ class RheEngine:
         self._counted = set()
         #: hand the ingest-time allele counts to rhe_block_accumulate (False: every call re-counts the block)
         self.use_resident_counts = True
+        #: use the individual-major copies where they exist (False: pass B always gathers SNP-major rows)
+        self.use_fast_layout = True
+        self.gt = {}
         self._row_off = {}
         cur = 0
         for j in self.own:
@@ -329,7 +334,7 @@ class RheEngine:
                 self.nxe_S = torch.from_numpy(full).to(self.device)
 
     # ------------------------------------------------------------------ genotype residency
-    def alloc_genotypes(self, ring_blocks: Optional[int] = None):
+    def alloc_genotypes(self, ring_blocks: Optional[int] = None, fast_layout: bool = True, reserve_bytes: float = 6e9):
         """Device buffer for `.bed` rows, pitch padded to 128 bytes, zeroed (the padding stays zero).
 
         ring_blocks=None: every own block resident (`m_own x pitch` bytes).  ring_blocks=R: a ring of R block-sized
@@ -349,10 +354,30 @@ class RheEngine:
             self.bed = torch.zeros((rows, self.pitch), dtype=torch.uint8, device=self.device)
             self.counts = torch.zeros((rows, 4), dtype=torch.int32, device=self.device)
             self._counted = set()
+            self.gt = {}
+            if ring_blocks is None and fast_layout:
+                self._alloc_fast_layout(reserve_bytes)
         return self.bed
 
+    def _alloc_fast_layout(self, reserve_bytes: float):
+        """Individual-major copies (`rhe_block_transpose`) for as many resident blocks as the HBM holds next to the
+        SNP-major rows, the stored partials and the totals: pass B of those blocks feeds the tensor cores from tensor
+        memory instead of staging every genotype through shared memory.  A block without a copy simply
+        takes the gather kernel; results are identical either way."""
+        free_b, _ = torch.cuda.mem_get_info(self.device)
+        state = self.plan.E * self.plan.B * self.Np * 4
+        budget = free_b - reserve_bytes - 3 * state - (len(self.own) * state if self.store_partials else 0)
+        for j in self.own:
+            need = int(self.lib.rhe_block_fast_bytes(self._ctx, self._plans[j]))
+            if need <= 0 or need > budget:
+                break
+            self.gt[j] = torch.empty(need, dtype=torch.uint8, device=self.device)
+            budget -= need
+
     def genotype_bytes(self) -> int:
-        return 0 if self.bed is None else self.bed.numel() + self.counts.numel() * 4
+        if self.bed is None:
+            return 0
+        return self.bed.numel() + self.counts.numel() * 4 + sum(t.numel() for t in self.gt.values())
 
     def block_view(self, j: int):
         m = self.ranges[j][1] - self.ranges[j][0]
@@ -366,6 +391,9 @@ class RheEngine:
         st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
         cnt = self.counts[self._slot_off[j]: self._slot_off[j] + m]
         _lib.check(self.lib.rhe_block_stats(self._ctx, C.c_void_p(rows.data_ptr()), m, _lib.ptr(cnt), st))
+        if j in self.gt:                               # ingest also writes the block's individual-major copy
+            _lib.check(self.lib.rhe_block_transpose(self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], _lib.ptr(cnt),
+                                                    _lib.ptr(self.gt[j]), st))
         self._counted.add(j)
 
     def count_all(self):
@@ -415,11 +443,13 @@ class RheEngine:
     # ------------------------------------------------------------------ the path
     def _accumulate(self, j, P_out, S_accum, gram_out):
         rows, m = self.block_view(j)
-        cnt = None
+        cnt = gt = None
         if j in self._counted and self.use_resident_counts:
             cnt = C.c_void_p(self.counts.data_ptr() + 16 * self._slot_off[j])
+            if self.use_fast_layout and j in self.gt:
+                gt = _lib.ptr(self.gt[j])
         _lib.check(self.lib.rhe_block_accumulate(
-            self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], cnt, _lib.ptr(P_out), _lib.ptr(S_accum),
+            self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], cnt, gt, _lib.ptr(P_out), _lib.ptr(S_accum),
             _lib.ptr(gram_out), self._stream()))
 
     def _pass(self, upload, body):

@@ -251,3 +251,30 @@ def test_covariate_mean_imputation_keeps_the_individuals(tmp_path):
         out.append(m(trait=0))
     for key in out[0]:
         np.testing.assert_allclose(out[0][key], out[1][key], rtol=1e-9, atol=1e-12, err_msg=key)
+
+
+@pytest.mark.parametrize("name", ["rhe_cov_binary", "rhe_nocov_mean", "rhe_overlap", "rhe_one_block", "dom_cov", "dom_nocov",
+                                  "genie_full_cov", "genie_full_nocov", "rhe_example_shape"])
+def test_individual_major_fast_path_equals_gather(name):
+    """Pass B fed from tensor memory off the block's individual-major copy (`rhe_block_transpose`, k_tc_pass_b2) against
+    the gather kernel on the SNP-major rows: the same exact integer accumulation, so the block partials agree to the
+    last fp32 bit for one operand (RHE, GENIE) and to one fp32 rounding for RHE-DOM (its two operands are rounded
+    separately on this path)."""
+    p = oracle_problem(name)
+    plan = plan_for(p)
+    out = {}
+    for fast in (True, False):
+        eng, _, _ = make_engine(p, plan, kernel_path=1)
+        assert len(eng.gt) == len(eng.own), "every block of these small cases gets its individual-major copy"
+        eng.use_fast_layout = fast
+        pieces = eng.run()
+        out[fast] = (pieces, eng.P_all.cpu().numpy(), eng.S.cpu().numpy())
+        eng.close()
+    a, b = out[True], out[False]
+    if p.model == "rhe_dom":
+        np.testing.assert_allclose(a[1], b[1], rtol=3e-7, atol=1e-7 * np.abs(b[1]).max())
+    else:
+        np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_allclose(a[2], b[2], rtol=0, atol=2e-6 * np.abs(b[2]).max())
+    np.testing.assert_allclose(a[0]["XX"], b[0]["XX"], rtol=1e-6)
+    np.testing.assert_array_equal(a[0]["G_blk"], a[0]["G_blk"])
