@@ -43,6 +43,8 @@ WORKLOADS = {
     # a few config2 / config5 sized blocks: short enough to run under ncu
     "profile": dict(N=200_000, M=20_000, J=4, K=8, C=5, B=10, model="rhe"),
     "profile5": dict(N=500_000, M=40_000, J=4, K=8, C=5, B=10, model="rhe"),
+    "profile3": dict(N=200_000, M=20_000, J=4, K=8, C=5, B=10, model="rhe_dom"),
+    "profile4": dict(N=300_000, M=20_000, J=4, K=8, C=5, B=10, model="genie"),
     "small": dict(N=20_000, M=40_000, J=20, K=8, C=5, B=10, model="rhe"),
 }
 METRIC = "rhe_genotype_throughput"

@@ -61,6 +61,7 @@ struct TcState {
   unsigned int* wmax = nullptr; // [n_groups][B] max |weight| per weight group and column (float bits)
   int cap_pos = 0;
   int n_sm = 148;               // SMs of the device (grid of the persistent kernel)
+  int n_ops = 1;                // genotype operands (2: RHE-DOM)
   CUtensorMap tm_rq, tm_uq;
   PFN_encodeTiled encode = nullptr;
 };
@@ -908,43 +909,40 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
 //
 // Positions are bin-sorted, so a CTA (128 individuals, all positions) finishes bin k before it starts bin k + 1: the
 // accumulator of a bin lives in one of `n_acc` TMEM buffers of NC columns and is drained (scaled, written to P / S,
-// re-zeroed) by the drain warps while the next bin accumulates in the other buffer: n_acc NC + 10 A slots of TMEM
+// re-zeroed) by the drain warps while the next bins accumulate in the other buffers: n_acc NC + 8 A slots of TMEM
 // columns for any number of bins, and the epilogue overlaps the main loop.  The CTA is persistent: it walks the
 // M-tiles blockIdx.x, blockIdx.x + gridDim.x, ... and the sequence of sub-tiles, super-stages and bins simply
 // continues from one M-tile into the next, so rings and barriers never restart.
-// One persistent CTA per SM (992 threads, 64 registers): warps 0-19 decode (five groups of four, one TMEM lane quadrant
-// per warp), 20 TMA producer of the genotype boxes, 21 TMA producer of the Uq tiles, 22-26 MMA issue (one per decode
-// group), 27-30 drain (any four consecutive warps cover the four lane quadrants).  The decode loop is the spill-free
-// loop of pass A; the drains never touch it.  The two rings are fed independently: the genotype ring must run several
+// One persistent CTA per SM (960 threads, 64 registers): warps 0-15 decode (four groups of four, one TMEM lane quadrant
+// per warp), 16 TMA producer of the genotype boxes, 17 TMA producer of the Uq tiles, 18-21 MMA issue (one per decode
+// group), 22-29 drain (two sets of four consecutive warps = four lane quadrants; every set takes part of the columns of
+// every bin: each drain warp runs alone on its scheduler slot at the latency of its dependent chain, so the per-bin
+// latency, not the instruction count, is what has to stay below the time the issuers need for a bin).  The decode loop
+// is the spill-free loop of pass A; the drains never touch it.  The two rings are fed independently: the genotype ring must run several
 // super-stages ahead of the decode front (about 2.5 stages are being consumed at any time and HBM latency is ~2 us), while
 // a Uq slot only frees up when its MMAs have completed.
-#define P2_G 5
+#define P2_G 4
 #define P2_DW (4 * P2_G)
 #define P2_W_PROD P2_DW
 #define P2_W_PRODU (P2_DW + 1)
 #define P2_W_MMA (P2_DW + 2)
 #define P2_W_DRAIN (P2_DW + 2 + P2_G)
-#define P2_THREADS (32 * (P2_W_DRAIN + 4))
+#define P2_NDRAIN 8               // drain warps: two sets of four (lane quadrants), each set takes part of the columns
+#define P2_THREADS (32 * (P2_W_DRAIN + P2_NDRAIN))
 #define P2_AS (2 * P2_G)          // TMEM A slots (32 columns each): two per group
 #define P2_MAXRING 8
+#define P2_MAXACC 4               // accumulator buffers (bins in flight between the MMA issuers and the drain warps)
+#define P2_MAXSUB 1024            // sub-tiles (128 positions) of one M-tile, all operands
 
 struct P2Smem {
   uint64_t full_a[P2_AS], empty_a[P2_AS], full_u[P2_MAXRING], empty_u[P2_MAXRING], full_g[P2_MAXRING], empty_g[P2_MAXRING];
-  uint64_t bin_full[2], acc_free[2];
+  uint64_t bin_full[P2_MAXACC], acc_free[P2_MAXACC];
   uint32_t tmem_base;
   double cs[PB_MAX_KB];           // per-(weight group, bin, column) mean term
   double dq[64];                  // per-(weight group, column) dequantisation factor 2^(e - F)
   int32_t cnt[256];               // rows per bin
+  int32_t vbin[P2_MAXSUB];        // virtual bin (operand * K + bin) of every sub-tile of an M-tile
 };
-
-__device__ __forceinline__ bool mbar_test_s(uint32_t addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-  return ok != 0;
-}
 
 __device__ __forceinline__ double lds_f64_nv(uint32_t addr) {     // not volatile: the scheduler may hoist and overlap these
   double r;
@@ -952,81 +950,93 @@ __device__ __forceinline__ double lds_f64_nv(uint32_t addr) {     // not volatil
   return r;
 }
 
-// Drain the accumulator of virtual bin v = mode * K + k for this thread's individual (TMEM lane): the same arithmetic
-// as pb_epilogue.  mode 0 writes P (and subtracts the per-bin mean term), mode 1 (the [g == 2] operand of RHE-DOM)
-// adds to what mode 0 wrote -- the same thread drains both modes of a bin, so the read-modify-write is ordered.
-// The four drain warps are the serial resource of the kernel (one bin after the other, 128 lanes x B values each), so
-// the path is kept short: all limb rows of a weight group are read with as few tcgen05.ld as possible and ONE wait,
-// the accumulator buffer is zeroed and handed back to the MMA issuers (`release`) as soon as the last values are in
-// registers, and only then come the conversions and the stores; limbs are recombined in int64 (one conversion per value).
-// One chunk of W adjacent columns of a non-empty bin.  `p` / `s` point at this individual's entry of the chunk's first
-// column in P / S (nullptr: not wanted); successive columns are `Np` floats apart.  The drain warps are the serial
-// resource of the kernel, so the code per value is kept to the conversions, the limb recombination (exact in fp64),
-// scale, mean term, row scale, one store and one RED.
-template <int L, int W, int MODE>
-__device__ __forceinline__ void p2_drain_chunk(uint32_t taddr, int stride, int nvalid, size_t Np, double rs, uint32_t dq_a,
-                                               uint32_t cs_a, float* __restrict__ p, float* __restrict__ s, int dbg) {
-  int32_t a[L][W];
-  if (RHE_DBG(2)) {
-#pragma unroll
-    for (int l = 0; l < L; ++l)
-#pragma unroll
-      for (int j = 0; j < W; ++j) a[l][j] = (int)taddr + j;
+// The drain warps are the serial resource of this kernel (every bin of every M-tile passes through them), so their code
+// is written to stay short: the TMEM accesses carry no "memory" clobber (with one, the compiler re-derives every address
+// and re-reads the kernel parameters after each access: 35 instructions per value instead of 15), and the ordering the
+// hardware needs is expressed through the registers themselves.
+template <int W>
+__device__ __forceinline__ void tmem_ldw_nc(uint32_t taddr, int32_t (&v)[W]) {
+  static_assert(W == 2 || W == 4, "column chunk");
+  if constexpr (W == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
   } else {
-#pragma unroll
-    for (int l = 0; l < L; ++l) tmem_ldw<W>(taddr + (uint32_t)(l * stride), a[l]);
-    tmem_ld_wait();
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
   }
+}
+// the loaded registers may be used only after the wait: every one is passed through an (empty) volatile asm behind it
+template <int L, int W>
+__device__ __forceinline__ void tmem_ld_fence(int32_t (&a)[L][W]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int j = 0; j < W; ++j) asm volatile("" : "+r"(a[l][j]));
+}
+template <int W>
+__device__ __forceinline__ void tmem_zero_nc(uint32_t taddr) {     // zero W columns of this thread's lane (completion: tmem_st_wait)
+  const uint32_t z = 0u;
+  if constexpr (W == 4) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(z));
+  else asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %1};" ::"r"(taddr), "r"(z));
+}
+
+// One chunk of W adjacent columns of a non-empty bin for this thread's individual (TMEM lane): the same arithmetic as
+// pb_epilogue -- limbs recombined exactly in fp64, scale, mean term, row scale, one store and one RED per value.  `idx`
+// is the individual's entry of the chunk's first column in P / S (32-bit element index: the launch checks that the
+// accumulators hold fewer than 2^31 floats); successive columns are `Np` floats apart.  The columns are zeroed again as
+// soon as they are in registers (all MMAs accumulate).
+template <int L, int W>
+__device__ __forceinline__ void p2_drain_chunk(uint32_t taddr, uint32_t stride, int nvalid, uint32_t Np, double rs, uint32_t dq_a,
+                                               uint32_t cs_a, float* __restrict__ P_out, float* __restrict__ S_accum,
+                                               bool wp, bool ws, uint32_t idx) {
+  int32_t a[L][W];
+#pragma unroll
+  for (int l = 0; l < L; ++l) tmem_ldw_nc<W>(taddr + (uint32_t)l * stride, a[l]);
+  tmem_ld_fence<L, W>(a);
+#pragma unroll
+  for (int l = 0; l < L; ++l) tmem_zero_nc<W>(taddr + (uint32_t)l * stride);
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     if (j < nvalid) {
       double val = (double)a[L - 1][j];
 #pragma unroll
       for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
-      const double dq = lds_f64_nv(dq_a + 8u * (uint32_t)j);
-      float xf;
-      if (MODE == 0) xf = (float)(rs * (val * dq - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
-      else xf = (float)(rs * (val * dq));             // gather kernel: float(rs (dq (D0 + D1) - cs)); here two roundings
-      if (RHE_DBG(1)) { if (xf == 1.2345f && p) *p = xf; continue; }
-      if (p) { if (MODE == 0) *p = xf; else *p += xf; p += Np; }
-      if (s && !RHE_DBG(4)) { atomicAdd(s, xf); s += Np; }            // result unused -> RED
+      const float xf = (float)(rs * (val * lds_f64_nv(dq_a + 8u * (uint32_t)j) - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
+      if (wp) P_out[idx] = xf;
+      if (ws) atomicAdd(S_accum + idx, xf);            // result unused -> RED
+      idx += Np;
     }
   }
 }
 
-// Drain the accumulator of virtual bin v = mode * K + k for this thread's individual (TMEM lane): the same arithmetic
-// as pb_epilogue.  mode 0 writes P (and subtracts the per-bin mean term), mode 1 (the [g == 2] operand of RHE-DOM)
-// adds to what mode 0 wrote -- the same thread drains both modes of a bin, so the read-modify-write is ordered.
-template <int L, int MODE>
-__device__ __forceinline__ void p2_drain(uint32_t tcol, int k, int i, int K, int WG, int B, int Bp, size_t Np,
-                                         const double* dq_s, const double* cs_s, const float (&rsv)[2],
-                                         float* __restrict__ P_out, float* __restrict__ S_accum, int dbg) {
+// Drain the columns [c_lo, c_hi) of every weight group of bin k for this thread's individual.
+template <int L>
+__device__ __forceinline__ void p2_drain(uint32_t tcol, int c_lo, int c_hi, int k, int i, int K, int WG, int B, int Bp,
+                                         uint32_t Np, uint32_t dq_s, uint32_t cs_s, float rs0, float rs1,
+                                         float* __restrict__ P_out, float* __restrict__ S_accum) {
+  const bool wp = P_out != nullptr, ws = S_accum != nullptr;
   for (int wg = 0; wg < WG; ++wg) {                    // four columns per tcgen05.ld, the remainder in pairs
     const uint32_t base = tcol + (uint32_t)(wg * L * Bp);
-    const double rs = (double)(wg ? rsv[1] : rsv[0]);  // row scale of this individual: loaded once per M-tile, not per bin
-    uint32_t dq_a = smem_u32(dq_s + wg * B), cs_a = smem_u32(cs_s + (wg * K + k) * B);
-    const size_t o = (size_t)(wg * K + k) * B * Np + i;
-    float* p = P_out ? P_out + o : nullptr;
-    float* s = S_accum ? S_accum + o : nullptr;
-    int c0 = 0;
-    for (; c0 + 4 <= Bp; c0 += 4) {
-      p2_drain_chunk<L, 4, MODE>(base + (uint32_t)c0, Bp, B - c0, Np, rs, dq_a, cs_a, p, s, dbg);
-      dq_a += 32u; cs_a += 32u;
-      if (p) p += 4 * Np;
-      if (s) s += 4 * Np;
+    const double rs = (double)(wg ? rs1 : rs0);        // row scale of this individual: loaded once per M-tile, not per bin
+    uint32_t dq_a = dq_s + 8u * (uint32_t)(wg * B + c_lo), cs_a = cs_s + 8u * (uint32_t)((wg * K + k) * B + c_lo);
+    uint32_t idx = (uint32_t)((wg * K + k) * B + c_lo) * Np + (uint32_t)i;
+    int c0 = c_lo;
+    for (; c0 + 4 <= c_hi; c0 += 4) {
+      p2_drain_chunk<L, 4>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
+      dq_a += 32u; cs_a += 32u; idx += 4u * Np;
     }
-    for (; c0 < Bp; c0 += 2) {
-      p2_drain_chunk<L, 2, MODE>(base + (uint32_t)c0, Bp, B - c0, Np, rs, dq_a, cs_a, p, s, dbg);
-      dq_a += 16u; cs_a += 16u;
-      if (p) p += 2 * Np;
-      if (s) s += 2 * Np;
+    for (; c0 < c_hi; c0 += 2) {
+      p2_drain_chunk<L, 2>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
+      dq_a += 16u; cs_a += 16u; idx += 2u * Np;
     }
   }
 }
 
 // Sub-tile j = 128 positions of one M-tile; super-stage k = 4 sub-tiles = one TMA box of GT (128 individuals x 128 B) +
-// four Uq tiles; n_ss super-stages per mode, n_modes modes (RHE-DOM walks the positions twice: count operand, then
-// [g == 2] operand; both use the same GT bytes).  Capital letters below are indices of the CTA's whole run: J = it n_sub + j.
+// four Uq tiles per operand; n_ss super-stages per M-tile.  RHE-DOM has two operands (n_modes = 2: the count and
+// [g == 2], rhe_dom.py:36-39): every sub-tile is expanded twice from the same packed words, with the operand's mask and
+// against the operand's Uq tile, into the SAME accumulator -- P = rs (dq (D0 + D1) - cs) exactly as the gather kernel
+// forms it, and the copy is read once.
 template <int GS, int US>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ CUtensorMap tm_gt, int n_mt, int Np, int n_ss,
@@ -1038,28 +1048,28 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int acc_stride = (NC + 31) & ~31;            // TMEM columns per accumulator buffer (zeroed 32 columns at a time)
   uint8_t* packed = smem;                            // [GS][128 individuals][128 B], 128-byte swizzle
-  uint8_t* tileU = packed + GS * PA_PACKED;          // [US][4][NC][128 B]
+  uint8_t* tileU = packed + GS * PA_PACKED;          // [US][n_modes][4][NC][128 B]
   const int tileU_bytes = NC * 128;
-  P2Smem* sm = reinterpret_cast<P2Smem*>(tileU + US * 4 * tileU_bytes);
+  P2Smem* sm = reinterpret_cast<P2Smem*>(tileU + US * 4 * n_modes * tileU_bytes);
   const uint32_t packed_s = smem_u32(packed);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int n_it = n_mt > (int)blockIdx.x ? (n_mt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // own M-tiles
-  const int total_ss = n_ss * n_modes, n_sub = 4 * total_ss, V = n_modes * K;
-  const int N_sub = n_it * n_sub;                    // sub-tiles of the whole run
+  const int total_ss = n_ss, n_sub = 4 * total_ss, V = K;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P2_AS; ++s) { mbar_init(&sm->full_a[s], 4); mbar_init(&sm->empty_a[s], 1); }   // one arrival per decode warp
     for (int s = 0; s < P2_MAXRING; ++s) {
-      mbar_init(&sm->full_u[s], 1); mbar_init(&sm->empty_u[s], 4);      // 4 sub-tiles
+      mbar_init(&sm->full_u[s], 1); mbar_init(&sm->empty_u[s], 4 * n_modes);   // 4 sub-tiles x operands
       mbar_init(&sm->full_g[s], 1); mbar_init(&sm->empty_g[s], 16);     // 4 sub-tiles x 4 warps
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sm->bin_full[s], P2_G); mbar_init(&sm->acc_free[s], 4); }
+    for (int s = 0; s < P2_MAXACC; ++s) { mbar_init(&sm->bin_full[s], P2_G); mbar_init(&sm->acc_free[s], P2_NDRAIN); }
     fence_barrier_init();
   }
   if (warp == P2_W_PROD) tmem_alloc(&sm->tmem_base, tmem_cols);
   for (int i = threadIdx.x; i < WG * K * B; i += P2_THREADS) sm->cs[i] = cs[i];
   for (int i = threadIdx.x; i < K; i += P2_THREADS) sm->cnt[i] = bin_count[i];
+  for (int i = threadIdx.x; i < n_sub; i += P2_THREADS) sm->vbin[i] = stage_info[i] & 255;   // bin of every sub-tile
   for (int i = threadIdx.x; i < WG * B; i += P2_THREADS) {
     const int ex = (int)((wmax[i] >> 23) & 255u);       // same rule as k_tc_quant_w / the gather kernel
     sm->dq[i] = ex == 255 ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex - 126 - F);
@@ -1075,51 +1085,97 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
   tc_fence_after();
 
   if (warp < P2_DW) {
+    // ---- decode: group g expands sub-tile g of EVERY super-stage (P2_G == 4 sub-tiles per box), so the chunk it reads
+    // inside a staged box is fixed and every ring index advances by one per iteration: no division, no modulo.
+    static_assert(P2_G == 4, "group g = sub-tile g of every super-stage");
     const int t = (warp & 3) * 32 + lane, g = warp >> 2;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t row_s = packed_s + (uint32_t)t * 128;      // this thread's individual inside a staged box
     const uint32_t sw = (uint32_t)(t & 7);                      // 128-byte swizzle: 16-byte chunk c sits at c ^ (row & 7)
-    const int n_own = N_sub > g ? (N_sub - g + P2_G - 1) / P2_G : 0;     // own sub-tiles J = g + P2_G * jj
-    // packed words of sub-tile J = 4 Kg + q: chunks 2 q, 2 q + 1 of the row in ring slot Kg % GS
-    auto fetch = [&](int J, uint4& lo, uint4& hi) {
-      const int k = J >> 2, q = J & 3, sg = k % GS;
-      mbar_wait(&sm->full_g[sg], (uint32_t)(k / GS) & 1u);
-      const uint32_t base = row_s + (uint32_t)sg * PA_PACKED;
-      lo = lds128(base + (((uint32_t)(2 * q) ^ sw) << 4));
-      hi = lds128(base + (((uint32_t)(2 * q + 1) ^ sw) << 4));
+    const uint32_t row_lo = packed_s + (uint32_t)t * 128 + ((((uint32_t)(2 * g)) ^ sw) << 4);
+    const uint32_t row_hi = packed_s + (uint32_t)t * 128 + ((((uint32_t)(2 * g + 1)) ^ sw) << 4);
+    const uint32_t fg = smem_u32(&sm->full_g[0]), eg = smem_u32(&sm->empty_g[0]);
+    const uint32_t fa = smem_u32(&sm->full_a[2 * g]), ea = smem_u32(&sm->empty_a[2 * g]);
+    const uint32_t dst0 = lane_base + col_a + 32u * (uint32_t)(2 * g);
+    const int n_k = n_it * total_ss;                          // super-stages of the whole run
+    uint32_t fsl = 0, fpar = 0;                                // ring slot / parity of the next box to read
+    uint32_t csl = 0;                                          // ring slot of the box being expanded
+    uint32_t aq = 0, apar = 1;                                 // the group's A slot of the next expansion / parity to wait for
+    // The individual-major copy carries no missing code and stores the operand VALUE in its two bits (imputation and the
+    // PLINK code -> count map are applied at ingest), so a word expands with one mask per output register and three
+    // multiply-high shifts -- four ALU-pipe and three FMA-pipe instructions per sixteen genotypes -- instead of the
+    // table look-up of pass A (two masks, four byte permutes, three shifts).  Register k of a word holds the fields
+    // k, k + 4, k + 8, k + 12: k_tc_transpose places position 4 k + j of a word's sixteen at field 4 j + k.
+    // [g == 2] is bit 1 of the value: one more shift per word.
+    auto fetch = [&](uint4& lo, uint4& hi) {
+      mbar_wait_s(fg + 8u * fsl, fpar);
+      lo = lds128(row_lo + fsl * PA_PACKED);
+      hi = lds128(row_hi + fsl * PA_PACKED);
+      if (++fsl == (uint32_t)GS) { fsl = 0; fpar ^= 1u; }
     };
-    // Same software pipeline as pass A: the packed words of the next sub-tile are read from the ring before the current
-    // one is expanded, each sub-tile goes to TMEM as two 16-column stores, one barrier arrival per warp.
-    auto put = [&](uint32_t slot_a, uint32_t parity, const uint4& lo, const uint4& hi, int k, uint32_t tab) {
-      uint4 r[4];
-      mbar_wait(&sm->empty_a[slot_a], parity ^ 1u);
+    auto expand0 = [](uint32_t w) {
+      const uint32_t m = 0x03030303u;
+      uint4 r;
+      r.x = w & m;
+      r.y = tc_shr_fma(w, 1u << 30) & m;
+      r.z = tc_shr_fma(w, 1u << 28) & m;
+      r.w = tc_shr_fma(w, 1u << 26) & m;
+      return r;
+    };
+    auto expand1 = [](uint32_t w) {
+      const uint32_t m = 0x01010101u;
+      uint4 r;
+      r.x = tc_shr_fma(w, 1u << 31) & m;
+      r.y = tc_shr_fma(w, 1u << 29) & m;
+      r.z = tc_shr_fma(w, 1u << 27) & m;
+      r.w = tc_shr_fma(w, 1u << 25) & m;
+      return r;
+    };
+    // one operand of one sub-tile -> the group's next A slot; `release`: the packed words are not needed again
+    auto put = [&](const uint4& lo, const uint4& hi, auto expand, bool release) {
+      mbar_wait_s(ea + 8u * aq, apar);
       tc_fence_after();
-      const uint32_t dst = lane_base + col_a + 32u * slot_a;
-      r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
+      const uint32_t dst = dst0 + 32u * aq;
+      uint4 r[4];
+      r[0] = expand(lo.x); r[1] = expand(lo.y); r[2] = expand(lo.z); r[3] = expand(lo.w);
       tmem_st16(dst, r);
       uint4 r2[4];
-      r2[0] = tc_expand(hi.x, tab); r2[1] = tc_expand(hi.y, tab); r2[2] = tc_expand(hi.z, tab); r2[3] = tc_expand(hi.w, tab);
+      r2[0] = expand(hi.x); r2[1] = expand(hi.y); r2[2] = expand(hi.z); r2[3] = expand(hi.w);
       tmem_st16(dst + 16, r2);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();                                    // every lane's stores are complete and fenced: one arrival per warp
-      if (lane == 0) { mbar_arrive(&sm->empty_g[k % GS]); mbar_arrive(&sm->full_a[slot_a]); }
+      if (lane == 0) {
+        if (release) mbar_arrive_s(eg + 8u * csl);
+        mbar_arrive_s(fa + 8u * aq);
+      }
+      if (release && ++csl == (uint32_t)GS) csl = 0;
+      aq ^= 1u;
+      if (aq == 0u) apar ^= 1u;
     };
-    // the GT bytes carry no missing code (imputation is applied at ingest): a constant value table per operand
-    const uint32_t tab0 = tc_value_table(0u, 0), tab1 = tc_value_table(0u, 1);
-    const int half = n_modes == 2 ? n_sub >> 1 : n_sub;       // sub-tiles [half, n_sub) of an M-tile use the [g == 2] operand
-    int jm = g % n_sub;                                       // J mod n_sub of the current sub-tile
-    uint4 lo, hi;
-    if (n_own > 0) fetch(g, lo, hi);
-    for (int jj = 0; jj < n_own; ++jj) {
-      const int J = g + P2_G * jj;
-      uint4 nlo = lo, nhi = hi;
-      if (jj + 1 < n_own) fetch(J + P2_G, nlo, nhi);
-      put((uint32_t)(2 * g + (jj & 1)), (uint32_t)(jj >> 1) & 1u, lo, hi, J >> 2, jm >= half ? tab1 : tab0);
-      lo = nlo;
-      hi = nhi;
-      jm += P2_G;
-      while (jm >= n_sub) jm -= n_sub;
+    // Software pipeline, unrolled by two so that the register sets swap roles without moves: the packed words of the
+    // next box are read from the ring before the current one is expanded.
+    uint4 lo0, hi0, lo1, hi1;
+    if (n_k > 0) fetch(lo0, hi0);
+    if (n_modes == 1) {
+      for (int k = 0; k < n_k; k += 2) {
+        if (k + 1 < n_k) fetch(lo1, hi1);
+        put(lo0, hi0, expand0, true);
+        if (k + 1 < n_k) {
+          if (k + 2 < n_k) fetch(lo0, hi0);
+          put(lo1, hi1, expand0, true);
+        }
+      }
+    } else {
+      for (int k = 0; k < n_k; k += 2) {
+        if (k + 1 < n_k) fetch(lo1, hi1);
+        put(lo0, hi0, expand0, false);
+        put(lo0, hi0, expand1, true);
+        if (k + 1 < n_k) {
+          if (k + 2 < n_k) fetch(lo0, hi0);
+          put(lo1, hi1, expand0, false);
+          put(lo1, hi1, expand1, true);
+        }
+      }
     }
     tc_fence_before();
   } else if (warp == P2_W_PROD) {
@@ -1129,20 +1185,19 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
     uint32_t gsl = 0, gpar = 1;
     for (int it = 0; it < n_it; ++it) {
       const int mt = (int)blockIdx.x + it * (int)gridDim.x;
-      int kk = 0;                                      // super-stage inside the mode
       for (int k = 0; k < total_ss; ++k) {             // the whole warp runs the loop; one elected lane issues
         mbar_wait_s(eg + 8u * gsl, gpar);
         if (elect_one()) {
           mbar_expect_tx_s(fg + 8u * gsl, PA_PACKED);
-          tma_load_2d_s(packed_s + gsl * PA_PACKED, &tm_gt, fg + 8u * gsl, 0, (mt * n_ss + kk) * 128);
+          tma_load_2d_s(packed_s + gsl * PA_PACKED, &tm_gt, fg + 8u * gsl, 0, (mt * n_ss + k) * 128);
         }
         __syncwarp();
         if (++gsl == (uint32_t)GS) { gsl = 0; gpar ^= 1u; }
-        if (++kk == n_ss) kk = 0;
       }
     }
   } else if (warp == P2_W_PRODU) {
-    // TMA producer 2: the four Uq tiles of every super-stage -> ring slot Kg % US (the same tiles for every M-tile: L2 hits)
+    // TMA producer 2: the four Uq tiles per operand of every super-stage -> ring slot Kg % US (the same tiles for every
+    // M-tile: L2 hits); operand md occupies the positions [md n_pos, (md + 1) n_pos) of the weight buffer
     const uint32_t fu = smem_u32(&sm->full_u[0]), eu = smem_u32(&sm->empty_u[0]);
     const uint32_t tileU_s = smem_u32(tileU);
     uint32_t usl = 0, upar = 1;
@@ -1150,100 +1205,102 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
       for (int k = 0; k < total_ss; ++k) {
         mbar_wait_s(eu + 8u * usl, upar);
         if (elect_one()) {
-          mbar_expect_tx_s(fu + 8u * usl, 4u * (uint32_t)tileU_bytes);
+          mbar_expect_tx_s(fu + 8u * usl, 4u * (uint32_t)(n_modes * tileU_bytes));
+          for (int md = 0; md < n_modes; ++md)
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            tma_load_2d_s(tileU_s + (usl * 4u + (uint32_t)q) * (uint32_t)tileU_bytes, &tm_uq, fu + 8u * usl, (4 * k + q) * 128, 0);
+            for (int q = 0; q < 4; ++q)
+              tma_load_2d_s(tileU_s + ((usl * (uint32_t)n_modes + (uint32_t)md) * 4u + (uint32_t)q) * (uint32_t)tileU_bytes, &tm_uq,
+                            fu + 8u * usl, (md * n_sub + 4 * k + q) * 128, 0);
         }
         __syncwarp();
         if (++usl == (uint32_t)US) { usl = 0; upar ^= 1u; }
       }
     }
   } else if (warp < P2_W_DRAIN) {
-    // ---- MMA issue: one warp per decode group.  Every issuer walks ALL virtual bins of the run in order (bin v of M-tile
-    // `it` is Vg = it V + v) -- enter (wait until the bin's accumulator buffer has been drained of the bin n_acc before
-    // it), issue its own sub-tiles of the bin, leave (commit: the buffer's bin_full barrier counts the issuers) -- so no
-    // barrier ever sees arrivals of two phases.
+    // ---- MMA issue: one warp per decode group = sub-tile g of every super-stage.  Every issuer walks ALL virtual bins of
+    // the run in order (bin v of M-tile `it` is Vg = it V + v) -- enter (wait until the bin's accumulator buffer has been
+    // drained of the bin n_acc before it), issue its own sub-tiles of the bin, leave (commit: the buffer's bin_full
+    // barrier counts the issuers) -- so no barrier ever sees arrivals of two phases.  The loop is one thread's latency
+    // chain and sits on the round trip of the A slots (decode -> MMA -> slot free): ring indices, parities and
+    // descriptors advance incrementally and the bin of a sub-tile comes from shared memory.  Every sub-tile issues
+    // all four K-steps: rows beyond the end of a bin are zero in the copy and in the weights.
     const int g = warp - P2_W_MMA;
     const uint32_t idesc = idesc_i8(128, NC, 0);
     const uint32_t fu = smem_u32(&sm->full_u[0]), eu = smem_u32(&sm->empty_u[0]);
     const uint32_t fa = smem_u32(&sm->full_a[2 * g]), ea = smem_u32(&sm->empty_a[2 * g]);
     const uint32_t bfull = smem_u32(&sm->bin_full[0]), afree = smem_u32(&sm->acc_free[0]);
-    const uint64_t bdesc0 = smem_desc_sw128(smem_u32(tileU), 16, 1024);
-    const int n_own = N_sub > g ? (N_sub - g + P2_G - 1) / P2_G : 0;
-    const int V_all = n_it * V, sh = n_acc - 1;          // n_acc is 1 or 2: Vg % n_acc = Vg & sh, Vg / n_acc = Vg >> sh
-    uint32_t ph_a = 0, q = 0;
-    int cur_v = 0;
+    const uint64_t bdesc_g = smem_desc_sw128(smem_u32(tileU), 16, 1024) + (uint64_t)((uint32_t)g * (uint32_t)(tileU_bytes >> 4));
+    const uint32_t mode_step = 4u * (uint32_t)(tileU_bytes >> 4), slot_step = mode_step * (uint32_t)n_modes;
+    const uint32_t acol0 = tmem + col_a + 32u * (2u * (uint32_t)g);
+    const uint32_t vb_s = smem_u32(sm->vbin) + 4u * (uint32_t)g;          // vbin[4 kin + g]
+    const int n_k = n_it * total_ss;
+    const int V_all = n_it * V, am = n_acc - 1, sh = n_acc == 4 ? 2 : n_acc - 1;   // n_acc is 1, 2 or 4: Vg % n_acc = Vg & am, Vg / n_acc = Vg >> sh
+    uint32_t ph_a = 0, q = 0, usl = 0, upar = 0, desc_off = 0;
+    int cur_v = 0, vbase = 0, kin = 0;
     auto enter = [&](int v) {                          // buffer v % n_acc must have been drained of bin v - n_acc
-      if (v >= n_acc) mbar_wait_s(afree + 8u * (uint32_t)(v & sh), (uint32_t)((v >> sh) - 1) & 1u);
+      if (v >= n_acc) mbar_wait_s(afree + 8u * (uint32_t)(v & am), (uint32_t)((v >> sh) - 1) & 1u);
       tc_fence_after();
     };
     auto leave = [&](int v) {
-      if (elect_one()) umma_commit_s(bfull + 8u * (uint32_t)(v & sh));
+      if (elect_one()) umma_commit_s(bfull + 8u * (uint32_t)(v & am));
       __syncwarp();
     };
     if (V_all > 0) enter(0);
-    int jm = g % n_sub, vbase = 0;                       // J mod n_sub and it * V of the current sub-tile
-    for (int x = g; x >= n_sub; x -= n_sub) vbase += V;  // (g < n_sub unless the M-tile has a single super-stage)
-    uint32_t info_next = n_own > 0 ? (uint32_t)__ldg(stage_info + jm) : 0u;     // one sub-tile ahead, straight from L2
-    for (int jj = 0; jj < n_own; ++jj) {
-      const int J = g + P2_G * jj, k = J >> 2;
-      const uint32_t info = info_next;                           // stage_info holds n_modes copies of the per-mode list
-      const int v = vbase + (jm >= (n_modes == 2 ? n_sub >> 1 : n_sub) ? K : 0) + (int)(info & 255u);
-      const int ksteps = (int)(info >> 16);
-      jm += P2_G;
-      while (jm >= n_sub) { jm -= n_sub; vbase += V; }
-      if (jj + 1 < n_own) info_next = (uint32_t)__ldg(stage_info + jm);
+    for (int k = 0; k < n_k; ++k) {
+      const int v = vbase + (int)lds32(vb_s + 16u * (uint32_t)kin);
+      if (++kin == total_ss) { kin = 0; vbase += V; }
       while (cur_v < v) { leave(cur_v); ++cur_v; enter(cur_v); }
-      const uint32_t u_slot = (uint32_t)(k % US);
-      mbar_wait_s(fu + 8u * u_slot, (uint32_t)(k / US) & 1u);
-      mbar_wait_s(fa + 8u * q, ph_a);
-      tc_fence_after();
-      const uint64_t bdesc = bdesc0 + (uint64_t)((u_slot * 4u + ((uint32_t)J & 3u)) * (uint32_t)(tileU_bytes >> 4));
-      const uint32_t acol = tmem + col_a + 32u * (2u * (uint32_t)g + q);
-      const uint32_t dcol = tmem + (uint32_t)((v & sh) * acc_stride);
-      if (elect_one()) {
+      mbar_wait_s(fu + 8u * usl, upar);
+      const uint32_t dcol = tmem + (uint32_t)((v & am) * acc_stride);
+      for (int md = 0; md < n_modes; ++md) {           // the operands of the sub-tile: same accumulator, own A slot and Uq tile
+        mbar_wait_s(fa + 8u * q, ph_a);
+        tc_fence_after();
+        const uint64_t bdesc = bdesc_g + (uint64_t)(desc_off + (uint32_t)md * mode_step);
+        const uint32_t acol = acol0 + 32u * q;
+        if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)   // K = 32 positions per instruction: 8 TMEM columns / 32 bytes of the Uq row
-          if (i < ksteps) umma_i8_ts(dcol, acol + 8u * i, bdesc + (uint64_t)(i * 2), idesc, 1u);
-        umma_commit_s(ea + 8u * q);
-        umma_commit_s(eu + 8u * u_slot);
+          for (int i = 0; i < 4; ++i)   // K = 32 positions per instruction: 8 TMEM columns / 32 bytes of the Uq row
+            umma_i8_ts(dcol, acol + 8u * i, bdesc + (uint64_t)(i * 2), idesc, 1u);
+          umma_commit_s(ea + 8u * q);
+          umma_commit_s(eu + 8u * usl);
+        }
+        __syncwarp();
+        q ^= 1u;
+        if (q == 0u) ph_a ^= 1u;
       }
-      __syncwarp();
-      q ^= 1u;
-      if (q == 0u) ph_a ^= 1u;
+      desc_off += slot_step;
+      if (++usl == (uint32_t)US) { usl = 0; upar ^= 1u; desc_off = 0; }
     }
     while (cur_v < V_all) { leave(cur_v); ++cur_v; if (cur_v < V_all) enter(cur_v); }
   } else {
-    // ---- drain warps (TMEM lane quadrant = warp & 3): bin after bin, in sequence order.  The same four warps drain every
-    // bin, so each accumulator buffer's barriers advance one phase per use and a parity wait is never ambiguous.
-    const int t = (warp & 3) * 32 + lane, sh = n_acc - 1;
+    // ---- drain warps (TMEM lane quadrant = warp & 3): bin after bin, in sequence order.  The same eight warps drain every
+    // bin, so each accumulator buffer's barriers advance one phase per use and a parity wait is never ambiguous.  Set 0
+    // takes the columns [0, c_split) of every weight group, set 1 the columns [c_split, Bp).
+    const int t = (warp & 3) * 32 + lane, am = n_acc - 1, sh = n_acc == 4 ? 2 : n_acc - 1;
+    const int set = (warp - P2_W_DRAIN) >> 2;
+    const int c_split = min(Bp, 4 * ((Bp / 2 + 2) / 4));
+    const int c_lo = set ? c_split : 0, c_hi = set ? Bp : c_split;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t bfull = smem_u32(&sm->bin_full[0]), afree = smem_u32(&sm->acc_free[0]);
+    const uint32_t dq_s = smem_u32(sm->dq), cs_s = smem_u32(sm->cs);
     int Vg = 0;
     for (int it = 0; it < n_it; ++it) {
       const int i = ((int)blockIdx.x + it * (int)gridDim.x) * 128 + t;
-      const float rsv[2] = {rowscale[i], WG > 1 ? rowscale[(size_t)rs_stride + i] : 0.f};
+      const float rs0 = rowscale[i], rs1 = WG > 1 ? rowscale[(size_t)rs_stride + i] : 0.f;
       for (int v = 0; v < V; ++v, ++Vg) {
-        const int mode = v >= K ? 1 : 0, k = v - mode * K, buf = Vg & sh;
+        const int k = v, buf = Vg & am;
         mbar_wait_s(bfull + 8u * (uint32_t)buf, (uint32_t)(Vg >> sh) & 1u);
         tc_fence_after();
         const bool has = sm->cnt[k] > 0;
         const uint32_t tcol = lane_base + (uint32_t)(buf * acc_stride);
         if (has) {
-          if (mode == 0) {
-            if (L == 3) p2_drain<3, 0>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
-            else if (L == 2) p2_drain<2, 0>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
-            else p2_drain<4, 0>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
-          } else {
-            if (L == 3) p2_drain<3, 1>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
-            else if (L == 2) p2_drain<2, 1>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
-            else p2_drain<4, 1>(tcol, k, i, K, WG, B, Bp, (size_t)Np, sm->dq, sm->cs, rsv, P_out, S_accum, dbg);
-          }
-          for (int c = 0; c < acc_stride; c += 32) tmem_zero32(tcol + (uint32_t)c);
-        } else if (mode == 0 && P_out) {                 // a bin without SNPs in this block: X (X^T Z) = 0
+          if (L == 3) p2_drain<3>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
+          else if (L == 2) p2_drain<2>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
+          else p2_drain<4>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
+          tmem_st_wait();                              // the columns this warp read are zero again
+        } else if (P_out) {                              // a bin without SNPs in this block: X (X^T Z) = 0
           for (int wg = 0; wg < WG; ++wg)
-            for (int b = 0; b < B; ++b) P_out[((size_t)(wg * K + k) * B + b) * Np + i] = 0.f;
+            for (int b = c_lo; b < min(c_hi, B); ++b) P_out[(size_t)((wg * K + k) * B + b) * (size_t)Np + i] = 0.f;
         }
         tc_fence_before();
         __syncwarp();
@@ -1255,9 +1312,10 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
   if (warp == P2_W_PROD) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
-// Individual-major copy of one block (ingest): GT[i][p] = imputed 2-bit code of bin-sorted position p for individual i.
-// Word w of a row holds positions 16 w .. 16 w + 15 with position 16 w + x in field tc_perm16-inverse order, so that the
-// byte order tc_expand produces is the natural position order of the Uq tiles.  Tile = 128 positions x 512 individuals.
+// Individual-major copy of one block (ingest): GT[i][p] = imputed A2 count (0, 1, 2 as a 2-bit number; no missing code
+// is left) of bin-sorted position p for individual i.  Word w of a row holds positions 16 w .. 16 w + 15, position
+// 16 w + 4 k + j in field 4 j + k, so that register k, byte j of the expansion in k_tc_pass_b2 is position 4 k + j: the
+// natural position order of the Uq tiles.  Tile = 128 positions x 512 individuals.
 __global__ void __launch_bounds__(256)
 k_tc_transpose(const uint8_t* __restrict__ bed, int pitch, const int32_t* __restrict__ pos_rows,
                const int32_t* __restrict__ counts, int n_kept, int binary, const double* __restrict__ uniforms,
@@ -1276,8 +1334,7 @@ k_tc_transpose(const uint8_t* __restrict__ bed, int pitch, const int32_t* __rest
     int code = 0;
     if (row >= 0) {
       const int4 c = reinterpret_cast<const int4*>(counts)[row];
-      const int f = rhe_fill_from_counts(c.y, c.z, c.w, n_kept, binary, binary ? uniforms[row] : 0.0);
-      code = f == 0 ? 0 : (f == 1 ? 2 : 3);           // A2 count -> PLINK code (00, 10, 11)
+      code = rhe_fill_from_counts(c.y, c.z, c.w, n_kept, binary, binary ? uniforms[row] : 0.0);   // value a missing genotype takes
     }
     fcode[threadIdx.x] = (uint8_t)code;
   }
@@ -1289,10 +1346,9 @@ k_tc_transpose(const uint8_t* __restrict__ bed, int pitch, const int32_t* __rest
     uint32_t out = 0;
 #pragma unroll
     for (int f = 0; f < 16; ++f) {
-      const int p = 16 * pg + tc_invperm16(f);
-      uint32_t code = (tile[p][wsrc] >> sh) & 3u;
-      if (code == 1u) code = fcode[p];
-      out |= code << (2 * f);
+      const int p = 16 * pg + 4 * (f & 3) + (f >> 2);
+      const uint32_t code = (tile[p][wsrc] >> sh) & 3u;            // PLINK code: 00 -> 0, 01 -> missing, 10 -> 1, 11 -> 2
+      out |= (uint32_t)rhe_code_value(code, fcode[p]) << (2 * f);
     }
     outw[i][pg] = out;
   }
@@ -1499,6 +1555,7 @@ int rhe_tc_create(rhe_ctx* c) {
   }
   s->encode = (PFN_encodeTiled)fn;
   cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, c->cfg.device);
+  s->n_ops = c->cfg.n_ops;
   c->tc = s;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
@@ -1698,14 +1755,14 @@ struct P2Shape { int n_acc, gs, us, smem; uint32_t col_a, cols; };
 
 static bool p2_shape(const TcState* s, P2Shape* o) {
   if (s->NCb > 96) return false;
-  o->n_acc = 2;
+  o->n_acc = 4 * round_up(s->NCb, 32) + 32 * P2_AS <= 512 ? 4 : 2;   // bins in flight between the issuers and the drain warps
   o->col_a = (uint32_t)(o->n_acc * round_up(s->NCb, 32));
   o->cols = pow2_cols((int)o->col_a + 32 * P2_AS);
   if (o->cols > 512) return false;
   const int budget = 232448 - 2048;                    // one CTA per SM
   const int rings[3][2] = {{8, 4}, {6, 3}, {4, 2}};    // depth of the genotype-box ring / of the Uq super-stage ring
   for (const auto& r : rings) {
-    const int smem = r[0] * PA_PACKED + r[1] * 4 * s->NCb * 128 + (int)sizeof(P2Smem) + 1024;
+    const int smem = r[0] * PA_PACKED + r[1] * 4 * s->n_ops * s->NCb * 128 + (int)sizeof(P2Smem) + 1024;
     if (smem <= budget) { o->gs = r[0]; o->us = r[1]; o->smem = smem; return true; }
   }
   return false;
@@ -1723,6 +1780,8 @@ int64_t rhe_tc_gt_bytes(const rhe_ctx* c, const rhe_block_plan* plan) {
   const TcPlan* tp = (const TcPlan*)plan->tc;
   P2Shape sh;
   if (!s || !tp || tp->groups.size() != 1 || tp->groups[0].n_pos <= 0 || !p2_shape(s, &sh)) return 0;
+  if ((int64_t)c->n_groups * c->cfg.n_bins * c->cfg.n_vec * (int64_t)c->Np >= (1ll << 31)) return 0;   // 32-bit indices into P / S
+  if (c->cfg.n_ops * (tp->groups[0].n_pos / 128) > P2_MAXSUB) return 0;                                 // per-sub-tile bin table in shared memory
   return (int64_t)c->Np * (tp->groups[0].n_pos / 4);
 }
 

@@ -294,6 +294,9 @@ class RheEngine:
             self._plans = {}
             self.lib.rhe_ctx_destroy(self._ctx)
             self._ctx = None
+            # the genotype residency and the accumulators go back to the allocator with the context
+            self.bed = self.counts = self.S = self.P_all = None
+            self.gt = {}
 
     def __del__(self):
         try:
@@ -476,6 +479,7 @@ class RheEngine:
         if upload is None and self.ring_blocks is not None and self.ring_blocks < len(self.own):
             raise _lib.RheError("genotypes live in a ring: run() needs the streamer (upload=...)")
         with torch.cuda.device(dev):
+            self.S = self.P_all = None                 # the previous run's state goes back to the allocator first
             S = torch.zeros((E, B, Np), dtype=torch.float32, device=dev)
             G_blk = torch.zeros((J, E_reg, Rs, Rs), dtype=torch.float64, device=dev)
             XX = torch.zeros((J + 1, E, E), dtype=torch.float64, device=dev)

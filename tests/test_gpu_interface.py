@@ -176,6 +176,7 @@ def test_resident_counts_equal_recounting():
     for resident in (True, False):
         eng, _, _ = make_engine(p, plan)
         eng.use_resident_counts = resident
+        eng.use_fast_layout = False                    # same pass-B kernel in both runs (the copies need the counts)
         outs.append(eng.run())
         eng.close()
     np.testing.assert_allclose(outs[0]["XX"], outs[1]["XX"], rtol=1e-12)
@@ -257,9 +258,10 @@ def test_covariate_mean_imputation_keeps_the_individuals(tmp_path):
                                   "genie_full_cov", "genie_full_nocov", "rhe_example_shape"])
 def test_individual_major_fast_path_equals_gather(name):
     """Pass B fed from tensor memory off the block's individual-major copy (`rhe_block_transpose`, k_tc_pass_b2) against
-    the gather kernel on the SNP-major rows: the same exact integer accumulation, so the block partials agree to the
-    last fp32 bit for one operand (RHE, GENIE) and to one fp32 rounding for RHE-DOM (its two operands are rounded
-    separately on this path)."""
+    the gather kernel on the SNP-major rows: the same exact integer accumulation and the same fp64 epilogue (RHE-DOM's
+    two operands accumulate into one tensor-memory accumulator on both paths), so the block partials agree to the last
+    fp32 bit wherever the per-bin mean term does -- that term is an fp64 atomic sum, whose last bit may differ from run
+    to run and move a partial that sits on a rounding boundary by one fp32 ulp."""
     p = oracle_problem(name)
     plan = plan_for(p)
     out = {}
@@ -271,10 +273,9 @@ def test_individual_major_fast_path_equals_gather(name):
         out[fast] = (pieces, eng.P_all.cpu().numpy(), eng.S.cpu().numpy())
         eng.close()
     a, b = out[True], out[False]
-    if p.model == "rhe_dom":
-        np.testing.assert_allclose(a[1], b[1], rtol=3e-7, atol=1e-7 * np.abs(b[1]).max())
-    else:
-        np.testing.assert_array_equal(a[1], b[1])
+    differ = a[1] != b[1]
+    assert differ.mean() < 1e-5
+    np.testing.assert_allclose(a[1], b[1], rtol=2.4e-7, atol=0)
     np.testing.assert_allclose(a[2], b[2], rtol=0, atol=2e-6 * np.abs(b[2]).max())
     np.testing.assert_allclose(a[0]["XX"], b[0]["XX"], rtol=1e-6)
     np.testing.assert_array_equal(a[0]["G_blk"], a[0]["G_blk"])
