@@ -377,20 +377,24 @@ extern "C" void rhe_tc_prof_dump() {
 #define PA_THREADS (32 * (PA_DW + 2 + PA_G))   // decode warps, two TMA warps (Rq tiles, genotype boxes), one MMA-issue warp per group
 #define PA_AS (2 * PA_G)          // TMEM A slots (32 columns each): two per group
 #define PA_RS 2                   // smem ring of Rq super-stages (four NB x 128 B tiles each, one barrier pair per slot)
-#define PA_GS 3                   // smem ring of packed super-stages (128 rows x 128 B each)
+#define PA_MAXGS 8                // deepest smem ring of packed super-stages (128 rows x 128 B each); the launch picks the depth
 #define PA_PACKED (128 * 128)
 
 struct PaSmem {
-  uint64_t full_a[PA_AS], empty_a[PA_AS], full_b[PA_RS], empty_b[PA_RS], full_g[PA_GS], empty_g[PA_GS], acc_full;
+  uint64_t full_a[PA_AS], empty_a[PA_AS], full_b[PA_RS], empty_b[PA_RS], full_g[PA_MAXGS], empty_g[PA_MAXGS], acc_full;
   uint32_t tmem_base;
 };
 
+template <int PA_GS>
 __global__ void __launch_bounds__(PA_THREADS, 2)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ CUtensorMap tm_bed, int m, int Np,
             int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
             double* __restrict__ t_raw, uint32_t tmem_cols, uint32_t col_a, int mode, int dbg) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // the 128-byte swizzle needs a 1 KB aligned base: declared, not padded for (the pad would cost the two co-resident
+  // CTAs their fourth ring slot); a misplaced window traps instead of corrupting the tiles
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) asm volatile("trap;");
   uint8_t* packed = smem;                            // [PA_GS][128 rows][128 B], 128-byte swizzle
   uint8_t* tileB = packed + PA_GS * PA_PACKED;
   const int tileB_bytes = NB * 128;
@@ -1455,7 +1459,19 @@ static int tc_encode_2d(TcState* s, CUtensorMap* map, void* base, uint64_t inner
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
-static inline int pa_smem_bytes(int nb) { return PA_RS * 4 * nb * 128 + PA_GS * PA_PACKED + (int)sizeof(PaSmem) + 1024; }
+static inline int pa_smem_bytes(int nb, int gs) { return PA_RS * 4 * nb * 128 + gs * PA_PACKED + (int)sizeof(PaSmem); }
+// Depth of pass A's genotype ring: the decode warps stall on HBM latency with fewer than four boxes in flight per CTA.
+// Two co-resident CTAs when four slots fit half an SM's shared memory (three as a last resort), else one CTA with as
+// deep a ring as fits.
+static inline int pa_ring(int nb) {
+  const int half = (233472 - 2048) / 2, whole = 232448 - 1024;
+  if (pa_smem_bytes(nb, 4) <= half) return 4;
+  if (pa_smem_bytes(nb, 3) <= half) return 3;
+  if (pa_smem_bytes(nb, 8) <= whole) return 8;
+  if (pa_smem_bytes(nb, 6) <= whole) return 6;
+  if (pa_smem_bytes(nb, 4) <= whole) return 4;
+  return 3;
+}
 static inline int pb_smem_bytes(int nc, int bs, int G = PB_G) { return G * PB_AS * TC_TILE_A + bs * nc * 128 + 4 * G * PB_PKG * 1024 + (int)sizeof(PbSmem) + 1024; }
 // Uq ring: `bs` tile slots in batches of 2^bzsh tiles that share one barrier pair.  Either a batch spans at least
 // one stage of every issuer (2^bzsh >= SI = G / MT), or there is no batching and bs is a multiple of SI (a slot is
@@ -1507,7 +1523,8 @@ static int tc_shape(const rhe_config& g, TcShape* o, int quiet) {
     const bool fits2 = g.n_bins * o->NCb <= 256 && pb_smem_bytes(o->NCb, 2, 2) <= pb_budget(2);
     if (fits2 && envG && atoi(envG) == 2) { o->G = 2; o->MT = 1; o->KG = g.n_bins; }
   }
-  if (pb_smem_bytes(o->NCb, o->G / o->MT, o->G) > pb_budget(o->G) || o->NBa > 256 || o->KG < 1 || o->KG > 255 ||
+  if (pb_smem_bytes(o->NCb, o->G / o->MT, o->G) > pb_budget(o->G) || o->NBa > 256 || pa_smem_bytes(o->NBa, 3) > 232448 - 1024 ||
+      o->KG < 1 || o->KG > 255 ||
       n_groups * o->KG * g.n_vec > PB_MAX_KB || n_groups * g.n_vec > 64) {
     if (!quiet)
       rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors x %d weight groups exceed the tensor kernels' "
@@ -1570,7 +1587,13 @@ int rhe_tc_create(rhe_ctx* c) {
   const int kg = s->KG < g.n_bins ? s->KG : g.n_bins;
   rc = tc_reserve_positions(c, s, g.n_ops * (round_up(g.max_block_snps, 128) + 128 * kg + 512));
   if (rc) return rc;
-  RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, pa_smem_bytes(s->NBa)));
+  {
+    const int gs = pa_ring(s->NBa), smem = pa_smem_bytes(s->NBa, gs);
+    if (gs == 8) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else if (gs == 6) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else if (gs == 4) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
   {
     int shb;
     const int smem = pb_smem_bytes(s->NCb, pb_ring(s->NCb, s->MT, s->G, &shb), s->G);
@@ -1625,14 +1648,18 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   int rc = tc_encode_2d(s, &tm_bed, const_cast<uint8_t*>(bed), (uint64_t)c->cfg.pitch_bytes, (uint64_t)m, 128);
   if (rc) return rc;
   const int dbg = RHE_DBG_ENV("PYRHE_TC_DEBUG_SKIPA", 0);
-  k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
-      s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq, c->t_raw,
-      pow2_cols((int)col_a + 32 * PA_AS), col_a, 0, dbg);
-  RHE_LAUNCH_CHECK(c);
-  if (c->cfg.n_ops == 2) {   // RHE-DOM: the same pass over the [g == 2] indicator operand
-    k_tc_pass_a<<<dim3(splits, tiles), PA_THREADS, pa_smem_bytes(s->NBa), st>>>(
-        s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, s->L, c->fill, s->col_dq,
-        c->t_raw + (size_t)m * c->R1, pow2_cols((int)col_a + 32 * PA_AS), col_a, 1, 0);
+  const int gs = pa_ring(s->NBa), smem = pa_smem_bytes(s->NBa, gs);
+  for (int mode = 0; mode < c->cfg.n_ops; ++mode) {      // RHE-DOM: the same pass over the [g == 2] indicator operand
+    double* t_out = c->t_raw + (size_t)mode * m * c->R1;
+    const uint32_t cols = pow2_cols((int)col_a + 32 * PA_AS);
+#define PA_LAUNCH(GS_)                                                                                               \
+    k_tc_pass_a<GS_><<<dim3(splits, tiles), PA_THREADS, smem, st>>>(s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, \
+                                                                     s->L, c->fill, s->col_dq, t_out, cols, col_a, mode, mode ? 0 : dbg)
+    if (gs == 8) PA_LAUNCH(8);
+    else if (gs == 6) PA_LAUNCH(6);
+    else if (gs == 4) PA_LAUNCH(4);
+    else PA_LAUNCH(3);
+#undef PA_LAUNCH
     RHE_LAUNCH_CHECK(c);
   }
   return RHE_OK;
