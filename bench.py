@@ -405,6 +405,7 @@ def main():
             rows, m = eng.block_view(eng.own[r])
             host[r * eng.max_m: r * eng.max_m + m].copy_(rows[:, : eng.row_bytes])
         torch.cuda.synchronize(dev)
+        rows = None                                            # (a view of the resident rows: must not outlive the engine)
         host_np = host.numpy()
 
         class CyclicRows:

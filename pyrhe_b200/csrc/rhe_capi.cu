@@ -625,24 +625,32 @@ static void launch_loo_small(const float* S, const float* P, int64_t len, double
 // iteration covers the positions {4 c + j}.  Differences are formed in fp64 from the fp32 inputs (exact); ~40
 // registers per thread leave the whole SM to loads in flight.  Memory bound: reads S and P once.
 // NBLK block partials P, P + p_stride, ... share one read of S (outputs out, out + out_stride, ...).
-template <int NT, int NBLK>
+template <int NT, int NBLK, int NX>
 __global__ void __launch_bounds__(256)
 k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int64_t p_stride, int E, int64_t len,
                double* __restrict__ out, int64_t out_stride) {
+  // E = 8 NT + NX estimates: the first 8 NT rows go through the FP64 tensor cores (for a Gram the A and B fragments of
+  // an 8-row tile are the same registers), NX (0 or 1) trailing rows through plain FP64 FMAs -- GENIE's 2 K + 1
+  // estimates (K = 8: 17) would otherwise pay for a third, almost empty, row tile in every tile pair.
   constexpr int NPAIR = NT * (NT + 1) / 2;
   double acc[NBLK][NPAIR][2];
+  double accx[NBLK][NX ? NT : 1], accxx[NBLK];
 #pragma unroll
-  for (int b = 0; b < NBLK; ++b)
+  for (int b = 0; b < NBLK; ++b) {
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) acc[b][p][0] = acc[b][p][1] = 0.0;
+#pragma unroll
+    for (int t = 0; t < (NX ? NT : 1); ++t) accx[b][t] = 0.0;
+    accxx[b] = 0.0;
+  }
   const int lane = threadIdx.x & 31, e = lane >> 2, c = lane & 3;
   const int64_t n16 = len >> 4;                      // len is a multiple of 16 (B * Np, Np a multiple of 512)
   const int64_t warp_id = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t it = warp_id; it < n16; it += n_warps) {
-    float4 v[NT], w[NBLK][NT];
+    float4 v[NT + NX], w[NBLK][NT + NX];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const int row = 8 * t + e;
+    for (int t = 0; t < NT + NX; ++t) {
+      const int row = t < NT ? 8 * t + e : 8 * NT;   // the trailing row: every lane reads its own four columns of it
       v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int b = 0; b < NBLK; ++b) w[b][t] = v[t];
@@ -657,9 +665,9 @@ k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int64_t
     }
 #pragma unroll
     for (int b = 0; b < NBLK; ++b) {
-      double d[NT][4];
+      double d[NT + NX][4];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < NT + NX; ++t) {
         d[t][0] = (double)v[t].x - (double)w[b][t].x; d[t][1] = (double)v[t].y - (double)w[b][t].y;
         d[t][2] = (double)v[t].z - (double)w[b][t].z; d[t][3] = (double)v[t].w - (double)w[b][t].w;
       }
@@ -674,19 +682,42 @@ k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int64_t
                          : "+d"(acc[b][p][0]), "+d"(acc[b][p][1]) : "d"(d[ti][j]), "d"(d[tj][j]));
           ++p;
         }
+      if (NX) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) accx[b][t] = fma(d[t][j], d[NT][j], accx[b][t]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) accxx[b] = fma(d[NT][j], d[NT][j], accxx[b]);
+      }
     }
   }
   // C fragment: row = lane / 4, columns 2 (lane % 4), + 1 of the (ti, tj) tile; block reduction, then one atomic per entry
   __shared__ double red[NPAIR][64];
+  __shared__ double redx[8 * NT + 1];
 #pragma unroll
   for (int b = 0; b < NBLK; ++b) {
     __syncthreads();
     for (int i = threadIdx.x; i < NPAIR * 64; i += blockDim.x) (&red[0][0])[i] = 0.0;
+    if (threadIdx.x < 8 * NT + 1) redx[threadIdx.x] = 0.0;
     __syncthreads();
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
       atomicAdd(&red[p][e * 8 + 2 * c], acc[b][p][0]);
       atomicAdd(&red[p][e * 8 + 2 * c + 1], acc[b][p][1]);
+    }
+    if (NX) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {                 // sum the four column quads of row 8 t + e
+        double x = accx[b][t];
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        if (c == 0) atomicAdd(&redx[8 * t + e], x);
+      }
+      double x = accxx[b];                           // every row group e holds the same four partial sums
+      x += __shfl_xor_sync(0xffffffffu, x, 1);
+      x += __shfl_xor_sync(0xffffffffu, x, 2);
+      if (lane == 0) atomicAdd(&redx[8 * NT], x);
     }
     __syncthreads();
     double* ob = out + (size_t)b * out_stride;
@@ -700,19 +731,50 @@ k_loo_gram_mma(const float* __restrict__ S, const float* __restrict__ P, int64_t
             if (ti != tj) atomicAdd(ob + bb * E + a, red[p][i]);
           }
         }
+    if (NX && 8 * NT < E) {
+      const int x = 8 * NT;
+      for (int i = threadIdx.x; i < 8 * NT; i += blockDim.x) {
+        atomicAdd(ob + x * E + i, redx[i]);
+        atomicAdd(ob + i * E + x, redx[i]);
+      }
+      if (threadIdx.x == 0) atomicAdd(ob + x * E + x, redx[x]);
+    }
   }
 }
 
-template <int NT>
+// Row tiling of n_est estimates: NT 8-row tensor-core tiles + NX trailing rows on the FP64 FMA pipe
+static inline void loo_tiling(int n_est, int* nt, int* nx) {
+  if (n_est > 8 && n_est % 8 == 1) { *nt = n_est / 8; *nx = 1; }
+  else { *nt = (n_est + 7) / 8; *nx = 0; }
+}
+
+template <int NT, int NX>
 static void launch_loo_mma(const float* S, const float* P, int64_t p_stride, int n_blk, int E, int64_t len, double* out,
                            int64_t out_stride, cudaStream_t st) {
   const int grid = 148 * 8;
-  switch (n_blk) {
-    case 4: k_loo_gram_mma<NT, 4><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
-    case 3: k_loo_gram_mma<NT, 3><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
-    case 2: k_loo_gram_mma<NT, 2><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
-    default: k_loo_gram_mma<NT, 1><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); break;
+  if constexpr (NT <= 2) {
+    if (n_blk == 4) { k_loo_gram_mma<NT, 4, NX><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); return; }
+    if (n_blk == 3) { k_loo_gram_mma<NT, 3, NX><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride); return; }
   }
+  if (n_blk == 2) k_loo_gram_mma<NT, 2, NX><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride);
+  else k_loo_gram_mma<NT, 1, NX><<<grid, 256, 0, st>>>(S, P, p_stride, E, len, out, out_stride);
+}
+
+// n_est <= 24; n_blk <= loo_share(n_est) blocks share the read of S
+static inline int loo_share(int n_est) {
+  int nt, nx;
+  loo_tiling(n_est, &nt, &nx);
+  return nt <= 2 ? 4 : 2;
+}
+static void launch_loo(const float* S, const float* P, int64_t p_stride, int n_blk, int E, int64_t len, double* out,
+                       int64_t out_stride, cudaStream_t st) {
+  int nt, nx;
+  loo_tiling(E, &nt, &nx);
+  if (nt == 1 && nx == 0) launch_loo_mma<1, 0>(S, P, p_stride, n_blk, E, len, out, out_stride, st);
+  else if (nt == 1) launch_loo_mma<1, 1>(S, P, p_stride, n_blk, E, len, out, out_stride, st);
+  else if (nt == 2 && nx == 0) launch_loo_mma<2, 0>(S, P, p_stride, n_blk, E, len, out, out_stride, st);
+  else if (nt == 2) launch_loo_mma<2, 1>(S, P, p_stride, n_blk, E, len, out, out_stride, st);
+  else launch_loo_mma<3, 0>(S, P, p_stride, n_blk, E, len, out, out_stride, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1021,9 +1083,10 @@ extern "C" int rhe_loo_gram_multi(rhe_ctx* c, const float* S, const float* P, in
   if (!c || !S || !P || !out) { rhe_set_error("rhe_loo_gram_multi: NULL argument"); return RHE_ERR_INVALID; }
   if (n_blocks < 1 || p_stride < 0 || out_stride < (int64_t)n_est * n_est) { rhe_set_error("rhe_loo_gram_multi: bad block count / strides"); return RHE_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  const bool mma = len % 16 == 0 && n_est >= 1 && n_est <= 16 && p_stride % 4 == 0 && !RHE_DBG_ENV("PYRHE_B200_LOO_SIMT", 0);
+  const bool mma = len % 16 == 0 && n_est >= 1 && n_est <= 24 && p_stride % 4 == 0 && !RHE_DBG_ENV("PYRHE_B200_LOO_SIMT", 0);
+  const int share = mma ? loo_share(n_est) : 1;      // blocks that share one read of S (three 8-row tiles: registers for two)
   for (int b0 = 0; b0 < n_blocks;) {
-    const int nb = mma ? (n_blocks - b0 < 4 ? n_blocks - b0 : 4) : 1;
+    const int nb = mma ? (n_blocks - b0 < share ? n_blocks - b0 : share) : 1;
     const float* Pb = P + (size_t)b0 * p_stride;
     double* ob = out + (size_t)b0 * out_stride;
     if (nb == 1) {
@@ -1031,8 +1094,7 @@ extern "C" int rhe_loo_gram_multi(rhe_ctx* c, const float* S, const float* P, in
       if (rc) return rc;
     } else {
       for (int b = 0; b < nb; ++b) RHE_CUDA(cudaMemsetAsync(ob + (size_t)b * out_stride, 0, sizeof(double) * n_est * n_est, st));
-      if (n_est <= 8) launch_loo_mma<1>(S, Pb, p_stride, nb, n_est, len, ob, out_stride, st);
-      else launch_loo_mma<2>(S, Pb, p_stride, nb, n_est, len, ob, out_stride, st);
+      launch_loo(S, Pb, p_stride, nb, n_est, len, ob, out_stride, st);
       RHE_LAUNCH_CHECK(c);
     }
     b0 += nb;
@@ -1083,9 +1145,7 @@ extern "C" int rhe_loo_gram(rhe_ctx* c, const float* S, const float* P, int32_t 
   RHE_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_est * n_est, st));
   // register-resident kernels for up to 8 estimates (8-byte loads: even length, always true for B * Np)
   if (len % 16 == 0 && n_est <= 24 && !RHE_DBG_ENV("PYRHE_B200_LOO_SIMT", 0)) {      // FP64 tensor-core Gram
-    if (n_est <= 8) launch_loo_mma<1>(S, P, 0, 1, n_est, len, out, 0, st);
-    else if (n_est <= 16) launch_loo_mma<2>(S, P, 0, 1, n_est, len, out, 0, st);
-    else launch_loo_mma<3>(S, P, 0, 1, n_est, len, out, 0, st);
+    launch_loo(S, P, 0, 1, n_est, len, out, 0, st);
     RHE_LAUNCH_CHECK(c);
     return RHE_OK;
   }

@@ -633,45 +633,91 @@ __device__ __forceinline__ void tmem_combine(uint32_t taddr, int stride, double 
   }
 }
 
+// TMEM reads of the epilogues without a "memory" clobber (with one, the compiler re-derives every address and re-reads
+// the kernel parameters after each access: 35 instructions per value instead of 15); the ordering the hardware needs is
+// expressed through the registers themselves.
+template <int W>
+__device__ __forceinline__ void tmem_ldw_nc(uint32_t taddr, int32_t (&v)[W]) {
+  static_assert(W == 2 || W == 4, "column chunk");
+  if constexpr (W == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+  }
+}
+// the loaded registers may be used only after the wait: every one is passed through an (empty) volatile asm behind it
+template <int L, int W>
+__device__ __forceinline__ void tmem_ld_fence(int32_t (&a)[L][W]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int j = 0; j < W; ++j) asm volatile("" : "+r"(a[l][j]));
+}
+__device__ __forceinline__ double lds_f64_nv(uint32_t addr) {     // not volatile: the scheduler may hoist and overlap these
+  double r;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
+  return r;
+}
+
+// One chunk of W adjacent columns of a non-empty bin for one individual (TMEM lane): limbs recombined exactly in fp64,
+// scale, mean term, row scale, one store and one RED per value.  `idx` is the individual's entry of the chunk's first
+// column in P / S (32-bit element index when the accumulators hold fewer than 2^31 floats, else 64-bit); successive
+// columns are `Np` floats apart.
+template <int L, int W, typename IDX>
+__device__ __forceinline__ void pb_chunk(uint32_t taddr, uint32_t stride, int nvalid, IDX Np, double rs, uint32_t dq_a,
+                                         uint32_t cs_a, float* __restrict__ P_out, float* __restrict__ S_accum,
+                                         bool wp, bool ws, IDX idx) {
+  int32_t a[L][W];
+#pragma unroll
+  for (int l = 0; l < L; ++l) tmem_ldw_nc<W>(taddr + (uint32_t)l * stride, a[l]);
+  tmem_ld_fence<L, W>(a);
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    if (j < nvalid) {
+      double val = (double)a[L - 1][j];
+#pragma unroll
+      for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
+      const float xf = (float)(rs * (val * lds_f64_nv(dq_a + 8u * (uint32_t)j) - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
+      if (wp) P_out[idx] = xf;
+      if (ws) atomicAdd(S_accum + idx, xf);            // result unused -> RED: no load round trip
+      idx += Np;
+    }
+  }
+}
+
 // Pass-B epilogue of one decode thread (TMEM lane = individual i): P[e][b][i] = rs_i * (acc * dq - cs) for the
-// bins k = par (mod SI) of M-tile q.  Columns are read eight at a time (one tcgen05.ld per limb row), the
+// bins k = par (mod SI) of M-tile q.  Columns are read four at a time (one tcgen05.ld per limb row), the
 // remainder of a row in pairs, so nothing is read beyond the limb rows of the (bin, tile) accumulator.
-template <int L>
+template <int L, typename IDX>
 __device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq_s, const double* cs_s, uint32_t trow, int i,
                                             int par, int SI, int q, int MT, int K, int K_total, int k0, int WG, int B, int Bp,
                                             int NC, int Np,
                                             const float* __restrict__ rowscale, int rs_stride,
                                             float* __restrict__ P_out, float* __restrict__ S_accum) {
-  for (int k = par; k < K; k += SI) {
-    const bool has = cnt[k] > 0;
-    const uint32_t tcol = trow + (uint32_t)((k * MT + q) * NC);
-    for (int wg = 0; wg < WG; ++wg) {                // weight group = RHS set (GxE) or operand (dominance) -> estimate wg * K + k
+  const bool wp = P_out != nullptr, ws = S_accum != nullptr;
+  const uint32_t dq0 = smem_u32(dq_s), cs0 = smem_u32(cs_s);
+  for (int wg = 0; wg < WG; ++wg) {                  // weight group = RHS set (GxE) or operand (dominance) -> estimate wg * K + k
+    const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
+    for (int k = par; k < K; k += SI) {
       const int e = wg * K_total + k0 + k;           // estimate index; k is local to this launch's bin group
-      const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
-      const size_t o0 = (size_t)e * B * Np + i;
-      // explicit shared-space loads: through the generic pointers these are LD.E with twice the latency
-      const uint32_t dq = smem_u32(dq_s + wg * B);
-      const uint32_t cs = smem_u32(cs_s + (wg * K + k) * B);
-      auto emit = [&](int b, double val) {
-        const float xf = has ? (float)(rs * (val * lds_f64(dq + 8u * (uint32_t)b) - lds_f64(cs + 8u * (uint32_t)b))) : 0.f;
-        const size_t o = o0 + (size_t)b * Np;
-        if (P_out) P_out[o] = xf;
-        if (S_accum && has) atomicAdd(S_accum + o, xf);   // result unused -> RED: no load round trip
-      };
+      IDX idx = (IDX)e * (IDX)B * (IDX)Np + (IDX)i;
+      if (cnt[k] <= 0) {                             // a bin without SNPs in this block: X (X^T Z) = 0
+        if (wp)
+          for (int b = 0; b < B; ++b, idx += (IDX)Np) P_out[idx] = 0.f;
+        continue;
+      }
+      const uint32_t base = trow + (uint32_t)((k * MT + q) * NC + wg * L * Bp);
+      uint32_t dq_a = dq0 + 8u * (uint32_t)(wg * B), cs_a = cs0 + 8u * (uint32_t)((wg * K + k) * B);
       int c0 = 0;
-      for (; c0 + 8 <= Bp; c0 += 8) {
-        double val[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (has) tmem_combine<L, 8>(tcol + (uint32_t)(wg * L * Bp + c0), Bp, val);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c0 + j < B) emit(c0 + j, val[j]);
+      for (; c0 + 4 <= Bp; c0 += 4) {
+        pb_chunk<L, 4, IDX>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, (IDX)Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
+        dq_a += 32u; cs_a += 32u; idx += (IDX)4 * (IDX)Np;
       }
       for (; c0 < Bp; c0 += 2) {
-        double val[2] = {0.0, 0.0};
-        if (has) tmem_combine<L, 2>(tcol + (uint32_t)(wg * L * Bp + c0), Bp, val);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (c0 + j < B) emit(c0 + j, val[j]);
+        pb_chunk<L, 2, IDX>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, (IDX)Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
+        dq_a += 16u; cs_a += 16u; idx += (IDX)2 * (IDX)Np;
       }
     }
   }
@@ -814,10 +860,13 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     PROF_ADD(5);
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
-    if (!(RHE_DBG(4))) switch (L) {
-      case 2: pb_epilogue<2>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
-      case 3: pb_epilogue<3>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
-      default: pb_epilogue<4>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum); break;
+    if (!(RHE_DBG(4))) {
+      // 32-bit element indices into P / S whenever the accumulators hold fewer than 2^31 floats (one IMAD.WIDE per access)
+      const bool small = (long long)WG * K_total * B * (long long)Np < (1ll << 31);
+#define PB_EPI(L_, T_) pb_epilogue<L_, T_>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum)
+      if (small) { if (L == 2) PB_EPI(2, uint32_t); else if (L == 3) PB_EPI(3, uint32_t); else PB_EPI(4, uint32_t); }
+      else { if (L == 2) PB_EPI(2, uint64_t); else if (L == 3) PB_EPI(3, uint64_t); else PB_EPI(4, uint64_t); }
+#undef PB_EPI
     }
     PROF_ADD(6);
     PROF_FLUSH(0);
@@ -948,35 +997,6 @@ struct P2Smem {
   int32_t vbin[P2_MAXSUB];        // virtual bin (operand * K + bin) of every sub-tile of an M-tile
 };
 
-__device__ __forceinline__ double lds_f64_nv(uint32_t addr) {     // not volatile: the scheduler may hoist and overlap these
-  double r;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
-  return r;
-}
-
-// The drain warps are the serial resource of this kernel (every bin of every M-tile passes through them), so their code
-// is written to stay short: the TMEM accesses carry no "memory" clobber (with one, the compiler re-derives every address
-// and re-reads the kernel parameters after each access: 35 instructions per value instead of 15), and the ordering the
-// hardware needs is expressed through the registers themselves.
-template <int W>
-__device__ __forceinline__ void tmem_ldw_nc(uint32_t taddr, int32_t (&v)[W]) {
-  static_assert(W == 2 || W == 4, "column chunk");
-  if constexpr (W == 4) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
-  } else {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
-  }
-}
-// the loaded registers may be used only after the wait: every one is passed through an (empty) volatile asm behind it
-template <int L, int W>
-__device__ __forceinline__ void tmem_ld_fence(int32_t (&a)[L][W]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;");
-#pragma unroll
-  for (int l = 0; l < L; ++l)
-#pragma unroll
-    for (int j = 0; j < W; ++j) asm volatile("" : "+r"(a[l][j]));
-}
 template <int W>
 __device__ __forceinline__ void tmem_zero_nc(uint32_t taddr) {     // zero W columns of this thread's lane (completion: tmem_st_wait)
   const uint32_t z = 0u;

@@ -276,6 +276,7 @@ class RheEngine:
         #: use the individual-major copies where they exist (False: pass B always gathers SNP-major rows)
         self.use_fast_layout = True
         self.gt = {}
+        self.S = self.P_all = None
         self._row_off = {}
         cur = 0
         for j in self.own:
@@ -358,6 +359,7 @@ class RheEngine:
             self.counts = torch.zeros((rows, 4), dtype=torch.int32, device=self.device)
             self._counted = set()
             self.gt = {}
+            self.reserve_state()
             if ring_blocks is None and fast_layout:
                 self._alloc_fast_layout(reserve_bytes)
         return self.bed
@@ -369,13 +371,26 @@ class RheEngine:
         takes the gather kernel; results are identical either way."""
         free_b, _ = torch.cuda.mem_get_info(self.device)
         state = self.plan.E * self.plan.B * self.Np * 4
-        budget = free_b - reserve_bytes - 3 * state - (len(self.own) * state if self.store_partials else 0)
+        budget = free_b - reserve_bytes - 3 * state      # S and the stored partials are allocated already (reserve_state)
         for j in self.own:
             need = int(self.lib.rhe_block_fast_bytes(self._ctx, self._plans[j]))
             if need <= 0 or need > budget:
                 break
             self.gt[j] = torch.empty(need, dtype=torch.uint8, device=self.device)
             budget -= need
+
+    def reserve_state(self):
+        """The accumulators of a pass -- totals `S [E, B, Np]` and, with stored partials, `P_all [own blocks, E, B, Np]`
+        (16 GB at config 5 on one GPU) -- allocated once and reused by every `run()`; `alloc_genotypes` calls this
+        before it sizes the individual-major copies, so the first pass of a model run allocates nothing."""
+        plan = self.plan
+        with torch.cuda.device(self.device):
+            if self.S is None:
+                self.S = torch.empty((plan.E, plan.B, self.Np), dtype=torch.float32, device=self.device)
+            if self.store_partials and self.P_all is None:
+                self.P_all = torch.empty((max(len(self.own), 1), plan.E, plan.B, self.Np), dtype=torch.float32,
+                                         device=self.device)
+        return self.S, (self.P_all if self.store_partials else None)
 
     def genotype_bytes(self) -> int:
         if self.bed is None:
@@ -479,17 +494,14 @@ class RheEngine:
         if upload is None and self.ring_blocks is not None and self.ring_blocks < len(self.own):
             raise _lib.RheError("genotypes live in a ring: run() needs the streamer (upload=...)")
         with torch.cuda.device(dev):
-            self.S = self.P_all = None                 # the previous run's state goes back to the allocator first
-            S = torch.zeros((E, B, Np), dtype=torch.float32, device=dev)
+            S, P_all = self.reserve_state()            # the same buffers every run: no allocation inside a pass
+            S.zero_()
             G_blk = torch.zeros((J, E_reg, Rs, Rs), dtype=torch.float64, device=dev)
             XX = torch.zeros((J + 1, E, E), dtype=torch.float64, device=dev)
-            P_all = None
-            if self.store_partials:
+            if P_all is not None and E > E_reg:
                 # every (estimate, column) row of a block partial is fully written by pass B; only the NxE row
                 # (no genotype contribution) has to be zeroed
-                P_all = torch.empty((max(len(self.own), 1), E, B, Np), dtype=torch.float32, device=dev)
-                if E > E_reg:
-                    P_all[:, E_reg:].zero_()
+                P_all[:, E_reg:].zero_()
             self._pass(upload, lambda jl, j: self._accumulate(j, P_all[jl] if self.store_partials else None, S, G_blk[j]))
             if self.world > 1:
                 allreduce_sum([S, G_blk], self.pg)

@@ -279,3 +279,28 @@ def test_individual_major_fast_path_equals_gather(name):
     np.testing.assert_allclose(a[2], b[2], rtol=0, atol=2e-6 * np.abs(b[2]).max())
     np.testing.assert_allclose(a[0]["XX"], b[0]["XX"], rtol=1e-6)
     np.testing.assert_array_equal(a[0]["G_blk"], a[0]["G_blk"])
+
+
+@pytest.mark.parametrize("n_est", [1, 7, 8, 9, 16, 17, 23, 24])
+def test_leave_one_out_gram_against_numpy(n_est):
+    """`rhe_loo_gram_multi` (base.py:578-581 after the aggregate of base.py:483-486): out[j][a][c] = <S_a - P_ja, S_c - P_jc>
+    for several stored blocks per launch, every row tiling of the FP64 tensor-core kernel (one to three 8-row tiles, with and
+    without the trailing row that GENIE's 2 K + 1 estimates add) against float64 numpy."""
+    import ctypes as C
+    import torch
+    from pyrhe_b200 import _lib
+    p = oracle_problem("rhe_nocov_mean")
+    eng, _, _ = make_engine(p, plan_for(p), kernel_path=1)
+    lib = _lib.load()
+    rng = np.random.default_rng(n_est)
+    length, n_blocks = 16 * 37, 7
+    S = rng.standard_normal((n_est, length)).astype(np.float32) * 3
+    P = rng.standard_normal((n_blocks, n_est, length)).astype(np.float32)
+    dS, dP = torch.from_numpy(S).cuda(), torch.from_numpy(P).cuda()
+    out = torch.full((n_blocks, n_est, n_est), 123.0, dtype=torch.float64, device="cuda")
+    _lib.check(lib.rhe_loo_gram_multi(eng._ctx, _lib.ptr(dS), _lib.ptr(dP), n_est * length, n_blocks, n_est, length,
+                                      _lib.ptr(out), n_est * n_est, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    D = S[None].astype(np.float64) - P.astype(np.float64)
+    want = np.einsum("jal,jcl->jac", D, D)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
+    eng.close()
