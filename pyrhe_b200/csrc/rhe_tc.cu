@@ -47,9 +47,11 @@ struct TcPlan {
 struct TcState {
   int L = 3;            // limbs per fixed-point value (PYRHE_B200_LIMBS)
   int F = 22;           // fixed-point magnitude bits: |q| <= 2^F, F = 8 L - 2
-  int R1p = 0;          // RHS columns rounded up to 4
+  int Rc = 0;           // RHS columns per pass-A launch (all R1 of them unless their limb columns exceed the MMA / shared-memory limits)
+  int R1p = 0;          // Rc rounded up to 4
   int NBa = 0;          // pass A MMA N  = round16(L * R1p)
-  int Bp = 0;           // pass-B columns rounded up to 2
+  int Bc = 0;           // pass-B vector columns per launch (all of them unless groups x vectors exceeds 64: then in chunks)
+  int Bp = 0;           // Bc rounded up to 2
   int NCb = 0;          // pass B MMA N per (bin, M-tile) = round16(L * Bp)
   int MT = 2;           // 128-individual M-tiles per pass-B CTA
   int G = 4;            // pass-B decode groups per CTA: 4 (one CTA per SM) or 2 (two co-resident CTAs per SM)
@@ -388,8 +390,9 @@ struct PaSmem {
 template <int PA_GS>
 __global__ void __launch_bounds__(PA_THREADS, 2)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ CUtensorMap tm_bed, int m, int Np,
-            int NB, int R1, int R1p, int L, const uint8_t* __restrict__ fill, const double* __restrict__ col_dq,
-            double* __restrict__ t_raw, uint32_t tmem_cols, uint32_t col_a, int mode, int dbg) {
+            int NB, int R1, int R1p, int L, int c_lo, int Rv, int rq_row0, const uint8_t* __restrict__ fill,
+            const double* __restrict__ col_dq, double* __restrict__ t_raw, uint32_t tmem_cols, uint32_t col_a, int mode, int dbg) {
+  // the launch's RHS columns [c_lo, c_lo + Rv) of R1 sit in the Rq rows [rq_row0, rq_row0 + NB)
   // the 128-byte swizzle needs a 1 KB aligned base: declared, not padded for (the pad would cost the two co-resident
   // CTAs their fourth ring slot); a misplaced window traps instead of corrupting the tiles
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -495,7 +498,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
       if (snp < m) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < R1) atomicAdd(t_raw + (size_t)snp * R1 + c0 + j, val[j] * col_dq[c0 + j]);
+          if (c0 + j < Rv) atomicAdd(t_raw + (size_t)snp * R1 + c_lo + c0 + j, val[j] * col_dq[c_lo + c0 + j]);
       }
     }
     PROF_ADD(6);
@@ -516,7 +519,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
             mbar_expect_tx_s(fb + 8u * sl, 4u * (uint32_t)tileB_bytes);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              tma_load_2d_s(tileB_s + (sl * 4u + (uint32_t)q) * (uint32_t)tileB_bytes, &tm_rq, fb + 8u * sl, x + q * 128, 0);
+              tma_load_2d_s(tileB_s + (sl * 4u + (uint32_t)q) * (uint32_t)tileB_bytes, &tm_rq, fb + 8u * sl, x + q * 128, rq_row0);
           }
         }
         __syncwarp();
@@ -692,8 +695,8 @@ __device__ __forceinline__ void pb_chunk(uint32_t taddr, uint32_t stride, int nv
 // remainder of a row in pairs, so nothing is read beyond the limb rows of the (bin, tile) accumulator.
 template <int L, typename IDX>
 __device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq_s, const double* cs_s, uint32_t trow, int i,
-                                            int par, int SI, int q, int MT, int K, int K_total, int k0, int WG, int B, int Bp,
-                                            int NC, int Np,
+                                            int par, int SI, int q, int MT, int K, int K_total, int k0, int WG, int B, int Bs,
+                                            int b0, int Bp, int NC, int Np,
                                             const float* __restrict__ rowscale, int rs_stride,
                                             float* __restrict__ P_out, float* __restrict__ S_accum) {
   const bool wp = P_out != nullptr, ws = S_accum != nullptr;
@@ -702,7 +705,7 @@ __device__ __forceinline__ void pb_epilogue(const int32_t* cnt, const double* dq
     const double rs = (double)rowscale[(size_t)wg * rs_stride + i];
     for (int k = par; k < K; k += SI) {
       const int e = wg * K_total + k0 + k;           // estimate index; k is local to this launch's bin group
-      IDX idx = (IDX)e * (IDX)B * (IDX)Np + (IDX)i;
+      IDX idx = ((IDX)e * (IDX)Bs + (IDX)b0) * (IDX)Np + (IDX)i;
       if (cnt[k] <= 0) {                             // a bin without SNPs in this block: X (X^T Z) = 0
         if (wp)
           for (int b = 0; b < B; ++b, idx += (IDX)Np) P_out[idx] = 0.f;
@@ -729,8 +732,8 @@ template <int MT, int G>
 __global__ void __launch_bounds__(PB_THREADS_OF(G), G == 2 ? 2 : 1)
 k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict__ bed, int pitch, int Np, int n_stage,
             const int32_t* __restrict__ meta_v, int n_chunk, const int32_t* __restrict__ stage_info,
-            const int32_t* __restrict__ bin_count, int K, int K_total, int k0, int WG, int B, int Bp, int L, int NC,
-            int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
+            const int32_t* __restrict__ bin_count, int K, int K_total, int k0, int WG, int B, int Bs, int b0, int Bp, int L,
+            int NC, int F, const unsigned int* __restrict__ wmax, const double* __restrict__ cs,
             const float* __restrict__ rowscale, int rs_stride, float* __restrict__ P_out, float* __restrict__ S_accum,
             uint32_t tmem_cols, int a_major, int kcap, int bs, int bzsh, int dbg) {
   if (RHE_DBG(16)) n_stage = 0;
@@ -755,16 +758,16 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     fence_barrier_init();
   }
   if (warp == PB_DW + 1) tmem_alloc(&sm->tmem_base, tmem_cols);
-  for (int i = threadIdx.x; i < WG * K * B; i += PB_THREADS) {   // mean terms of this group's bins [k0, k0 + K)
-    const int wg = i / (K * B), rem = i - wg * (K * B);
-    sm->cs[i] = cs[(size_t)(wg * K_total + k0) * B + rem];
+  for (int i = threadIdx.x; i < WG * K * B; i += PB_THREADS) {   // mean terms of this group's bins [k0, k0 + K), columns [b0, b0 + B)
+    const int wg = i / (K * B), rem = i - wg * (K * B), kl = rem / B, b = rem - kl * B;
+    sm->cs[i] = cs[(size_t)(wg * K_total + k0 + kl) * Bs + b0 + b];
   }
   for (int i = threadIdx.x; i < K; i += PB_THREADS) sm->cnt[i] = bin_count[i];
   // power-of-two dequantisation factor 2^(e - F), 2^e > max |w| (same rule as k_tc_quant_w)
   // A non-finite weight (a monomorphic SNP: base.py:291-296 divides by sqrt(mu (1 - mu / 2)) = 0) has no fixed-point
   // image; it poisons its whole column exactly as the NaN does in the reference's products.
   for (int i = threadIdx.x; i < WG * B; i += PB_THREADS) {
-    const int ex = (int)((wmax[i] >> 23) & 255u);
+    const int ex = (int)((wmax[(i / B) * Bs + b0 + i % B] >> 23) & 255u);
     sm->dq[i] = ex == 255 ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex - 126 - F);
   }
   tc_fence_before();
@@ -862,8 +865,8 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
     const int i = i0 + q * 128 + (t & ~15) + tc_perm16(t & 15);
     if (!(RHE_DBG(4))) {
       // 32-bit element indices into P / S whenever the accumulators hold fewer than 2^31 floats (one IMAD.WIDE per access)
-      const bool small = (long long)WG * K_total * B * (long long)Np < (1ll << 31);
-#define PB_EPI(L_, T_) pb_epilogue<L_, T_>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum)
+      const bool small = (long long)WG * K_total * Bs * (long long)Np < (1ll << 31);
+#define PB_EPI(L_, T_) pb_epilogue<L_, T_>(sm->cnt, sm->dq, sm->cs, trow, i, par, SI, q, MT, K, K_total, k0, WG, B, Bs, b0, Bp, NC, Np, rowscale, rs_stride, P_out, S_accum)
       if (small) { if (L == 2) PB_EPI(2, uint32_t); else if (L == 3) PB_EPI(3, uint32_t); else PB_EPI(4, uint32_t); }
       else { if (L == 2) PB_EPI(2, uint64_t); else if (L == 3) PB_EPI(3, uint64_t); else PB_EPI(4, uint64_t); }
 #undef PB_EPI
@@ -1398,9 +1401,10 @@ __device__ __forceinline__ void tc_limbs(long long q, int L, int8_t* out, size_t
 
 // One block per RHS column: max |R|, power-of-two scale, int8 limbs in the permuted individual order.
 __global__ void __launch_bounds__(256)
-k_tc_quant_rhs(const float* __restrict__ rhs, int Np, int R1p, int L, int F, int8_t* __restrict__ rq,
+k_tc_quant_rhs(const float* __restrict__ rhs, int Np, int Rc, int R1p, int NB, int L, int F, int8_t* __restrict__ rq,
                double* __restrict__ col_dq) {
-  const int c = blockIdx.x;
+  // column c = chunk ch, local column cl: limb l at row ch * NB + l * R1p + cl of rq
+  const int c = blockIdx.x, ch = c / Rc, cl = c - ch * Rc;
   const float* col = rhs + (size_t)c * Np;
   __shared__ float red[8];
   __shared__ int s_e;
@@ -1419,7 +1423,7 @@ k_tc_quant_rhs(const float* __restrict__ rhs, int Np, int R1p, int L, int F, int
   for (int i = threadIdx.x; i < Np; i += 256) {
     long long q = llrint(ldexp((double)col[i], F - e));
     const int pos = (i & ~15) | tc_invperm16(i & 15);
-    tc_limbs(q, L, rq + (size_t)c * Np + pos, (size_t)R1p * Np);
+    tc_limbs(q, L, rq + (size_t)(ch * NB + cl) * Np + pos, (size_t)R1p * Np);
   }
 }
 
@@ -1442,9 +1446,10 @@ __global__ void k_tc_wmax(const float* __restrict__ w1, int m, int B, unsigned i
 // (weight w1, with w2 = 2 w1 + extra); mode 1 multiplies the [g == 2] indicator operand (weight extra = w2 - 2 w1,
 // non-zero only for the dominance group) and occupies positions [n_pos, 2 n_pos).
 __global__ void k_tc_quant_w(const float* __restrict__ w1, const float* __restrict__ w2, const int32_t* __restrict__ pos_rows,
-                             int n_pos, int cap_pos, int m, int WG, int n_modes, int B, int Bp, int L, int F,
+                             int n_pos, int cap_pos, int m, int WG, int n_modes, int B, int Bs, int b0, int Bp, int L, int F,
                              const unsigned int* __restrict__ wmax, int8_t* __restrict__ uq,
                              const uint8_t* __restrict__ fill, int32_t* __restrict__ meta_v, int SI, int n_chunk) {
+  // B columns [b0, b0 + B) of the Bs vector columns
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pos * B * WG * n_modes) return;
   const int p = idx % n_pos, b = (idx / n_pos) % B, wg = (idx / (n_pos * B)) % WG, mode = idx / (n_pos * B * WG);
@@ -1455,10 +1460,10 @@ __global__ void k_tc_quant_w(const float* __restrict__ w1, const float* __restri
     meta_v[((((size_t)par * n_chunk + (u >> 2)) * 128 + t) << 2) + (u & 3)] =
         row >= 0 ? (row | ((int)fill[row] << 24) | (mode << 26)) : -1;
   }
-  const int e = (int)((wmax[wg * B + b] >> 23) & 255u) - 126;   // one fixed-point scale per (weight group, column)
+  const int e = (int)((wmax[wg * Bs + b0 + b] >> 23) & 255u) - 126;   // one fixed-point scale per (weight group, column)
   long long q = 0ll;
   if (row >= 0) {
-    const size_t o = ((size_t)wg * m + row) * B + b;
+    const size_t o = ((size_t)wg * m + row) * Bs + b0 + b;
     const double w = mode == 0 ? (double)w1[o] : (double)w2[o] - 2.0 * (double)w1[o];
     q = llrint(ldexp(w, F - e));
   }
@@ -1516,7 +1521,7 @@ static int p2_smem_of(const TcState* s);
 
 // Shape plan of the tensor kernels for one configuration (pure host arithmetic: shared by rhe_tc_supported and
 // rhe_tc_create so that the Python side never has to mirror the limits).
-struct TcShape { int L, F, R1p, NBa, Bp, NCb, MT, G, KG; };
+struct TcShape { int L, F, Rc, R1p, NBa, Bc, Bp, NCb, MT, G, KG; };
 
 static int tc_shape(const rhe_config& g, TcShape* o, int quiet) {
   const int R1 = g.n_sets * g.n_cols_set, n_groups = g.n_ops * g.n_sets;
@@ -1524,32 +1529,50 @@ static int tc_shape(const rhe_config& g, TcShape* o, int quiet) {
   o->L = envL ? atoi(envL) : 3;
   if (o->L < 2 || o->L > 4) { if (!quiet) rhe_set_error("PYRHE_B200_LIMBS must be 2..4"); return RHE_ERR_INVALID; }
   o->F = 8 * o->L - 2;
-  o->R1p = round_up(R1, 4);
-  o->NBa = round_up(o->L * o->R1p, 16);
-  o->Bp = round_up(g.n_vec, 2);
-  o->NCb = round_up(n_groups * o->L * o->Bp, 16);   // weight groups (RHS sets) are stacked along N
-  o->G = PB_G;
-  // M-tiles per CTA and bins per launch: everything in one launch when the accumulators fit (two tiles if possible),
-  // otherwise bin groups of two-tile CTAs.
-  if (g.n_bins * 2 * o->NCb <= 512) { o->MT = 2; o->KG = g.n_bins; }
-  else if (g.n_bins * o->NCb <= 512) { o->MT = 1; o->KG = g.n_bins; }
-  else if (2 * o->NCb <= 512) { o->MT = 2; o->KG = 512 / (2 * o->NCb); }
-  else { o->MT = 1; o->KG = o->NCb <= 512 ? 512 / o->NCb : 0; }
+  // pass A takes all RHS columns in one launch when their limb columns fit one MMA (N <= 256) and the Rq ring fits the
+  // shared memory; otherwise in balanced chunks of Rc columns, each a pass of its own over the block
+  for (int n_ch = 1;; ++n_ch) {
+    o->Rc = round_up(rhe_div_up(R1, n_ch), 4);
+    o->R1p = o->Rc;
+    o->NBa = round_up(o->L * o->R1p, 16);
+    if ((o->NBa <= 256 && pa_smem_bytes(o->NBa, 3) <= 232448 - 1024) || o->Rc <= 4) break;
+  }
+  // pass B runs over all vector columns at once when they fit -- groups x vectors <= 64 (shared-memory tables), MMA
+  // N <= 256, the Uq ring within the shared memory the decoded tiles leave -- otherwise in chunks of Bc columns, each a
+  // pass of its own over the block's rows (e.g. RHE-DOM / GENIE with the reference's 50 random vectors).
+  auto plan_b = [&](int bc) {
+    o->Bc = bc;
+    o->Bp = round_up(o->Bc, 2);
+    o->NCb = round_up(n_groups * o->L * o->Bp, 16);   // weight groups (RHS sets) are stacked along N
+    o->G = PB_G;
+    // M-tiles per CTA and bins per launch: everything in one launch when the accumulators fit (two tiles if possible),
+    // otherwise bin groups of two-tile CTAs.
+    if (g.n_bins * 2 * o->NCb <= 512) { o->MT = 2; o->KG = g.n_bins; }
+    else if (g.n_bins * o->NCb <= 512) { o->MT = 1; o->KG = g.n_bins; }
+    else if (2 * o->NCb <= 512) { o->MT = 2; o->KG = 512 / (2 * o->NCb); }
+    else { o->MT = 1; o->KG = o->NCb <= 512 ? 512 / o->NCb : 0; }
+    if (o->KG > 0 && n_groups * o->KG * o->Bc > PB_MAX_KB) o->KG = PB_MAX_KB / (n_groups * o->Bc);   // per-(bin, column) mean terms staged in shared memory
+    return o->NCb <= 256 && o->KG >= 1 && pb_smem_bytes(o->NCb, o->G / o->MT, o->G) <= pb_budget(o->G);
+  };
+  int bc = n_groups * g.n_vec <= 64 ? g.n_vec : (64 / n_groups) & ~1;
+  while (bc > 2 && !plan_b(bc)) bc = (bc - 1) & ~1;
+  plan_b(bc);
   {
     // Optional variant (PYRHE_B200_PASSB_GROUPS=2): two half-size CTAs per SM (one M-tile, two decode groups, 256 TMEM
     // columns each), so that the epilogue of one overlaps the main loop of the other.  Measured equal to the default
     // on config 5, so it stays opt-in.
     const char* envG = getenv("PYRHE_B200_PASSB_GROUPS");
-    const bool fits2 = g.n_bins * o->NCb <= 256 && pb_smem_bytes(o->NCb, 2, 2) <= pb_budget(2);
+    const bool fits2 = o->Bc == g.n_vec && g.n_bins * o->NCb <= 256 && pb_smem_bytes(o->NCb, 2, 2) <= pb_budget(2);
     if (fits2 && envG && atoi(envG) == 2) { o->G = 2; o->MT = 1; o->KG = g.n_bins; }
   }
   if (pb_smem_bytes(o->NCb, o->G / o->MT, o->G) > pb_budget(o->G) || o->NBa > 256 || pa_smem_bytes(o->NBa, 3) > 232448 - 1024 ||
       o->KG < 1 || o->KG > 255 ||
-      n_groups * o->KG * g.n_vec > PB_MAX_KB || n_groups * g.n_vec > 64) {
+      n_groups * o->KG * o->Bc > PB_MAX_KB || o->Bc < 1) {
     if (!quiet)
       rhe_set_error("RHE_PATH_TCGEN05: %d RHS columns / %d bins x %d vectors x %d weight groups exceed the tensor kernels' "
-                    "TMEM / shared-memory layout (pass A: %d limb columns <= 256; pass B: %d x %d <= 64 vector columns)",
-                    R1, g.n_bins, g.n_vec, n_groups, o->NBa, n_groups, g.n_vec);
+                    "TMEM / shared-memory layout (pass A: %d limb columns <= 256 and its Rq ring within 227 KB; pass B: "
+                    "%d limb columns per bin <= 512)",
+                    R1, g.n_bins, g.n_vec, n_groups, o->NBa, o->NCb);
     return RHE_ERR_UNSUPPORTED;
   }
   return RHE_OK;
@@ -1582,7 +1605,7 @@ int rhe_tc_create(rhe_ctx* c) {
   int rc = tc_shape(g, &sh, 0);
   if (rc) return rc;
   TcState* s = new TcState();
-  s->L = sh.L; s->F = sh.F; s->R1p = sh.R1p; s->NBa = sh.NBa; s->Bp = sh.Bp; s->NCb = sh.NCb; s->MT = sh.MT; s->G = sh.G; s->KG = sh.KG;
+  s->L = sh.L; s->F = sh.F; s->Rc = sh.Rc; s->R1p = sh.R1p; s->NBa = sh.NBa; s->Bc = sh.Bc; s->Bp = sh.Bp; s->NCb = sh.NCb; s->MT = sh.MT; s->G = sh.G; s->KG = sh.KG;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
@@ -1596,11 +1619,11 @@ int rhe_tc_create(rhe_ctx* c) {
   c->tc = s;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
-  alloc((void**)&s->rq, (size_t)s->NBa * c->Np);
+  alloc((void**)&s->rq, (size_t)s->NBa * rhe_div_up(c->R1, s->Rc) * c->Np);
   alloc((void**)&s->col_dq, sizeof(double) * c->R1);
   alloc((void**)&s->wmax, sizeof(unsigned int) * c->n_groups * g.n_vec);
   if (e != cudaSuccess) { rhe_set_error("tensor-core workspace allocation failed: %s", cudaGetErrorString(e)); return RHE_ERR_CUDA; }
-  rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa, (uint32_t)s->NBa);
+  rc = tc_encode_2d(s, &s->tm_rq, s->rq, (uint64_t)c->Np, (uint64_t)s->NBa * (uint64_t)rhe_div_up(c->R1, s->Rc), (uint32_t)s->NBa);
   if (rc) return rc;
   // pass-B staging for the largest block of a one-bin-per-SNP annotation (every bin padded to 128 rows); plans with
   // overlapping annotations grow it at plan creation
@@ -1640,7 +1663,7 @@ void rhe_tc_destroy(rhe_ctx* c) {
 
 int rhe_tc_set_rhs(rhe_ctx* c, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
-  k_tc_quant_rhs<<<c->R1, 256, 0, st>>>(c->rhs, c->Np, s->R1p, s->L, s->F, s->rq, s->col_dq);
+  k_tc_quant_rhs<<<c->R1, 256, 0, st>>>(c->rhs, c->Np, s->Rc, s->R1p, s->NBa, s->L, s->F, s->rq, s->col_dq);
   RHE_LAUNCH_CHECK(c);
   return RHE_OK;
 }
@@ -1669,18 +1692,21 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   if (rc) return rc;
   const int dbg = RHE_DBG_ENV("PYRHE_TC_DEBUG_SKIPA", 0);
   const int gs = pa_ring(s->NBa), smem = pa_smem_bytes(s->NBa, gs);
+  const uint32_t cols = pow2_cols((int)col_a + 32 * PA_AS);
   for (int mode = 0; mode < c->cfg.n_ops; ++mode) {      // RHE-DOM: the same pass over the [g == 2] indicator operand
     double* t_out = c->t_raw + (size_t)mode * m * c->R1;
-    const uint32_t cols = pow2_cols((int)col_a + 32 * PA_AS);
-#define PA_LAUNCH(GS_)                                                                                               \
-    k_tc_pass_a<GS_><<<dim3(splits, tiles), PA_THREADS, smem, st>>>(s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, \
-                                                                     s->L, c->fill, s->col_dq, t_out, cols, col_a, mode, mode ? 0 : dbg)
-    if (gs == 8) PA_LAUNCH(8);
-    else if (gs == 6) PA_LAUNCH(6);
-    else if (gs == 4) PA_LAUNCH(4);
-    else PA_LAUNCH(3);
+    for (int ch = 0; ch * s->Rc < c->R1; ++ch) {          // one pass per chunk of RHS columns (a single one as a rule)
+      const int c_lo = ch * s->Rc, rv = c->R1 - c_lo < s->Rc ? c->R1 - c_lo : s->Rc;
+#define PA_LAUNCH(GS_)                                                                                                 \
+      k_tc_pass_a<GS_><<<dim3(splits, tiles), PA_THREADS, smem, st>>>(s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, \
+          s->L, c_lo, rv, ch * s->NBa, c->fill, s->col_dq, t_out, cols, col_a, mode, mode ? 0 : dbg)
+      if (gs == 8) PA_LAUNCH(8);
+      else if (gs == 6) PA_LAUNCH(6);
+      else if (gs == 4) PA_LAUNCH(4);
+      else PA_LAUNCH(3);
 #undef PA_LAUNCH
-    RHE_LAUNCH_CHECK(c);
+      RHE_LAUNCH_CHECK(c);
+    }
   }
   return RHE_OK;
 }
@@ -1771,12 +1797,6 @@ static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, co
   if (n_modes * n_pos > s->cap_pos) { rhe_set_error("pass B staging smaller than the plan (plan of another context?)"); return RHE_ERR_STATE; }
   const int n_stage = n_modes * n_pos / 128, SI = s->G / s->MT;
   const int n_chunk = rhe_div_up(rhe_div_up(n_stage, SI), 4);       // chunks of four own stages per decode group
-  if (n_pos > 0) {
-    k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B * c->n_groups * n_modes, 256), 256, 0, st>>>(
-        c->w1, c->w2, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, n_modes, B, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill,
-        s->pos_meta, SI, n_chunk);
-    RHE_LAUNCH_CHECK(c);
-  }
   const uint32_t cols = pow2_cols(kn * s->MT * s->NCb);
   int bzsh = 0;
   const int bs = pb_ring(s->NCb, s->MT, s->G, &bzsh), smem = pb_smem_bytes(s->NCb, bs, s->G);
@@ -1784,16 +1804,25 @@ static int tc_pass_b_group(rhe_ctx* c, TcState* s, const uint8_t* bed, int m, co
   const int kcap = RHE_DBG_ENV("PYRHE_TC_DEBUG_KSTEPS", 4);
   const int dbg = RHE_DBG_ENV("PYRHE_TC_DEBUG_SKIP", 0);
   const int rs_stride = g.n_sets == 2 ? c->Np : 0;
+  for (int b0 = 0; b0 < B; b0 += s->Bc) {              // one pass per chunk of vector columns (a single one as a rule)
+    const int bc = B - b0 < s->Bc ? B - b0 : s->Bc;
+    if (n_pos > 0) {
+      k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * bc * c->n_groups * n_modes, 256), 256, 0, st>>>(
+          c->w1, c->w2, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, n_modes, bc, B, b0, s->Bp, s->L, s->F, s->wmax, s->uq,
+          c->fill, s->pos_meta, SI, n_chunk);
+      RHE_LAUNCH_CHECK(c);
+    }
 #define PB_LAUNCH(MT_, G_)                                                                                                   \
-  k_tc_pass_b<MT_, G_><<<c->Np / (128 * MT_), PB_THREADS_OF(G_), smem, st>>>(                                                \
-      s->tm_uq, bed, g.pitch_bytes, c->Np, n_stage, s->pos_meta, n_chunk, meta->stage_info, meta->bin_count, kn, K, k0,      \
-      c->n_groups, B, s->Bp, s->L, s->NCb, s->F, s->wmax, c->cs, c->rowscale, rs_stride, P_out, S_accum, cols, a_major,      \
-      kcap, bs, bzsh, dbg)
-  if (s->G == 2) PB_LAUNCH(1, 2);
-  else if (s->MT == 2) PB_LAUNCH(2, 4);
-  else PB_LAUNCH(1, 4);
+    k_tc_pass_b<MT_, G_><<<c->Np / (128 * MT_), PB_THREADS_OF(G_), smem, st>>>(                                              \
+        s->tm_uq, bed, g.pitch_bytes, c->Np, n_stage, s->pos_meta, n_chunk, meta->stage_info, meta->bin_count, kn, K, k0,    \
+        c->n_groups, bc, B, b0, s->Bp, s->L, s->NCb, s->F, s->wmax, c->cs, c->rowscale, rs_stride, P_out, S_accum, cols,     \
+        a_major, kcap, bs, bzsh, dbg)
+    if (s->G == 2) PB_LAUNCH(1, 2);
+    else if (s->MT == 2) PB_LAUNCH(2, 4);
+    else PB_LAUNCH(1, 4);
 #undef PB_LAUNCH
-  RHE_LAUNCH_CHECK(c);
+    RHE_LAUNCH_CHECK(c);
+  }
   return RHE_OK;
 }
 
@@ -1827,6 +1856,7 @@ int64_t rhe_tc_gt_bytes(const rhe_ctx* c, const rhe_block_plan* plan) {
   const TcPlan* tp = (const TcPlan*)plan->tc;
   P2Shape sh;
   if (!s || !tp || tp->groups.size() != 1 || tp->groups[0].n_pos <= 0 || !p2_shape(s, &sh)) return 0;
+  if (s->Bc < c->cfg.n_vec) return 0;                                                                   // pass B runs in column chunks
   if ((int64_t)c->n_groups * c->cfg.n_bins * c->cfg.n_vec * (int64_t)c->Np >= (1ll << 31)) return 0;   // 32-bit indices into P / S
   if (c->cfg.n_ops * (tp->groups[0].n_pos / 128) > P2_MAXSUB) return 0;                                 // per-sub-tile bin table in shared memory
   return (int64_t)c->Np * (tp->groups[0].n_pos / 4);
@@ -1856,7 +1886,7 @@ static int tc_pass_b2(rhe_ctx* c, TcState* s, const uint8_t* gt, int m, const Tc
   const int n_stage = n_modes * n_pos / 128, SI = s->G / s->MT;
   const int n_chunk = rhe_div_up(rhe_div_up(n_stage, SI), 4);
   k_tc_quant_w<<<rhe_div_up((int64_t)n_pos * B * c->n_groups * n_modes, 256), 256, 0, st>>>(
-      c->w1, c->w2, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, n_modes, B, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill,
+      c->w1, c->w2, meta->pos_rows, n_pos, s->cap_pos, m, c->n_groups, n_modes, B, B, 0, s->Bp, s->L, s->F, s->wmax, s->uq, c->fill,
       s->pos_meta, SI, n_chunk);
   RHE_LAUNCH_CHECK(c);
   CUtensorMap tm_gt;                                   // GT as a 2-D byte tensor [(Np / 128) n_ss 128 rows][128 B]: one box = 16 KB contiguous

@@ -108,10 +108,12 @@ def test_tcgen05_capability_is_answered_by_the_library():
     assert _lib.tcgen05_supported(PathPlan(model="rhe_dom", K=8, B=10, C=5))
     assert _lib.tcgen05_supported(PathPlan(model="genie", K=8, B=10, C=5))
     assert _lib.tcgen05_supported(PathPlan(model="rhe", K=20, B=10, C=2))         # bin groups
-    # K = 2, B = 64: passes a naive TMEM-column count but not the shared-memory budget / vector-column limit
-    wide = PathPlan(model="rhe", K=2, B=64, C=0)
-    assert not _lib.tcgen05_supported(wide)
-    assert "exceed" in _lib.tcgen05_unsupported_reason(wide)
+    # shapes beyond one launch's TMEM / shared-memory layout run in column chunks instead of leaving the tensor path:
+    # 64 vectors, the reference's 50 vectors with two weight groups, 40 covariates with two RHS sets
+    assert _lib.tcgen05_supported(PathPlan(model="rhe", K=2, B=64, C=0))
+    assert _lib.tcgen05_supported(PathPlan(model="rhe_dom", K=8, B=50, C=5))
+    assert _lib.tcgen05_supported(PathPlan(model="genie", K=8, B=50, C=40))
+    assert _lib.tcgen05_unsupported_reason(PathPlan(model="genie", K=8, B=50, C=40)) == ""
     bad = _lib.plan_config(PathPlan(model="rhe", K=1, B=2, C=0), pitch_bytes=100)   # invalid config -> 0, not a crash
     assert _lib.load().rhe_tc_supported(ctypes.byref(bad)) == 0
 

@@ -195,6 +195,10 @@ EDGE_SHAPES = [
     (640,  512, 2, 3, 4, 2, 0.01, (),            "binary", "genie"),     # G + GxE + NxE
     (600, 1280, 20, 10, 4, 2, 0.01, (),          "binary", "rhe"),       # 20 bins: three pass-B launches of <= 8 bins (TMEM columns)
     (520,  960, 11, 9, 3, 0, 0.00, (3,),         "mean",   "rhe_dom"),   # 11 bins x 2 weight groups: bin groups of 4
+    (400,  516, 2, 50, 3, 1, 0.01, (),           "binary", "rhe_dom"),   # 50 vectors x 2 weight groups: pass B in column chunks of 32
+    (400,  516, 3, 34, 3, 2, 0.01, (5,),         "mean",   "genie"),     # 34 vectors x 2 RHS sets: chunks of 32 + 2
+    (300,  384, 8, 50, 3, 0, 0.00, (),           "binary", "rhe"),       # 50 vectors, one weight group: one bin per launch
+    (400,  516, 2, 10, 3, 40, 0.01, (),          "binary", "genie"),     # 40 covariates x 2 RHS sets: pass A in two column chunks
 ]
 
 
