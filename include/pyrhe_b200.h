@@ -34,6 +34,9 @@
  *   P / S             float [E_reg][n_vec][Np]   X (X^T Z) per estimate e = group * K + bin
  *   gram              double [E_reg][Rs][Rs]    sum over the (block, bin) SNPs of t t^T,
  *                     t = X_s^T [Z | W | y]
+ *   individual-major copy (optional, per resident block; rhe_block_transpose)
+ *                     uint8 [Np / 128][n_pos / 512][128][128]: one contiguous 16 KB box per (128 individuals, 512
+ *                     bin-sorted positions), 2 bits per genotype holding the imputed A2 COUNT (0, 1, 2; no missing code)
  */
 #ifndef PYRHE_B200_H
 #define PYRHE_B200_H
@@ -44,7 +47,7 @@
 extern "C" {
 #endif
 
-#define RHE_ABI_VERSION 2
+#define RHE_ABI_VERSION 3
 
 #define RHE_OK 0
 #define RHE_ERR_INVALID (-1)   /* bad argument */
@@ -80,8 +83,10 @@ const char* rhe_last_error(void);
 int rhe_ctx_create(rhe_ctx** out, const rhe_config* cfg);
 int rhe_ctx_destroy(rhe_ctx* ctx);
 
-/* 1 when the shapes of `cfg` fit the tcgen05 kernels (TMEM columns, shared memory), else 0 with the reason in
- * rhe_last_error(); such a configuration needs kernel_path = RHE_PATH_SIMT.  No device is touched. */
+/* 1 when the shapes of `cfg` fit the tcgen05 kernels, else 0 with the reason in rhe_last_error() (such a configuration
+ * needs kernel_path = RHE_PATH_SIMT).  Shapes beyond one launch's tensor-memory / shared-memory layout run in chunks of
+ * vector columns (pass B) or right-hand-side columns (pass A), so every valid configuration is supported today; the
+ * call stays the single place where the limits live.  No device is touched. */
 int rhe_tc_supported(const rhe_config* cfg);
 
 /* base.py:176-178,396-401 (Z, covariates, regressed phenotype as right-hand sides). */

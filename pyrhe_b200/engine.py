@@ -360,6 +360,14 @@ class RheEngine:
             self._counted = set()
             self.gt = {}
             self.reserve_state()
+            if self.world > 1 and not getattr(self, "_collective_warm", False):
+                # the first all-reduce of a communicator sets up its channels and staging buffers: pay for that here, on
+                # the buffers of the real exchange, so that the first pass over the blocks runs like every later one
+                self.S.zero_()
+                plan = self.plan
+                allreduce_sum([self.S, torch.zeros((self.J, plan.E_reg, plan.Rs, plan.Rs), dtype=torch.float64,
+                                                   device=self.device)], self.pg)
+                self._collective_warm = True
             if ring_blocks is None and fast_layout:
                 self._alloc_fast_layout(reserve_bytes)
         return self.bed
