@@ -2,7 +2,7 @@
 
     python bench.py --gpus 1 --steps 3 --warmup 3                       # this implementation
     python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 ...
-    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1      # CPU arm (oracle port)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1      # CPU arm (the unmodified reference from oracle/_ref)
 
 A "step" is one full RHE jackknife over synthetic genotypes of the named shape: every jackknife
 block of every rank through the block kernels, the all-reduce of the totals, the leave-one-out
@@ -96,27 +96,51 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
+def cpu_arm(wl, args):
+    """The CPU side of the comparison on the host cores: the UNMODIFIED reference from oracle/_ref (kind "reference") when
+    the shipped copy is intact, else the oracle port (kind "port").  Returns (baseline object, kind)."""
+    from oracle import ref_baseline
+    why = ref_baseline.available()
+    if not why and not args.cpu_port:
+        return ref_baseline.RefBaseline(wl["N"], wl["K"], wl["C"], wl["B"], snps_per_block=args.ref_snps), "reference"
+    from oracle.cpu_baseline import CpuBaseline
+    return CpuBaseline(wl["N"], wl["K"], wl["C"], wl["B"], snps_per_block=args.cpu_snps), "port"
+
+
 def reference_arm(args, wl, rank):
-    """CPU implementation of the path (oracle port), all host cores, bounded sample per step."""
+    """CPU implementation of the path -- the reference's own code when oracle/_ref is present --, all host cores, bounded
+    sample per step (each step of the reference takes about half a minute: at most one warm-up step is run)."""
     if rank != 0:
         return
-    from oracle.cpu_baseline import CpuBaseline
-    cb = CpuBaseline(wl["N"], wl["K"], wl["C"], wl["B"], snps_per_block=args.cpu_snps)
-    for _ in range(args.warmup):
-        cb.step()
-    secs, geno = 0.0, 0.0
-    for _ in range(args.steps):
-        s, _, g = cb.step()
-        secs += s
-        geno += g
-    cb.close()
+    def measure():
+        cb, kind = cpu_arm(wl, args)
+        try:
+            for _ in range(min(args.warmup, 1)):
+                cb.step()
+            secs, geno = 0.0, 0.0
+            for _ in range(args.steps):
+                s, _, g = cb.step()
+                secs += s
+                geno += g
+        finally:
+            cb.close()
+        return cb, kind, secs, geno
+
+    try:
+        cb, kind, secs, geno = measure()
+    except Exception as exc:                                 # e.g. the host cannot hold the reference's state arrays
+        if args.cpu_port:
+            raise
+        sys.stderr.write(f"reference arm: the unmodified reference failed ({exc}); timing the oracle port instead\n")
+        args.cpu_port = True
+        cb, kind, secs, geno = measure()
     gbs = geno / 4 / secs / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, **wl, "sample": cb.describe()},
-        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": cb.cores, "kind": "port", "sample": cb.describe()},
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": cb.cores, "kind": kind, "sample": cb.describe()},
         "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "projected_full_job_s": wl["N"] / 4 * wl["M"] / 1e9 / gbs,
     }
@@ -280,7 +304,9 @@ def main():
     ap.add_argument("--workload", default="config5", choices=list(WORKLOADS))
     ap.add_argument("--kernel_path", type=int, default=int(os.environ.get("PYRHE_B200_PATH", "1")),
                     help="1 = int8 tcgen05 kernels (default), 0 = CUDA-core validation kernels")
-    ap.add_argument("--cpu_snps", type=int, default=200, help="SNPs per block of the CPU sample")
+    ap.add_argument("--cpu_snps", type=int, default=200, help="SNPs per block of the CPU sample (oracle port)")
+    ap.add_argument("--ref_snps", type=int, default=100, help="SNPs per block of the CPU sample (unmodified reference)")
+    ap.add_argument("--cpu_port", action="store_true", help="time the oracle port even when oracle/_ref is present")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--ring_blocks", type=int, default=4, help="distinct host blocks served cyclically in the e2e leg")
@@ -493,12 +519,25 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_baseline import CpuBaseline
-        cb = CpuBaseline(N, K, Cc, B, snps_per_block=args.cpu_snps)
-        cb.step()
-        secs, _, geno = cb.step()
-        cb.close()
-        cpu = {"value": geno / 4 / secs / 1e9, "unit": UNIT, "cores": cb.cores, "kind": "port",
+        def measure():
+            cb, kind = cpu_arm(wl, args)
+            try:
+                if kind == "port":
+                    cb.step()                               # (the port's pool warms up; a reference step is half a minute)
+                secs, _, geno = cb.step()
+            finally:
+                cb.close()
+            return cb, kind, secs, geno
+
+        try:
+            cb, kind, secs, geno = measure()
+        except Exception as exc:
+            if args.cpu_port:
+                raise
+            sys.stderr.write(f"cpu_baseline: the unmodified reference failed ({exc}); timing the oracle port instead\n")
+            args.cpu_port = True
+            cb, kind, secs, geno = measure()
+        cpu = {"value": geno / 4 / secs / 1e9, "unit": UNIT, "cores": cb.cores, "kind": kind,
                "sample": cb.describe(), "sample_seconds": secs}
 
     eng.close()

@@ -7,17 +7,22 @@
 // 8-bit limbs stacked along N, so the int32 accumulation is EXACT and the result is independent of how
 // the work is split.
 //
-// A decode thread owns one SNP row; a 32-bit packed word expands to sixteen int8 values with 2 logic ops,
-// 4 byte-permutes and 3 multiply-high shifts.  Warps are specialised (decode groups, TMA producers, one MMA-issue
-// warp per decode group); every role loop is warp-uniform with elect.sync around the issue.
-//   pass A: packed super-stages (128 rows x 128 B) arrive as 2-D TMA boxes; the expanded A operand goes straight
-//           from registers into TENSOR MEMORY (tcgen05.st) and the MMA reads A from TMEM (K-major), so the big
-//           operand never touches shared memory as bytes; only the small Rq tiles (TMA, 128B swizzle) do.
-//   pass B: needs the same bytes as an MN-major operand (128 individuals contiguous per SNP row), which TMEM
-//           cannot provide, so the tile is written to shared memory (128B swizzle) and read by the MMA through an
-//           MN-major descriptor.  Rows are gathered by bin through per-warp cp.async rings.  One CTA owns
-//           MT x 128 individuals and the bins of one bin group (all bins when their accumulators fit the 512 TMEM
-//           columns): bin k accumulates in its own TMEM columns and the mainloop runs over the group's rows.
+// Warps are specialised (decode groups, TMA producers, one MMA-issue warp per decode group, drain warps); every role
+// loop is warp-uniform with elect.sync around the issue.
+//   pass A (k_tc_pass_a): packed super-stages (128 SNP rows x 128 B) arrive as 2-D TMA boxes; a decode thread owns one
+//           SNP row, a 32-bit packed word expands to sixteen int8 values with 2 logic ops, 4 byte-permutes and 3
+//           multiply-high shifts; the expanded A operand goes straight from registers into TENSOR MEMORY (tcgen05.st)
+//           and the MMA reads A from TMEM (K-major), so the big operand never touches shared memory as bytes; only the
+//           small Rq tiles (TMA, 128B swizzle) do.
+//   pass B needs the same bytes as an MN-major operand (128 individuals contiguous per SNP row), which TMEM cannot
+//           provide.  Two kernels:
+//           k_tc_pass_b2 -- the block also has an INDIVIDUAL-MAJOR copy (rhe_block_transpose, written at ingest: imputed
+//           A2 counts, 2 bits each, contiguous 16 KB boxes): then pass B is pass A with the roles swapped -- TMEM lane =
+//           individual, K = bin-sorted positions, the A operand from tensor memory, a mask-and-shift decode -- in a
+//           persistent CTA per SM whose drain warps write a bin's result while the next bins accumulate.
+//           k_tc_pass_b  -- no copy: the tile is decoded into shared memory (128B swizzle) and read by the MMA through
+//           an MN-major descriptor; rows are gathered by bin through per-warp cp.async rings; one CTA owns MT x 128
+//           individuals and the bins of one bin group (bin k accumulates in its own TMEM columns).
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -113,11 +118,6 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t addr, uint32_t parity) {
     if (ok) return;
   }
   asm volatile("trap;");
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double r;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
-  return r;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t r;
@@ -284,25 +284,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, int32_t (&v)[2]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
-}
-// value[j] = sum_l 256^l * limb_l[j] for two adjacent columns; limb l sits `stride` columns further on
-__device__ __forceinline__ void tmem_combine2(uint32_t taddr, int L, int stride, double (&val)[2]) {
-  int32_t v[4][2];
-#pragma unroll
-  for (int l = 0; l < 4; ++l)
-    if (l < L) tmem_ld2(taddr + (uint32_t)(l * stride), v[l]);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    double acc = 0.0;
-#pragma unroll
-    for (int l = 3; l >= 0; --l)
-      if (l < L) acc = acc * 256.0 + (double)v[l][j];
-    val[j] = acc;
-  }
-}
 // 32 registers (one 128-byte operand row) -> 32 consecutive TMEM columns of this thread's lane
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint4 (&r)[8]) {
   asm volatile(
@@ -606,35 +587,6 @@ struct PbSmem {
   double dq[64];                  // per-column dequantisation factor 2^(e - F)
   int32_t cnt[256];               // rows per bin
 };
-
-// W adjacent accumulator columns of the L limb rows (limb l sits `stride` columns further on) -> exact doubles
-template <int W>
-__device__ __forceinline__ void tmem_ldw(uint32_t taddr, int32_t (&v)[W]) {
-  static_assert(W == 2 || W == 4 || W == 8, "column chunk");
-  if constexpr (W == 4) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
-  } else if constexpr (W == 2) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
-  } else {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
-  }
-}
-template <int L, int W>
-__device__ __forceinline__ void tmem_combine(uint32_t taddr, int stride, double (&val)[W]) {
-  int32_t v[L][W];
-#pragma unroll
-  for (int l = 0; l < L; ++l) tmem_ldw<W>(taddr + (uint32_t)(l * stride), v[l]);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < W; ++j) {
-    double acc = (double)v[L - 1][j];
-#pragma unroll
-    for (int l = L - 2; l >= 0; --l) acc = fma(acc, 256.0, (double)v[l][j]);   // exact: |value| < 2^53
-    val[j] = acc;
-  }
-}
 
 // TMEM reads of the epilogues without a "memory" clobber (with one, the compiler re-derives every address and re-reads
 // the kernel parameters after each access: 35 instructions per value instead of 15); the ordering the hardware needs is
