@@ -34,7 +34,12 @@ def main():
     hdr, units = rows[0], rows[1]
     unit = dict(zip(hdr, units))
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
+    # the source page holds one section per profiled launch: a "Kernel Name" line, the column header, the instructions
+    names = [i for i, l in enumerate(src) if l.startswith('"Kernel Name"')]
     starts = [i for i, l in enumerate(src) if l.startswith('"Address"')] + [len(src) + 1]
+    n_k = len(rows) - 2
+    per = len(names) // n_k if n_k and len(names) % n_k == 0 else 0      # 1, or 2 (SASS view + source-line view) sections per launch
+    aligned = per > 0 and len(starts) - 1 == len(names)
     kernels = []
     for n, r in enumerate(rows[2:]):
         d = dict(zip(hdr, r))
@@ -46,8 +51,10 @@ def main():
         if rd and wr:
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             k["dram_bytes"] = rd["value"] * scale.get(rd["unit"], 1.0) + wr["value"] * scale.get(wr["unit"], 1.0)
-        if n + 1 < len(starts):
-            srows = list(csv.reader(src[starts[n]:starts[n + 1] - 1]))
+        if aligned:
+            sec = per * n
+            end = names[sec + 1] if sec + 1 < len(names) else len(src)
+            srows = list(csv.reader(src[starts[sec]:end]))
             sh = srows[0]
             ix = {name: i for i, name in enumerate(sh)}
             stalls = [c for c in sh if c.startswith("stall_") and "Not Issued" not in c]
