@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--kernel_path", type=int, default=int(os.environ.get("PYRHE_B200_PATH", "1")),
                     help="1 = int8 tcgen05 kernels (default), 0 = CUDA-core validation kernels")
     ap.add_argument("--cpu_snps", type=int, default=200, help="SNPs per block of the CPU sample (oracle port)")
-    ap.add_argument("--ref_snps", type=int, default=100, help="SNPs per block of the CPU sample (unmodified reference)")
+    ap.add_argument("--ref_snps", type=int, default=200, help="SNPs per block of the CPU sample (unmodified reference)")
     ap.add_argument("--cpu_port", action="store_true", help="time the oracle port even when oracle/_ref is present")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
