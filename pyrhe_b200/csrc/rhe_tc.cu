@@ -419,59 +419,66 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t row_s = packed_s + (uint32_t)t * 128;      // this thread's SNP row inside a staged box
     const uint32_t sw = (uint32_t)(t & 7);                      // 128-byte swizzle: 16-byte chunk c sits at c ^ (row & 7)
+    const uint32_t fg = smem_u32(&sm->full_g[0]), eg = smem_u32(&sm->empty_g[0]);
+    const uint32_t fa = smem_u32(&sm->full_a[2 * g]), ea = smem_u32(&sm->empty_a[2 * g]);
+    const uint32_t dst0 = lane_base + col_a + 32u * (uint32_t)(2 * g);
     const int n_own = n_sub > g ? (n_sub - g + PA_G - 1) / PA_G : 0;     // own sub-tiles j = g + PA_G * jj
-    PROF_T0();
-    // packed words of sub-tile j = 4 k + q: chunks 2 q, 2 q + 1 of the row in ring slot k % PA_GS
-    auto fetch = [&](int j, uint4& lo, uint4& hi) {
-      const int k = j >> 2, q = j & 3, sg = k % PA_GS;
-      mbar_wait(&sm->full_g[sg], (uint32_t)(k / PA_GS) & 1u);
-      const uint32_t base = row_s + (uint32_t)sg * PA_PACKED;
-      lo = lds128(base + (((uint32_t)(2 * q) ^ sw) << 4));
-      hi = lds128(base + (((uint32_t)(2 * q + 1) ^ sw) << 4));
+    // Sub-tile j = 4 k + q is chunks 2 q, 2 q + 1 of this thread's row in ring slot k % PA_GS.  The group walks
+    // j = g, g + PA_G, ...: q advances by PA_G (mod 4) and k by the carry, so slot, parity and chunk offsets advance
+    // incrementally (no division in the loop); the same walk, one sub-tile behind, tells which slot to release.
+    static_assert(PA_G < 4, "one carry per step");
+    uint32_t fq = (uint32_t)g, fsl = 0, fpar = 0;              // next sub-tile to read: chunk pair, ring slot, parity
+    uint32_t cq = (uint32_t)g, csl = 0;                        // sub-tile being expanded
+    uint32_t aq = 0, apar = 1;                                 // the group's A slot of the next expansion / parity to wait for
+    const uint32_t sw4 = sw << 4;
+    auto fetch = [&](uint4& lo, uint4& hi) {
+      mbar_wait_s(fg + 8u * fsl, fpar);
+      // chunk (2 q) ^ sw of the row: ((2 q) ^ sw) << 4 = (sw << 4) ^ (q << 5), and its partner 2 q + 1 is the same
+      // address with bit 4 flipped (the row starts on a 128-byte boundary)
+      const uint32_t a_lo = row_s + fsl * PA_PACKED + (sw4 ^ (fq << 5));
+      lo = lds128(a_lo);
+      hi = lds128(a_lo ^ 16u);
+      fq += PA_G;
+      if (fq >= 4u) { fq -= 4u; if (++fsl == (uint32_t)PA_GS) { fsl = 0; fpar ^= 1u; } }
     };
     // Software pipeline: the packed words of the next sub-tile are read from the ring before the current one is
     // expanded, and each sub-tile goes to TMEM as two 16-column stores so that the first store overlaps the
     // expansion of the second half.  The ring slot is released once the words are in registers (consumed).
-    auto put = [&](uint32_t slot_a, uint32_t parity, const uint4& lo, const uint4& hi, int k) {
-      uint4 r[4];
-      PROF_ADD(0);
-      mbar_wait(&sm->empty_a[slot_a], parity ^ 1u);
+    auto put = [&](const uint4& lo, const uint4& hi) {
+      mbar_wait_s(ea + 8u * aq, apar);
       tc_fence_after();
-      PROF_ADD(1);
-      const uint32_t dst = lane_base + col_a + 32u * slot_a;
-      if (RHE_DBG(8)) {
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&sm->empty_g[k % PA_GS]); mbar_arrive(&sm->full_a[slot_a]); }
-        return;
+      const uint32_t dst = dst0 + 32u * aq;
+      if (!(RHE_DBG(8))) {
+        uint4 r[4];
+        r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
+        tmem_st16(dst, r);
+        uint4 r2[4];
+        r2[0] = tc_expand(hi.x, tab); r2[1] = tc_expand(hi.y, tab); r2[2] = tc_expand(hi.z, tab); r2[3] = tc_expand(hi.w, tab);
+        tmem_st16(dst + 16, r2);
+        tmem_st_wait();
+        tc_fence_before();
       }
-      r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
-      tmem_st16(dst, r);
-      uint4 r2[4];
-      r2[0] = tc_expand(hi.x, tab); r2[1] = tc_expand(hi.y, tab); r2[2] = tc_expand(hi.z, tab); r2[3] = tc_expand(hi.w, tab);
-      tmem_st16(dst + 16, r2);
-      PROF_ADD(2);
-      tmem_st_wait();
-      tc_fence_before();
       __syncwarp();                                    // every lane's stores are complete and fenced: one arrival per warp
-      if (lane == 0) { mbar_arrive(&sm->empty_g[k % PA_GS]); mbar_arrive(&sm->full_a[slot_a]); }
-      PROF_ADD(3);
+      if (lane == 0) { mbar_arrive_s(eg + 8u * csl); mbar_arrive_s(fa + 8u * aq); }
+      cq += PA_G;
+      if (cq >= 4u) { cq -= 4u; if (++csl == (uint32_t)PA_GS) csl = 0; }
+      aq ^= 1u;
+      if (aq == 0u) apar ^= 1u;
     };
-    uint4 lo, hi;
-    if (n_own > 0) fetch(g, lo, hi);
-    for (int jj = 0; jj < n_own; ++jj) {
-      const int j = g + PA_G * jj;
-      uint4 nlo = lo, nhi = hi;
-      if (jj + 1 < n_own) fetch(j + PA_G, nlo, nhi);
-      PROF_ADD(4);
-      put((uint32_t)(2 * g + (jj & 1)), (uint32_t)(jj >> 1) & 1u, lo, hi, j >> 2);
-      lo = nlo;
-      hi = nhi;
+    // unrolled by two so that the two register sets swap roles without moves
+    uint4 lo0, hi0, lo1, hi1;
+    if (n_own > 0) fetch(lo0, hi0);
+    for (int jj = 0; jj < n_own; jj += 2) {
+      if (jj + 1 < n_own) fetch(lo1, hi1);
+      put(lo0, hi0);
+      if (jj + 1 < n_own) {
+        if (jj + 2 < n_own) fetch(lo0, hi0);
+        put(lo1, hi1);
+      }
     }
     // ---- epilogue: lane quadrant (warp & 3) of TMEM, row = SNP; the groups split the columns
-    PROF_ADD(0);
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
-    PROF_ADD(5);
     const int snp = snp0 + t;
     for (int c0 = 4 * g; c0 < R1p; c0 += 4 * PA_G) {
       double val[4];
@@ -482,8 +489,6 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
           if (c0 + j < Rv) atomicAdd(t_raw + (size_t)snp * R1 + c_lo + c0 + j, val[j] * col_dq[c_lo + c0 + j]);
       }
     }
-    PROF_ADD(6);
-    PROF_FLUSH(16);
     tc_fence_before();
   } else if (warp == PA_DW) {
     {                                                  // TMA producer 1: the four Rq tiles of super-stage k -> slot k % PA_RS
