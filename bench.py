@@ -276,7 +276,8 @@ def build_problem(wl, args, rank, world, dev):
     free_b, total_b = torch.cuda.mem_get_info(dev)
     store = bytes_geno + bytes_part + 6e9 < free_b
     eng = RheEngine(plan, n_indv=N, keep=keep, annot=annot, num_jack=J, impute="binary", seed=0, device=dev,
-                    kernel_path=args.kernel_path, rank=rank, world=world, store_partials=store)
+                    kernel_path=args.kernel_path, rank=rank, world=world, store_partials=store,
+                    retile=getattr(args, "retile", True))
     eng.set_rhs(Z, W, Y_res, env)
     eng.alloc_genotypes()
     stream = torch.cuda.current_stream(dev)
@@ -313,6 +314,8 @@ def main():
     ap.add_argument("--e2e_source", default="pinned", choices=["pinned", "pageable"])
     ap.add_argument("--no_other_configs", action="store_true")
     ap.add_argument("--no_api_e2e", action="store_true")
+    ap.add_argument("--no_retile", dest="retile", action="store_false",
+                    help="keep the PLINK rows of blocks that own an individual-major copy (default: re-tile them for pass A)")
     ap.add_argument("--api_workload", default="config2", choices=list(WORKLOADS))
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -404,27 +407,37 @@ def main():
     # feed the tensor cores from tensor memory (k_tc_pass_b2); the others gather SNP rows through shared memory (k_tc_pass_b)
     n_own, n_fast = max(len(eng.own), 1), len(eng.gt)
     pb_kernels = {}
-    if args.kernel_path == 1:
-        ms_gather = ph["pass_b"]
-        if 0 < n_fast:
-            eng.use_fast_layout = False
+    pass_a_kernels = {}
+    if args.kernel_path == 1 and len(eng.own) > 0:
+        S_buf, P_buf = eng.reserve_state()
+        gscr = torch.zeros((plan.E_reg, plan.Rs, plan.Rs), dtype=torch.float64, device=dev)
+
+        def phases_of(blocks):
             _lib.check(lib.rhe_timing_enable(eng._ctx, 1))
-            step_resident()
-            ph2 = (C.c_double * 4)()
-            _lib.check(lib.rhe_timing_collect(eng._ctx, ph2, C.byref(ncalls)))
+            for j in blocks:
+                eng._accumulate(j, P_buf[eng.own.index(j)] if P_buf is not None else None, S_buf, gscr)
+            out, n = (C.c_double * 4)(), C.c_int32()
+            _lib.check(lib.rhe_timing_collect(eng._ctx, out, C.byref(n)))
             _lib.check(lib.rhe_timing_enable(eng._ctx, 0))
-            eng.use_fast_layout = True
-            ms_gather = ph2[3] / max(ncalls.value, 1)
-            ms_fast = (ph["pass_b"] * n_own - ms_gather * (n_own - n_fast)) / n_fast
-            pb_kernels["k_tc_pass_b2 (A operand from tensor memory, individual-major copy)"] = {"blocks": n_fast, "launch_ms": ms_fast}
-        if n_fast < n_own:
-            pb_kernels["k_tc_pass_b (SNP rows gathered through shared memory)"] = {"blocks": n_own - n_fast, "launch_ms": ms_gather}
+            return [out[i] / max(n.value, 1) for i in range(4)]
+
+        fast_blocks = [j for j in eng.own if j in eng.gt]
+        slow_blocks = [j for j in eng.own if j not in eng.gt]
+        for name_a, name_b, blocks in (
+                ("k_tc_pass_a<., 1> (re-tiled rows: contiguous boxes of imputed counts)" if eng._tiled else
+                 "k_tc_pass_a<., 0> (PLINK rows)",
+                 "k_tc_pass_b2 (A operand from tensor memory, individual-major copy)", fast_blocks),
+                ("k_tc_pass_a<., 0> (PLINK rows)", "k_tc_pass_b (SNP rows gathered through shared memory)", slow_blocks)):
+            if blocks:
+                p4 = phases_of(blocks)
+                pass_a_kernels[name_a] = {"blocks": len(blocks), "launch_ms": p4[1]}
+                pb_kernels[name_b] = {"blocks": len(blocks), "launch_ms": p4[3]}
     dom = max(("pass_a", "pass_b"), key=lambda n: ph[n])
     m_avg = sum(eng.ranges[j][1] - eng.ranges[j][0] for j in eng.own) / max(len(eng.own), 1)
     alg_bytes = float((N + 3) // 4) * m_avg
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (ph[dom] * 1e-3) / 1e9 if ph[dom] > 0 else 0.0
-    for v in pb_kernels.values():
+    for v in list(pb_kernels.values()) + list(pass_a_kernels.values()):
         v["achieved"] = alg_bytes / (v["launch_ms"] * 1e-3) / 1e9
         v["frac"] = v["achieved"] / peak
     traffic = None
@@ -439,7 +452,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ph[dom], "phases_ms_per_block": ph,
-                "pass_b_kernels": pb_kernels,
+                "pass_a_kernels": pass_a_kernels, "pass_b_kernels": pb_kernels,
                 "ingest_ms_per_block": ingest_count_ms,
                 "fused_block_frac": alg_bytes / (block_ms * 1e-3) / 1e9 / peak if block_ms > 0 else 0.0}
 
@@ -452,11 +465,15 @@ def main():
     if not args.no_e2e:
         R = max(1, min(args.ring_blocks, len(eng.own)))
         host = torch.empty((R * eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
-        for r in range(R):
-            rows, m = eng.block_view(eng.own[r])
-            host[r * eng.max_m: r * eng.max_m + m].copy_(rows[:, : eng.row_bytes])
+        tmp = torch.zeros((eng.max_m, eng.pitch), dtype=torch.uint8, device=dev)
+        for r in range(R):                                     # the same generator as the resident leg (the resident rows may be re-tiled)
+            j = eng.own[r]
+            m = eng.ranges[j][1] - eng.ranges[j][0]
+            _lib.check(lib.rhe_synth_genotypes(C.c_void_p(tmp.data_ptr()), m, eng.pitch, N, eng.ranges[j][0], 1234, 0.0,
+                                               C.c_void_p(stream.cuda_stream)))
+            host[r * eng.max_m: r * eng.max_m + m].copy_(tmp[:m, : eng.row_bytes])
         torch.cuda.synchronize(dev)
-        rows = None                                            # (a view of the resident rows: must not outlive the engine)
+        del tmp
         host_np = host.numpy()
 
         class CyclicRows:

@@ -47,13 +47,16 @@
 extern "C" {
 #endif
 
-#define RHE_ABI_VERSION 3
+#define RHE_ABI_VERSION 4
 
 #define RHE_OK 0
 #define RHE_ERR_INVALID (-1)   /* bad argument */
 #define RHE_ERR_CUDA (-2)      /* CUDA runtime error (message holds cudaGetErrorString) */
 #define RHE_ERR_STATE (-3)     /* call order violated (e.g. accumulate before set_rhs) */
 #define RHE_ERR_UNSUPPORTED (-4)
+
+#define RHE_ROWS_PLINK 0       /* SNP-major rows exactly as in the .bed file                */
+#define RHE_ROWS_TILED 1       /* re-tiled and re-encoded by rhe_block_retile (pass A only) */
 
 #define RHE_PATH_SIMT 0        /* fp32/fp64 CUDA-core kernels (validation path)            */
 #define RHE_PATH_TCGEN05 1     /* int8 tcgen05 tensor-core kernels with TMEM accumulators   */
@@ -135,17 +138,29 @@ int64_t rhe_block_fast_bytes(const rhe_ctx* ctx, const rhe_block_plan* plan);
 int rhe_block_transpose(rhe_ctx* ctx, const uint8_t* bed_dev, const rhe_block_plan* plan,
                         const int32_t* counts_dev, uint8_t* gt_dev, void* stream);
 
+/* Optional in-place re-layout of a resident block's SNP-major rows for pass A (X^T [Z | W | y], base.py:403-417), once the
+ * counts are taken and the individual-major copy is written (both read the PLINK rows):
+ *   [n_snps / 128][pitch / 128][128 rows][128 B]   every TMA box of pass A is one contiguous 16 KB piece (streams from HBM
+ *                        like a copy instead of 128 row-strided segments) and the two bits of a genotype hold the imputed
+ *                        A2 count (mask-and-shift decode, no per-SNP table).
+ * The rows buffer must hold rhe_block_tiled_bytes (the SNP count rounded up to 128 rows); scratch_dev as many bytes.
+ * Afterwards the rows are readable ONLY by rhe_block_accumulate(..., rows_layout = RHE_ROWS_TILED) with counts and copy. */
+int64_t rhe_block_tiled_bytes(const rhe_ctx* ctx, const rhe_block_plan* plan);
+int rhe_block_retile(rhe_ctx* ctx, uint8_t* bed_dev, const rhe_block_plan* plan, const int32_t* counts_dev,
+                     uint8_t* scratch_dev, void* stream);
+
 /* rhe.py:13-22 / rhe_dom.py:43-68 / genie.py:46-82 for ONE jackknife block:
  *   plan             from rhe_block_plan_create (its n_snps rows start at bed_dev)
  *   counts_dev       int32 [n_snps][4] from rhe_block_stats on the same rows, or NULL (counted here: one more
  *                    read of the block)
  *   gt_dev           the block's individual-major copy (rhe_block_transpose) or NULL (pass B gathers SNP rows)
+ *   rows_layout      RHE_ROWS_PLINK, or RHE_ROWS_TILED after rhe_block_retile (then counts_dev and gt_dev are required)
  *   P_out_dev        float [E_reg][B][Np] or NULL   this block's X (X^T Z)
  *   S_accum_dev      float [E_reg][B][Np] or NULL   running totals (+=)
  *   gram_out_dev     double [E_reg][Rs][Rs]         overwritten
  * Enqueues kernels on `stream` only: no allocation, no host synchronisation. */
 int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, const rhe_block_plan* plan,
-                         const int32_t* counts_dev, const uint8_t* gt_dev, float* P_out_dev,
+                         const int32_t* counts_dev, const uint8_t* gt_dev, int32_t rows_layout, float* P_out_dev,
                          float* S_accum_dev, double* gram_out_dev, void* stream);
 
 /* base.py:578-581 after aggregate (base.py:483-486): out[a][c] = sum (S_a - P_a)(S_c - P_c)

@@ -10,10 +10,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpyrhe_b200.so")
+# PYRHE_B200_LIB: another build of the same library (profiling / ablation builds made with PYRHE_B200_EXTRA_NVCC)
+LIB_PATH = os.environ.get("PYRHE_B200_LIB") or os.path.join(_HERE, "csrc", "libpyrhe_b200.so")
 
 PATH_SIMT = 0
 PATH_TCGEN05 = 1
+ROWS_PLINK = 0
+ROWS_TILED = 1
 
 
 class RheConfig(C.Structure):
@@ -43,7 +46,9 @@ SIGNATURES = {
     "rhe_block_plan_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rhe_block_fast_bytes": (C.c_int64, [C.c_void_p, C.c_void_p]),
     "rhe_block_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "rhe_block_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+    "rhe_block_tiled_bytes": (C.c_int64, [C.c_void_p, C.c_void_p]),
+    "rhe_block_retile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rhe_block_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "rhe_loo_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "rhe_loo_gram_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,

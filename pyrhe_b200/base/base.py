@@ -278,7 +278,8 @@ class Base(BlockHookDriver, LegacyBlockOps, ABC):
         eng = RheEngine(plan, n_indv=self.num_indv_original, keep=keep, annot=self.annot_matrix,
                         num_jack=self.num_jack, impute=self.geno_impute_methods, seed=self.seed, device=self.device,
                         kernel_path=path, rank=self._rank, world=self._world,
-                        store_partials=not self._recompute_blocks, process_group=pg)
+                        store_partials=not self._recompute_blocks, process_group=pg,
+                        retile=os.environ.get("PYRHE_B200_RETILE", "1") != "0")
         eng.set_rhs(self.all_zb, self.cov_matrix, Y_res, self._env_vector())
         # bounded-memory ingest overlapped with compute: block j+1 is staged and copied while
         # block j runs; the rank's `.bed` share stays resident only when it fits the HBM, otherwise it streams

@@ -18,7 +18,11 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
+    """`out`: write another build of the library there (ablation / profiling builds with PYRHE_B200_EXTRA_NVCC)."""
+    global LIB
+    if out:
+        LIB, force = out, True
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -35,4 +39,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    out = [a for a in sys.argv[1:] if a.endswith(".so")]
+    print(build(force="--force" in sys.argv, verbose=True, out=out[0] if out else None))

@@ -994,14 +994,34 @@ extern "C" int rhe_block_transpose(rhe_ctx* c, const uint8_t* bed, const rhe_blo
   return rhe_tc_transpose(c, bed, plan, counts, gt, (cudaStream_t)stream);
 }
 
+extern "C" int64_t rhe_block_tiled_bytes(const rhe_ctx* c, const rhe_block_plan* plan) {
+  if (!c || !plan || !c->tc) return 0;
+  return rhe_tc_tiled_bytes(c, plan->m);
+}
+
+extern "C" int rhe_block_retile(rhe_ctx* c, uint8_t* bed, const rhe_block_plan* plan, const int32_t* counts, uint8_t* scratch,
+                                void* stream) {
+  if (!c || !bed || !plan || !counts || !scratch) { rhe_set_error("rhe_block_retile: NULL argument"); return RHE_ERR_INVALID; }
+  if (!c->tc) { rhe_set_error("rhe_block_retile: the context runs the CUDA-core path"); return RHE_ERR_UNSUPPORTED; }
+  return rhe_tc_retile(c, bed, plan->m, counts, scratch, (cudaStream_t)stream);
+}
+
 extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, const rhe_block_plan* plan, const int32_t* counts_in,
-                                    const uint8_t* gt, float* P_out, float* S_accum, double* gram_out, void* stream) {
+                                    const uint8_t* gt, int32_t rows_layout, float* P_out, float* S_accum, double* gram_out,
+                                    void* stream) {
   if (!plan) { rhe_set_error("rhe_block_accumulate: plan is NULL"); return RHE_ERR_INVALID; }
   const int m = plan->m;
   int rc = check_block(c, bed, m, "rhe_block_accumulate");
   if (rc) return rc;
   if (!gram_out) { rhe_set_error("rhe_block_accumulate: NULL argument"); return RHE_ERR_INVALID; }
   if (gt && c->cfg.kernel_path != RHE_PATH_TCGEN05) { rhe_set_error("rhe_block_accumulate: the individual-major copy belongs to the tensor-core path"); return RHE_ERR_INVALID; }
+  if (rows_layout != RHE_ROWS_PLINK && rows_layout != RHE_ROWS_TILED) { rhe_set_error("rhe_block_accumulate: unknown rows_layout %d", rows_layout); return RHE_ERR_INVALID; }
+  if (rows_layout == RHE_ROWS_TILED && (c->cfg.kernel_path != RHE_PATH_TCGEN05 || !counts_in || !gt)) {
+    // re-tiled rows carry imputed counts in box order: only pass A of the tensor path reads them, so the allele counts
+    // and pass B's operand must come from the ingest-time artefacts
+    rhe_set_error("rhe_block_accumulate: re-tiled rows need the tensor-core path, the ingest-time counts and the individual-major copy");
+    return RHE_ERR_INVALID;
+  }
   const int32_t* bin_rows = plan->bin_rows;
   const int32_t* s_off_dev = plan->off_dev;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1031,7 +1051,7 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, const rhe_bl
 
   // ---- pass A
   if (g.kernel_path == RHE_PATH_TCGEN05) {
-    rc = rhe_tc_pass_a(c, bed, m, st);
+    rc = rhe_tc_pass_a(c, bed, m, rows_layout == RHE_ROWS_TILED, st);
     if (rc) return rc;
   } else {
     int chunk = 8192;

@@ -95,7 +95,9 @@ static inline int rhe_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / 
 int rhe_tc_create(rhe_ctx* ctx);
 void rhe_tc_destroy(rhe_ctx* ctx);
 int rhe_tc_set_rhs(rhe_ctx* ctx, cudaStream_t st);
-int rhe_tc_pass_a(rhe_ctx* ctx, const uint8_t* bed, int m, cudaStream_t st);
+int rhe_tc_pass_a(rhe_ctx* ctx, const uint8_t* bed, int m, int tiled, cudaStream_t st);
+int64_t rhe_tc_tiled_bytes(const rhe_ctx* ctx, int m);                          // bytes of a block's rows once re-tiled (128-row tiles)
+int rhe_tc_retile(rhe_ctx* ctx, uint8_t* bed, int m, const int32_t* counts, uint8_t* scratch, cudaStream_t st);
 unsigned int* rhe_tc_wmax(rhe_ctx* ctx);   // per-column max |pass-B weight| (float bits), or NULL
 int rhe_tc_pass_b(rhe_ctx* ctx, const uint8_t* bed, const uint8_t* gt, const rhe_block_plan* plan, float* P_out,
                   float* S_accum, cudaStream_t st);

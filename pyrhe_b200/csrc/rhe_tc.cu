@@ -30,6 +30,13 @@
 #include "rhe_common.cuh"
 
 #define TC_TILE_A 16384          // 128 rows x 128 bytes
+// Right shifts of the decode: plain SHF on the ALU pipe (1), or multiply-high on the FMA pipe (0).  Measured on config-5
+// blocks: IMAD.HI costs more issue time than it saves the ALU pipe wherever the expansion is mask-and-shift (pass B from
+// tensor memory 0.379 -> 0.340 ms, pass A on re-tiled rows 0.286 -> 0.272 ms) and in pass A's table look-up (0.295 -> 0.289 ms);
+// only the gather kernel, whose ALU pipe also writes the tile to shared memory, keeps the multiply-high (0.543 vs 0.554 ms).
+#ifndef TC_SHIFT_VARIANT
+#define TC_SHIFT_VARIANT 1
+#endif
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -239,14 +246,23 @@ __device__ __forceinline__ uint32_t tc_shr_fma(uint32_t x, uint32_t pow2) {   //
   asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(pow2));
   return r;
 }
+template <int MULHI = 1>
 __device__ __forceinline__ uint4 tc_expand(uint32_t w, uint32_t tab) {
   const uint32_t e = w & 0x33333333u;
-  const uint32_t o = tc_shr_fma(w, 1u << 30) & 0x33333333u;
   uint4 r;
-  r.x = tc_prmt(tab, e);
-  r.y = tc_prmt(tab, tc_shr_fma(e, 1u << 16));
-  r.z = tc_prmt(tab, o);
-  r.w = tc_prmt(tab, tc_shr_fma(o, 1u << 16));
+  if constexpr (MULHI) {
+    const uint32_t o = tc_shr_fma(w, 1u << 30) & 0x33333333u;
+    r.x = tc_prmt(tab, e);
+    r.y = tc_prmt(tab, tc_shr_fma(e, 1u << 16));
+    r.z = tc_prmt(tab, o);
+    r.w = tc_prmt(tab, tc_shr_fma(o, 1u << 16));
+  } else {
+    const uint32_t o = (w >> 2) & 0x33333333u;
+    r.x = tc_prmt(tab, e);
+    r.y = tc_prmt(tab, e >> 16);
+    r.z = tc_prmt(tab, o);
+    r.w = tc_prmt(tab, o >> 16);
+  }
   return r;
 }
 
@@ -368,7 +384,11 @@ struct PaSmem {
   uint32_t tmem_base;
 };
 
-template <int PA_GS>
+// TILED = 1: the block's rows were re-tiled at ingest (rhe_block_retile): every (128 SNP rows x 128 B) box is one
+// contiguous 16 KB piece of memory -- [row tile][512-individual column][128 rows][128 B] -- and the two bits of a genotype
+// hold the imputed A2 COUNT, so a box streams from HBM like a plain copy (the row-strided boxes of the PLINK layout top
+// out at 4.2-4.5 TB/s on this part, tools/membench.cu) and a word expands with masks and shifts only (no per-SNP table).
+template <int PA_GS, int TILED>
 __global__ void __launch_bounds__(PA_THREADS, 2)
 k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ CUtensorMap tm_bed, int m, int Np,
             int NB, int R1, int R1p, int L, int c_lo, int Rv, int rq_row0, const uint8_t* __restrict__ fill,
@@ -415,9 +435,35 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
   if (warp < PA_DW) {
     const int t = (warp & 3) * 32 + lane, g = warp >> 2;
     const int s = min(snp0 + t, m - 1);
-    const uint32_t tab = tc_value_table(fill[s], mode);
+    const uint32_t tab = TILED ? 0u : tc_value_table(fill[s], mode);
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t row_s = packed_s + (uint32_t)t * 128;      // this thread's SNP row inside a staged box
+    // value-coded rows: register k of a word = fields k, k + 4, k + 8, k + 12 (rhe_block_retile places the individual
+    // that the table look-up would deliver at byte 4 k + j into field 4 j + k); [g == 2] is bit 1 of the value
+    auto expand = [&](uint32_t w) {
+      if constexpr (TILED) {
+        uint4 r;
+        if (mode == 0) {
+          const uint32_t mk = 0x03030303u;
+#if TC_SHIFT_VARIANT == 1
+          r.x = w & mk; r.y = (w >> 2) & mk; r.z = (w >> 4) & mk; r.w = (w >> 6) & mk;
+#else
+          r.x = w & mk; r.y = tc_shr_fma(w, 1u << 30) & mk; r.z = tc_shr_fma(w, 1u << 28) & mk; r.w = tc_shr_fma(w, 1u << 26) & mk;
+#endif
+        } else {
+          const uint32_t mk = 0x01010101u;
+#if TC_SHIFT_VARIANT == 1
+          r.x = (w >> 1) & mk; r.y = (w >> 3) & mk; r.z = (w >> 5) & mk; r.w = (w >> 7) & mk;
+#else
+          r.x = tc_shr_fma(w, 1u << 31) & mk; r.y = tc_shr_fma(w, 1u << 29) & mk;
+          r.z = tc_shr_fma(w, 1u << 27) & mk; r.w = tc_shr_fma(w, 1u << 25) & mk;
+#endif
+        }
+        return r;
+      } else {
+        return tc_expand<1 - TC_SHIFT_VARIANT>(w, tab);
+      }
+    };
     const uint32_t sw = (uint32_t)(t & 7);                      // 128-byte swizzle: 16-byte chunk c sits at c ^ (row & 7)
     const uint32_t fg = smem_u32(&sm->full_g[0]), eg = smem_u32(&sm->empty_g[0]);
     const uint32_t fa = smem_u32(&sm->full_a[2 * g]), ea = smem_u32(&sm->empty_a[2 * g]);
@@ -450,10 +496,10 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
       const uint32_t dst = dst0 + 32u * aq;
       if (!(RHE_DBG(8))) {
         uint4 r[4];
-        r[0] = tc_expand(lo.x, tab); r[1] = tc_expand(lo.y, tab); r[2] = tc_expand(lo.z, tab); r[3] = tc_expand(lo.w, tab);
+        r[0] = expand(lo.x); r[1] = expand(lo.y); r[2] = expand(lo.z); r[3] = expand(lo.w);
         tmem_st16(dst, r);
         uint4 r2[4];
-        r2[0] = tc_expand(hi.x, tab); r2[1] = tc_expand(hi.y, tab); r2[2] = tc_expand(hi.z, tab); r2[3] = tc_expand(hi.w, tab);
+        r2[0] = expand(hi.x); r2[1] = expand(hi.y); r2[2] = expand(hi.z); r2[3] = expand(hi.w);
         tmem_st16(dst + 16, r2);
         tmem_st_wait();
         tc_fence_before();
@@ -521,7 +567,10 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
           if (RHE_DBG(4)) mbar_arrive_s(fg + 8u * sg);
           else {
             mbar_expect_tx_s(fg + 8u * sg, PA_PACKED);
-            tma_load_2d_s(packed_s + sg * PA_PACKED, &tm_bed, fg + 8u * sg, (y + splits * k) * 128, snp0);
+            if constexpr (TILED)   // box (row tile, column ss) = rows [(tile n_cc + ss) 128, + 128) of a [..][128 B] tensor
+              tma_load_2d_s(packed_s + sg * PA_PACKED, &tm_bed, fg + 8u * sg, 0, ((int)blockIdx.y * total_ss + (y + splits * k)) * 128);
+            else
+              tma_load_2d_s(packed_s + sg * PA_PACKED, &tm_bed, fg + 8u * sg, (y + splits * k) * 128, snp0);
           }
         }
         __syncwarp();
@@ -1100,18 +1149,31 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
       const uint32_t m = 0x03030303u;
       uint4 r;
       r.x = w & m;
+#if TC_SHIFT_VARIANT == 1
+      r.y = (w >> 2) & m;
+      r.z = (w >> 4) & m;
+      r.w = (w >> 6) & m;
+#else
       r.y = tc_shr_fma(w, 1u << 30) & m;
       r.z = tc_shr_fma(w, 1u << 28) & m;
       r.w = tc_shr_fma(w, 1u << 26) & m;
+#endif
       return r;
     };
     auto expand1 = [](uint32_t w) {
       const uint32_t m = 0x01010101u;
       uint4 r;
+#if TC_SHIFT_VARIANT == 1
+      r.x = (w >> 1) & m;
+      r.y = (w >> 3) & m;
+      r.z = (w >> 5) & m;
+      r.w = (w >> 7) & m;
+#else
       r.x = tc_shr_fma(w, 1u << 31) & m;
       r.y = tc_shr_fma(w, 1u << 29) & m;
       r.z = tc_shr_fma(w, 1u << 27) & m;
       r.w = tc_shr_fma(w, 1u << 25) & m;
+#endif
       return r;
     };
     // one operand of one sub-tile -> the group's next A slot; `release`: the packed words are not needed again
@@ -1343,6 +1405,49 @@ k_tc_transpose(const uint8_t* __restrict__ bed, int pitch, const int32_t* __rest
     // box (M-tile, super-stage) = 128 individuals x 128 B, contiguous: [mtile][ss][row][q * 32 + pg * 4]
     const size_t box = (size_t)((i0 + i) >> 7) * n_ss + (size_t)(st >> 2);
     *reinterpret_cast<uint32_t*>(gt + (box * 128 + (size_t)((i0 + i) & 127)) * 128 + (size_t)((st & 3) * 32 + pg * 4)) = outw[i][pg];
+  }
+}
+
+// Re-tile + re-encode the SNP-major rows of one block for pass A (ingest, rhe_block_retile): source = the PLINK rows
+// [m][pitch]; destination (a scratch buffer, copied back over the rows afterwards) = [row tile][column of 128 B][128 rows]
+// [128 B], the two bits of a genotype holding the imputed A2 count (missing -> the SNP's fill), fields permuted inside
+// every word so that the mask-and-shift expansion of k_tc_pass_a<., 1> delivers the individuals in the order the table
+// look-up does (byte 4 k + j of the expansion = individual tc_perm16(4 k + j) of the word's sixteen).
+__global__ void __launch_bounds__(256)
+k_tc_retile(const uint8_t* __restrict__ bed, int pitch, int m, const int32_t* __restrict__ counts, int n_kept, int binary,
+            const double* __restrict__ uniforms, uint8_t* __restrict__ out) {
+  const int n_cc = pitch >> 7;                         // 128-byte columns per row
+  const int tile = blockIdx.y, cc0 = blockIdx.x * 8;   // 8 columns (1 KB of every row) per CTA
+  __shared__ uint8_t fillv[128];
+  if (threadIdx.x < 128) {
+    const int row = tile * 128 + (int)threadIdx.x;
+    int f = 0;
+    if (row < m) {
+      const int4 c = reinterpret_cast<const int4*>(counts)[row];
+      f = rhe_fill_from_counts(c.y, c.z, c.w, n_kept, binary, binary ? uniforms[row] : 0.0);
+    }
+    fillv[threadIdx.x] = (uint8_t)f;
+  }
+  __syncthreads();
+  // word index inside the CTA's piece: [128 rows][8 columns][32 words]; a warp reads 128 contiguous bytes of one row
+  for (int idx = threadIdx.x; idx < 128 * 8 * 32; idx += 256) {
+    const int w = idx & 31, c = (idx >> 5) & 7, r = idx >> 8;
+    const int row = tile * 128 + r, cc = cc0 + c;
+    if (cc >= n_cc) continue;
+    uint32_t v = 0u;
+    if (row < m) {
+      const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(bed + (size_t)row * pitch + (size_t)cc * 128) + w);
+      // PLINK code -> count, sixteen fields at once: 00 -> 0, 10 -> 1, 11 -> 2, 01 (missing) -> fill
+      const uint32_t b0 = x & 0x55555555u, b1 = (x >> 1) & 0x55555555u;
+      const uint32_t miss = b0 & ~b1, f = fillv[r];
+      const uint32_t val = b1 + (b1 & b0) + (f == 1u ? miss : (f == 2u ? miss << 1 : 0u));
+#pragma unroll
+      for (int nf = 0; nf < 16; ++nf) {                // new field 4 j + k <- raw field tc_perm16(4 k + j)
+        const int j = nf >> 2, k = nf & 3;
+        v |= ((val >> (2 * tc_perm16(4 * k + j))) & 3u) << (2 * nf);
+      }
+    }
+    reinterpret_cast<uint32_t*>(out + (((size_t)tile * n_cc + cc) * 128 + r) * 128)[w] = v;
   }
 }
 
@@ -1589,10 +1694,16 @@ int rhe_tc_create(rhe_ctx* c) {
   if (rc) return rc;
   {
     const int gs = pa_ring(s->NBa), smem = pa_smem_bytes(s->NBa, gs);
-    if (gs == 8) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else if (gs == 6) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else if (gs == 4) RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#define PA_ATTR(GS_)                                                                                            \
+    do {                                                                                                         \
+      RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<GS_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+      RHE_CUDA(cudaFuncSetAttribute(k_tc_pass_a<GS_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+    } while (0)
+    if (gs == 8) PA_ATTR(8);
+    else if (gs == 6) PA_ATTR(6);
+    else if (gs == 4) PA_ATTR(4);
+    else PA_ATTR(3);
+#undef PA_ATTR
   }
   {
     int shb;
@@ -1627,7 +1738,20 @@ int rhe_tc_set_rhs(rhe_ctx* c, cudaStream_t st) {
 
 unsigned int* rhe_tc_wmax(rhe_ctx* c) { return c->tc ? ((TcState*)c->tc)->wmax : nullptr; }
 
-int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
+int64_t rhe_tc_tiled_bytes(const rhe_ctx* c, int m) { return (int64_t)rhe_div_up(m, 128) * 128 * c->cfg.pitch_bytes; }
+
+int rhe_tc_retile(rhe_ctx* c, uint8_t* bed, int m, const int32_t* counts, uint8_t* scratch, cudaStream_t st) {
+  const rhe_config& g = c->cfg;
+  if (g.impute_binary && (!c->uniforms || c->n_uniforms < m)) { rhe_set_error("binary imputation needs rhe_set_uniforms first"); return RHE_ERR_STATE; }
+  const int n_cc = g.pitch_bytes / 128;
+  k_tc_retile<<<dim3(rhe_div_up(n_cc, 8), rhe_div_up(m, 128)), 256, 0, st>>>(bed, g.pitch_bytes, m, counts, g.n_kept,
+                                                                               g.impute_binary, c->uniforms, scratch);
+  RHE_LAUNCH_CHECK(c);
+  RHE_CUDA(cudaMemcpyAsync(bed, scratch, (size_t)rhe_tc_tiled_bytes(c, m), cudaMemcpyDeviceToDevice, st));
+  return RHE_OK;
+}
+
+int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, int tiled, cudaStream_t st) {
   TcState* s = (TcState*)c->tc;
   const int tiles = rhe_div_up(m, 128);
   // Split the individuals so that the grid fills whole waves of 2 resident CTAs per SM (a nearly empty last wave
@@ -1644,8 +1768,9 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
   }
   if (splits > c->Np / 512) splits = c->Np / 512 > 0 ? c->Np / 512 : 1;
   const uint32_t col_a = (uint32_t)round_up(s->NBa, 32);
-  CUtensorMap tm_bed;                                  // the block's packed rows as a 2-D byte tensor [m][pitch]
-  int rc = tc_encode_2d(s, &tm_bed, const_cast<uint8_t*>(bed), (uint64_t)c->cfg.pitch_bytes, (uint64_t)m, 128);
+  CUtensorMap tm_bed;                                  // the block's packed rows as a 2-D byte tensor [m][pitch], or its tiles
+  int rc = tiled ? tc_encode_2d(s, &tm_bed, const_cast<uint8_t*>(bed), 128, (uint64_t)tiles * 128 * (uint64_t)(c->cfg.pitch_bytes / 128), 128)
+                 : tc_encode_2d(s, &tm_bed, const_cast<uint8_t*>(bed), (uint64_t)c->cfg.pitch_bytes, (uint64_t)m, 128);
   if (rc) return rc;
   const int dbg = RHE_DBG_ENV("PYRHE_TC_DEBUG_SKIPA", 0);
   const int gs = pa_ring(s->NBa), smem = pa_smem_bytes(s->NBa, gs);
@@ -1654,13 +1779,11 @@ int rhe_tc_pass_a(rhe_ctx* c, const uint8_t* bed, int m, cudaStream_t st) {
     double* t_out = c->t_raw + (size_t)mode * m * c->R1;
     for (int ch = 0; ch * s->Rc < c->R1; ++ch) {          // one pass per chunk of RHS columns (a single one as a rule)
       const int c_lo = ch * s->Rc, rv = c->R1 - c_lo < s->Rc ? c->R1 - c_lo : s->Rc;
-#define PA_LAUNCH(GS_)                                                                                                 \
-      k_tc_pass_a<GS_><<<dim3(splits, tiles), PA_THREADS, smem, st>>>(s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, \
+#define PA_LAUNCH(GS_, T_)                                                                                                 \
+      k_tc_pass_a<GS_, T_><<<dim3(splits, tiles), PA_THREADS, smem, st>>>(s->tm_rq, tm_bed, m, c->Np, s->NBa, c->R1, s->R1p, \
           s->L, c_lo, rv, ch * s->NBa, c->fill, s->col_dq, t_out, cols, col_a, mode, mode ? 0 : dbg)
-      if (gs == 8) PA_LAUNCH(8);
-      else if (gs == 6) PA_LAUNCH(6);
-      else if (gs == 4) PA_LAUNCH(4);
-      else PA_LAUNCH(3);
+      if (tiled) { if (gs == 8) PA_LAUNCH(8, 1); else if (gs == 6) PA_LAUNCH(6, 1); else if (gs == 4) PA_LAUNCH(4, 1); else PA_LAUNCH(3, 1); }
+      else { if (gs == 8) PA_LAUNCH(8, 0); else if (gs == 6) PA_LAUNCH(6, 0); else if (gs == 4) PA_LAUNCH(4, 0); else PA_LAUNCH(3, 0); }
 #undef PA_LAUNCH
       RHE_LAUNCH_CHECK(c);
     }

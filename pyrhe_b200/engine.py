@@ -193,7 +193,7 @@ class RheEngine:
     def __init__(self, plan: PathPlan, *, n_indv: int, keep: np.ndarray, annot: np.ndarray, num_jack: int,
                  impute: str = "binary", seed: int = 0, device: Optional[torch.device] = None,
                  kernel_path: Optional[int] = None, rank: int = 0, world: int = 1,
-                 store_partials: bool = True, process_group=None):
+                 store_partials: bool = True, process_group=None, retile: bool = False):
         if not torch.cuda.is_available():
             raise _lib.RheError("pyrhe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -276,6 +276,13 @@ class RheEngine:
         #: use the individual-major copies where they exist (False: pass B always gathers SNP-major rows)
         self.use_fast_layout = True
         self.gt = {}
+        #: re-tile the SNP-major rows of every block that owns an individual-major copy once both ingest products are
+        #: taken (`rhe_block_retile`: contiguous 16 KB boxes of imputed counts for pass A).  Such a block can then be
+        #: read by `run()` only: no decode / recount / gather-kernel toggles (the models switch this on, the test hooks
+        #: of the engine leave it off)
+        self.retile = bool(retile) and kernel_path == _lib.PATH_TCGEN05
+        self._tiled = set()
+        self._retile_scratch = None
         self.S = self.P_all = None
         self._row_off = {}
         cur = 0
@@ -296,7 +303,7 @@ class RheEngine:
             self.lib.rhe_ctx_destroy(self._ctx)
             self._ctx = None
             # the genotype residency and the accumulators go back to the allocator with the context
-            self.bed = self.counts = self.S = self.P_all = None
+            self.bed = self.counts = self.S = self.P_all = self._retile_scratch = None
             self.gt = {}
 
     def __del__(self):
@@ -347,7 +354,17 @@ class RheEngine:
         lives in slot n % R until its kernels have run.  Next to the rows sit the per-SNP allele counts
         (`rhe_block_stats`), filled when a block becomes resident."""
         with torch.cuda.device(self.device):
-            if ring_blocks is None:
+            self._tiled = set()
+            self._retile_scratch = None
+            if ring_blocks is None and fast_layout and self.retile:
+                # every block starts on a 128-row boundary and owns whole 128-row tiles (rhe_block_retile)
+                self.ring_blocks = None
+                self._slot_off, rows = {}, 0
+                for j in self.own:
+                    self._slot_off[j] = rows
+                    rows += -(-(self.ranges[j][1] - self.ranges[j][0]) // 128) * 128
+                rows = max(rows, 1)
+            elif ring_blocks is None:
                 self.ring_blocks = None
                 rows = max(self.m_own, 1)
                 self._slot_off = dict(self._row_off)
@@ -370,6 +387,9 @@ class RheEngine:
                 self._collective_warm = True
             if ring_blocks is None and fast_layout:
                 self._alloc_fast_layout(reserve_bytes)
+                if self.retile and self.gt:
+                    self._retile_scratch = torch.empty(-(-self.max_m // 128) * 128 * self.pitch, dtype=torch.uint8,
+                                                       device=self.device)
         return self.bed
 
     def _alloc_fast_layout(self, reserve_bytes: float):
@@ -380,6 +400,8 @@ class RheEngine:
         free_b, _ = torch.cuda.mem_get_info(self.device)
         state = self.plan.E * self.plan.B * self.Np * 4
         budget = free_b - reserve_bytes - 3 * state      # S and the stored partials are allocated already (reserve_state)
+        if self.retile:
+            budget -= -(-self.max_m // 128) * 128 * self.pitch      # the scratch block of rhe_block_retile
         for j in self.own:
             need = int(self.lib.rhe_block_fast_bytes(self._ctx, self._plans[j]))
             if need <= 0 or need > budget:
@@ -413,6 +435,8 @@ class RheEngine:
     def count_block(self, j: int, stream=None):
         """Per-SNP allele counts of resident block j (`rhe_block_stats`): the one read of the block that depends on
         nothing but the genotypes, done when the block lands so that no later pass repeats it."""
+        if j in self._tiled:                           # counts and copies of a re-tiled block are final
+            return
         rows, m = self.block_view(j)
         st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
         cnt = self.counts[self._slot_off[j]: self._slot_off[j] + m]
@@ -420,6 +444,12 @@ class RheEngine:
         if j in self.gt:                               # ingest also writes the block's individual-major copy
             _lib.check(self.lib.rhe_block_transpose(self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], _lib.ptr(cnt),
                                                     _lib.ptr(self.gt[j]), st))
+            if self._retile_scratch is not None:       # ... and, last, re-tiles the rows themselves for pass A
+                if stream is not None:
+                    self._retile_scratch.record_stream(stream)
+                _lib.check(self.lib.rhe_block_retile(self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], _lib.ptr(cnt),
+                                                     _lib.ptr(self._retile_scratch), st))
+                self._tiled.add(j)
         self._counted.add(j)
 
     def count_all(self):
@@ -431,6 +461,7 @@ class RheEngine:
         a, b = self.ranges[j]
         m = b - a
         st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        self._tiled.discard(j)                         # fresh PLINK rows
         dst = self.bed[self._slot_off[j]]
         _lib.check(self.lib.rhe_upload_rows(_lib.ptr(host_rows), self.row_bytes, m, C.c_void_p(dst.data_ptr()),
                                             self.pitch, st))
@@ -470,12 +501,18 @@ class RheEngine:
     def _accumulate(self, j, P_out, S_accum, gram_out):
         rows, m = self.block_view(j)
         cnt = gt = None
+        layout = _lib.ROWS_PLINK
+        if j in self._tiled:
+            if not (self.use_resident_counts and self.use_fast_layout):
+                raise _lib.RheError(f"block {j} was re-tiled at ingest (retile=True): its rows serve pass A only, the "
+                                    "recount / gather-kernel toggles need an engine built with retile=False")
+            layout = _lib.ROWS_TILED
         if j in self._counted and self.use_resident_counts:
             cnt = C.c_void_p(self.counts.data_ptr() + 16 * self._slot_off[j])
             if self.use_fast_layout and j in self.gt:
                 gt = _lib.ptr(self.gt[j])
         _lib.check(self.lib.rhe_block_accumulate(
-            self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], cnt, gt, _lib.ptr(P_out), _lib.ptr(S_accum),
+            self._ctx, C.c_void_p(rows.data_ptr()), self._plans[j], cnt, gt, layout, _lib.ptr(P_out), _lib.ptr(S_accum),
             _lib.ptr(gram_out), self._stream()))
 
     def _pass(self, upload, body):
@@ -563,15 +600,20 @@ class RheEngine:
         return out
 
     # ------------------------------------------------------------------ test hooks
+    def _plink_rows(self, j: int):
+        if j in self._tiled:
+            raise _lib.RheError(f"block {j} was re-tiled at ingest (retile=True): its PLINK rows are gone")
+        return self.block_view(j)
+
     def decode_block(self, j: int, apply_impute: bool) -> np.ndarray:
-        rows, m = self.block_view(j)
+        rows, m = self._plink_rows(j)
         out = torch.empty((m, self.Np), dtype=torch.int8, device=self.device)
         _lib.check(self.lib.rhe_decode_block(self._ctx, C.c_void_p(rows.data_ptr()), m, int(apply_impute),
                                              _lib.ptr(out), self._stream()))
         return out.cpu().numpy()[:, : self.n_indv]
 
     def block_stats(self, j: int) -> np.ndarray:
-        rows, m = self.block_view(j)
+        rows, m = self._plink_rows(j)
         out = torch.empty((m, 4), dtype=torch.int32, device=self.device)
         _lib.check(self.lib.rhe_block_stats(self._ctx, C.c_void_p(rows.data_ptr()), m, _lib.ptr(out), self._stream()))
         return out.cpu().numpy()

@@ -90,7 +90,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.rhe_version() == 3
+    assert lib.rhe_version() == 4
     # argument validation happens before any CUDA call
     cfg = _lib.RheConfig(device=0, n_indv=10, n_kept=10, pitch_bytes=100, n_cols_set=4, n_sets=1, n_ops=1, n_vec=2,
                          n_bins=1, max_block_snps=8, impute_binary=0, kernel_path=0)

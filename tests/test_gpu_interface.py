@@ -304,3 +304,33 @@ def test_leave_one_out_gram_against_numpy(n_est):
     want = np.einsum("jal,jcl->jac", D, D)
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["rhe_cov_binary", "rhe_nocov_mean", "rhe_overlap", "dom_cov", "genie_full_cov", "rhe_example_shape"])
+def test_retiled_rows_give_the_same_block_results(name):
+    """`retile=True`: once the counts and the individual-major copy of a block are taken, its SNP-major rows are
+    rewritten in place as contiguous 16 KB boxes of imputed counts (`rhe_block_retile`) and pass A reads those
+    (`k_tc_pass_a<., 1>`: mask-and-shift decode, no per-SNP table).  Pass A is exact integer arithmetic on the same
+    values in the same order, so the per-bin Grams agree to fp64 round-off of their atomic sums; the decode / recount /
+    gather-kernel hooks of such an engine refuse to run instead of misreading the rows."""
+    from pyrhe_b200 import _lib
+    p = oracle_problem(name)
+    plan = plan_for(p)
+    out = {}
+    for retile in (False, True):
+        eng, _, _ = make_engine(p, plan, kernel_path=1, retile=retile)
+        assert len(eng._tiled) == (len(eng.own) if retile else 0)
+        pieces = eng.run()
+        out[retile] = (pieces, eng.S.cpu().numpy())
+        if retile:
+            with pytest.raises(_lib.RheError):
+                eng.decode_block(eng.own[0], apply_impute=False)
+            eng.use_fast_layout = False
+            with pytest.raises(_lib.RheError):
+                eng.run()
+        eng.close()
+    a, b = out[True], out[False]
+    gmax = np.abs(b[0]["G_blk"]).max()
+    np.testing.assert_allclose(a[0]["G_blk"], b[0]["G_blk"], rtol=0, atol=1e-12 * gmax)
+    np.testing.assert_allclose(a[0]["XX"], b[0]["XX"], rtol=1e-6)
+    np.testing.assert_allclose(a[1], b[1], rtol=0, atol=2e-6 * np.abs(b[1]).max())

@@ -20,7 +20,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 wl = dict(bench.WORKLOADS[wl_name])
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-args = types.SimpleNamespace(kernel_path=1)
+args = types.SimpleNamespace(kernel_path=1, retile=False)
 pb = bench.build_problem(wl, args, 0, 1, dev)
 eng = pb["eng"]
 lib = _lib.load()
@@ -48,3 +48,21 @@ if out[True][0] is not None:
         print("  [block, e, b, i] =", r, "fast", float(a[tuple(r)]), "gather", float(b[tuple(r)]))
 a, b = out[True][1], out[False][1]
 print("S max |diff| / max |S|:", float((a - b).abs().max() / b.abs().max()))
+
+# the same blocks with their rows re-tiled for pass A (contiguous boxes of imputed counts); results must not change
+G0 = eng.run()["G_blk"]
+eng.close()
+del pb, eng
+torch.cuda.empty_cache()
+pb = bench.build_problem(wl, types.SimpleNamespace(kernel_path=1, retile=True), 0, 1, dev)
+eng = pb["eng"]
+eng.run()
+_lib.check(lib.rhe_timing_enable(eng._ctx, 1))
+for _ in range(steps):
+    pieces = eng.run()
+ph = (C.c_double * 4)()
+n = C.c_int32()
+_lib.check(lib.rhe_timing_collect(eng._ctx, ph, C.byref(n)))
+print("retiled", {k: round(ph[i] / max(n.value, 1), 4) for i, k in enumerate(names)}, "tiled blocks", len(eng._tiled), flush=True)
+print("G_blk max |diff| / max:", float(np.abs(pieces["G_blk"] - G0).max() / np.abs(G0).max()),
+      "P identical to the PLINK-row run:", bool(torch.equal(eng.P_all, out[True][0])) if out[True][0] is not None else None)
