@@ -389,10 +389,12 @@ def main():
     total_bytes = float((N + 3) // 4) * M
     value = total_bytes / (ms_step * 1e-3) / 1e9
     # the round-1 structure for comparison: allele counts re-taken inside every block call (three reads per block)
-    eng.use_resident_counts = False
-    step_resident()
-    ms_recount, _ = timed(step_resident, 1)
-    eng.use_resident_counts = True
+    ms_recount = None
+    if not eng._tiled:                                         # (re-tiled rows cannot be re-counted: --no_retile runs this leg)
+        eng.use_resident_counts = False
+        step_resident()
+        ms_recount, _ = timed(step_resident, 1)
+        eng.use_resident_counts = True
 
     # ---- roofline of the dominant kernel: per-phase CUDA-event timing over one more step
     _lib.check(lib.rhe_timing_enable(eng._ctx, 1))
