@@ -194,6 +194,7 @@ def model_api_e2e(args, dev):
     threads -> pinned ring -> PCIe -> HBM -> kernels -> estimates).  Run twice more with the genotype ring forced
     (`PYRHE_B200_RING_BLOCKS=4`): HBM use bounded by four block slots whatever the size of the file, once with stored
     partials (one pass over the file) and once with the streaming policy (two passes)."""
+    import gc
     import shutil
     import tempfile
     import torch
@@ -216,6 +217,7 @@ def model_api_e2e(args, dev):
                 os.environ.pop("PYRHE_B200_RING_BLOCKS", None)
             else:
                 os.environ["PYRHE_B200_RING_BLOCKS"] = str(ring)
+            gc.collect()                                       # the previous model's engine (cyclic references) must be gone
             torch.cuda.empty_cache()
             torch.cuda.reset_peak_memory_stats(dev)
             t0 = time.perf_counter()

@@ -143,7 +143,8 @@ int rhe_block_transpose(rhe_ctx* ctx, const uint8_t* bed_dev, const rhe_block_pl
  *   [n_snps / 128][pitch / 128][128 rows][128 B]   every TMA box of pass A is one contiguous 16 KB piece (streams from HBM
  *                        like a copy instead of 128 row-strided segments) and the two bits of a genotype hold the imputed
  *                        A2 count (mask-and-shift decode, no per-SNP table).
- * The rows buffer must hold rhe_block_tiled_bytes (the SNP count rounded up to 128 rows); scratch_dev as many bytes.
+ * The rows buffer must hold rhe_block_tiled_bytes (the SNP count rounded up to 128 rows; 0 = not available: 2^21 or more
+ * individuals, or no tensor-core path); scratch_dev as many bytes.
  * Afterwards the rows are readable ONLY by rhe_block_accumulate(..., rows_layout = RHE_ROWS_TILED) with counts and copy. */
 int64_t rhe_block_tiled_bytes(const rhe_ctx* ctx, const rhe_block_plan* plan);
 int rhe_block_retile(rhe_ctx* ctx, uint8_t* bed_dev, const rhe_block_plan* plan, const int32_t* counts_dev,

@@ -246,6 +246,22 @@ __device__ __forceinline__ uint32_t tc_shr_fma(uint32_t x, uint32_t pow2) {   //
   asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(pow2));
   return r;
 }
+// x << s as a multiply: IMAD.SHL on the FMA pipe (the ALU pipe carries the masks and the right shifts of the decode)
+__device__ __forceinline__ uint32_t tc_shl_fma(uint32_t x, uint32_t pow2) {
+  uint32_t r;
+  asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(pow2));
+  return r;
+}
+// TC_SHIFT_VARIANT 2: the mask-and-shift expansions deliver 4 x value (the two bits of a field land on bits 2-3 of their
+// byte), which turns one of the three right shifts per word into a left shift on the other pipe; the epilogues divide by 4.
+// Measured: pass A on re-tiled rows 0.272 -> 0.261 ms, pass B from tensor memory 0.343 -> 0.349 ms -- so pass A takes it
+// (TC_PA_SHIFT_VARIANT) and pass B does not.  With values up to 8 the int32 accumulation of pass A is exact for
+// 8 x 128 x N < 2^31, i.e. N < 2^21 individuals (rhe_block_tiled_bytes answers 0 beyond that).
+#ifndef TC_PA_SHIFT_VARIANT
+#define TC_PA_SHIFT_VARIANT 2
+#endif
+#define TC_VALUE_SCALE (TC_SHIFT_VARIANT == 2 ? 0.25 : 1.0)
+#define TC_PA_VALUE_SCALE (TC_PA_SHIFT_VARIANT == 2 ? 0.25 : 1.0)
 template <int MULHI = 1>
 __device__ __forceinline__ uint4 tc_expand(uint32_t w, uint32_t tab) {
   const uint32_t e = w & 0x33333333u;
@@ -444,17 +460,25 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
       if constexpr (TILED) {
         uint4 r;
         if (mode == 0) {
+#if TC_PA_SHIFT_VARIANT == 2
+          const uint32_t mk = 0x0C0C0C0Cu;
+          r.x = tc_shl_fma(w, 4u) & mk; r.y = w & mk; r.z = (w >> 2) & mk; r.w = (w >> 4) & mk;
+#elif TC_PA_SHIFT_VARIANT == 1
           const uint32_t mk = 0x03030303u;
-#if TC_SHIFT_VARIANT == 1
           r.x = w & mk; r.y = (w >> 2) & mk; r.z = (w >> 4) & mk; r.w = (w >> 6) & mk;
 #else
+          const uint32_t mk = 0x03030303u;
           r.x = w & mk; r.y = tc_shr_fma(w, 1u << 30) & mk; r.z = tc_shr_fma(w, 1u << 28) & mk; r.w = tc_shr_fma(w, 1u << 26) & mk;
 #endif
         } else {
+#if TC_PA_SHIFT_VARIANT == 2
+          const uint32_t mk = 0x04040404u;
+          r.x = tc_shl_fma(w, 2u) & mk; r.y = (w >> 1) & mk; r.z = (w >> 3) & mk; r.w = (w >> 5) & mk;
+#elif TC_PA_SHIFT_VARIANT == 1
           const uint32_t mk = 0x01010101u;
-#if TC_SHIFT_VARIANT == 1
           r.x = (w >> 1) & mk; r.y = (w >> 3) & mk; r.z = (w >> 5) & mk; r.w = (w >> 7) & mk;
 #else
+          const uint32_t mk = 0x01010101u;
           r.x = tc_shr_fma(w, 1u << 31) & mk; r.y = tc_shr_fma(w, 1u << 29) & mk;
           r.z = tc_shr_fma(w, 1u << 27) & mk; r.w = tc_shr_fma(w, 1u << 25) & mk;
 #endif
@@ -532,7 +556,7 @@ k_tc_pass_a(const __grid_constant__ CUtensorMap tm_rq, const __grid_constant__ C
       if (snp < m) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < Rv) atomicAdd(t_raw + (size_t)snp * R1 + c_lo + c0 + j, val[j] * col_dq[c_lo + c0 + j]);
+          if (c0 + j < Rv) atomicAdd(t_raw + (size_t)snp * R1 + c_lo + c0 + j, val[j] * ((TILED ? TC_PA_VALUE_SCALE : 1.0) * col_dq[c_lo + c0 + j]));
       }
     }
     tc_fence_before();
@@ -1105,7 +1129,7 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
   for (int i = threadIdx.x; i < n_sub; i += P2_THREADS) sm->vbin[i] = stage_info[i] & 255;   // bin of every sub-tile
   for (int i = threadIdx.x; i < WG * B; i += P2_THREADS) {
     const int ex = (int)((wmax[i] >> 23) & 255u);       // same rule as k_tc_quant_w / the gather kernel
-    sm->dq[i] = ex == 255 ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, ex - 126 - F);
+    sm->dq[i] = ex == 255 ? __longlong_as_double(0x7ff8000000000000ll) : TC_VALUE_SCALE * ldexp(1.0, ex - 126 - F);
   }
   tc_fence_before();
   __syncthreads();
@@ -1146,6 +1170,15 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
       if (++fsl == (uint32_t)GS) { fsl = 0; fpar ^= 1u; }
     };
     auto expand0 = [](uint32_t w) {
+#if TC_SHIFT_VARIANT == 2
+      const uint32_t m = 0x0C0C0C0Cu;
+      uint4 r;
+      r.x = tc_shl_fma(w, 4u) & m;
+      r.y = w & m;
+      r.z = (w >> 2) & m;
+      r.w = (w >> 4) & m;
+      return r;
+#else
       const uint32_t m = 0x03030303u;
       uint4 r;
       r.x = w & m;
@@ -1159,8 +1192,18 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
       r.w = tc_shr_fma(w, 1u << 26) & m;
 #endif
       return r;
+#endif
     };
     auto expand1 = [](uint32_t w) {
+#if TC_SHIFT_VARIANT == 2
+      const uint32_t m4 = 0x04040404u;
+      uint4 r4;
+      r4.x = tc_shl_fma(w, 2u) & m4;
+      r4.y = (w >> 1) & m4;
+      r4.z = (w >> 3) & m4;
+      r4.w = (w >> 5) & m4;
+      return r4;
+#else
       const uint32_t m = 0x01010101u;
       uint4 r;
 #if TC_SHIFT_VARIANT == 1
@@ -1175,6 +1218,7 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
       r.w = tc_shr_fma(w, 1u << 25) & m;
 #endif
       return r;
+#endif
     };
     // one operand of one sub-tile -> the group's next A slot; `release`: the packed words are not needed again
     auto put = [&](const uint4& lo, const uint4& hi, auto expand, bool release) {
@@ -1738,10 +1782,14 @@ int rhe_tc_set_rhs(rhe_ctx* c, cudaStream_t st) {
 
 unsigned int* rhe_tc_wmax(rhe_ctx* c) { return c->tc ? ((TcState*)c->tc)->wmax : nullptr; }
 
-int64_t rhe_tc_tiled_bytes(const rhe_ctx* c, int m) { return (int64_t)rhe_div_up(m, 128) * 128 * c->cfg.pitch_bytes; }
+int64_t rhe_tc_tiled_bytes(const rhe_ctx* c, int m) {
+  if (TC_PA_SHIFT_VARIANT == 2 && c->Np >= (1 << 21)) return 0;      // the x4 operand values need 8 x 128 x N < 2^31
+  return (int64_t)rhe_div_up(m, 128) * 128 * c->cfg.pitch_bytes;
+}
 
 int rhe_tc_retile(rhe_ctx* c, uint8_t* bed, int m, const int32_t* counts, uint8_t* scratch, cudaStream_t st) {
   const rhe_config& g = c->cfg;
+  if (rhe_tc_tiled_bytes(c, m) == 0) { rhe_set_error("rhe_block_retile: not available for %d individuals (see rhe_block_tiled_bytes)", c->Np); return RHE_ERR_UNSUPPORTED; }
   if (g.impute_binary && (!c->uniforms || c->n_uniforms < m)) { rhe_set_error("binary imputation needs rhe_set_uniforms first"); return RHE_ERR_STATE; }
   const int n_cc = g.pitch_bytes / 128;
   k_tc_retile<<<dim3(rhe_div_up(n_cc, 8), rhe_div_up(m, 128)), 256, 0, st>>>(bed, g.pitch_bytes, m, counts, g.n_kept,

@@ -387,7 +387,7 @@ class RheEngine:
                 self._collective_warm = True
             if ring_blocks is None and fast_layout:
                 self._alloc_fast_layout(reserve_bytes)
-                if self.retile and self.gt:
+                if self.retile and self.gt and int(self.lib.rhe_block_tiled_bytes(self._ctx, self._plans[self.own[0]])) > 0:
                     self._retile_scratch = torch.empty(-(-self.max_m // 128) * 128 * self.pitch, dtype=torch.uint8,
                                                        device=self.device)
         return self.bed
