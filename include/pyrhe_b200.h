@@ -164,6 +164,13 @@ int rhe_block_accumulate(rhe_ctx* ctx, const uint8_t* bed_dev, const rhe_block_p
                          const int32_t* counts_dev, const uint8_t* gt_dev, int32_t rows_layout, float* P_out_dev,
                          float* S_accum_dev, double* gram_out_dev, void* stream);
 
+/* base.py:483-486 (totals over the blocks): S[i] = sum_j P[j * p_stride + i], j in block order, `len` floats (a multiple
+ * of 4).  With stored partials a caller may pass S_accum_dev = NULL to rhe_block_accumulate and sum once here: one
+ * streaming read of the partials instead of a read-modify-write of S in every block's pass B, for a total that is
+ * bit-reproducible from run to run (the RED accumulation is not; it is slightly faster). */
+int rhe_sum_partials(rhe_ctx* ctx, const float* P_dev, int64_t p_stride, int32_t n_blocks, int64_t len, float* S_dev,
+                     void* stream);
+
 /* base.py:578-581 after aggregate (base.py:483-486): out[a][c] = sum (S_a - P_a)(S_c - P_c)
  * over `len` floats per estimate; P_dev may be NULL (totals).  out_dev double [n_est][n_est]. */
 int rhe_loo_gram(rhe_ctx* ctx, const float* S_dev, const float* P_dev, int32_t n_est,

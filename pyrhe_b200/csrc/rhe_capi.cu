@@ -1098,6 +1098,40 @@ extern "C" int rhe_block_accumulate(rhe_ctx* c, const uint8_t* bed, const rhe_bl
   return RHE_OK;
 }
 
+// S = sum_j P_j over the stored block partials, in block order (fp32, one streaming read of the partials): the totals of
+// base.py:483-486 without a read-modify-write of S in every block's pass B, and bit-reproducible from run to run.
+__global__ void __launch_bounds__(256)
+k_sum_partials(const float4* __restrict__ P, int64_t p_stride4, int n_blocks, int64_t len4, float4* __restrict__ S) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + 4 <= n_blocks; j += 4) {                // four loads in flight per thread
+      const float4 a = __ldcs(P + (size_t)j * p_stride4 + i), b = __ldcs(P + (size_t)(j + 1) * p_stride4 + i);
+      const float4 c = __ldcs(P + (size_t)(j + 2) * p_stride4 + i), d = __ldcs(P + (size_t)(j + 3) * p_stride4 + i);
+      acc.x = ((acc.x + a.x) + b.x) + c.x + d.x; acc.y = ((acc.y + a.y) + b.y) + c.y + d.y;
+      acc.z = ((acc.z + a.z) + b.z) + c.z + d.z; acc.w = ((acc.w + a.w) + b.w) + c.w + d.w;
+    }
+    for (; j < n_blocks; ++j) {
+      const float4 a = __ldcs(P + (size_t)j * p_stride4 + i);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    S[i] = acc;
+  }
+}
+
+extern "C" int rhe_sum_partials(rhe_ctx* c, const float* P, int64_t p_stride, int32_t n_blocks, int64_t len, float* S,
+                                void* stream) {
+  if (!c || !P || !S) { rhe_set_error("rhe_sum_partials: NULL argument"); return RHE_ERR_INVALID; }
+  if (n_blocks < 1 || len < 0 || len % 4 != 0 || p_stride % 4 != 0) { rhe_set_error("rhe_sum_partials: bad block count / length / stride"); return RHE_ERR_INVALID; }
+  if (len == 0) return RHE_OK;
+  const int64_t len4 = len / 4;
+  const int grid = (int)(len4 / 256 + 1 < 148 * 16 ? len4 / 256 + 1 : 148 * 16);
+  k_sum_partials<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(P), p_stride / 4, n_blocks, len4,
+                                                         reinterpret_cast<float4*>(S));
+  RHE_LAUNCH_CHECK(c);
+  return RHE_OK;
+}
+
 extern "C" int rhe_loo_gram_multi(rhe_ctx* c, const float* S, const float* P, int64_t p_stride, int32_t n_blocks,
                                   int32_t n_est, int64_t len, double* out, int64_t out_stride, void* stream) {
   if (!c || !S || !P || !out) { rhe_set_error("rhe_loo_gram_multi: NULL argument"); return RHE_ERR_INVALID; }

@@ -334,3 +334,25 @@ def test_retiled_rows_give_the_same_block_results(name):
     np.testing.assert_allclose(a[0]["G_blk"], b[0]["G_blk"], rtol=0, atol=1e-12 * gmax)
     np.testing.assert_allclose(a[0]["XX"], b[0]["XX"], rtol=1e-6)
     np.testing.assert_allclose(a[1], b[1], rtol=0, atol=2e-6 * np.abs(b[1]).max())
+
+
+def test_totals_summed_from_stored_partials_are_reproducible():
+    """`sum_stored_partials`: S = sum_j P_j in block order (`rhe_sum_partials`) instead of RED from every pass B -- the
+    same totals to fp32 round-off, and identical from run to run."""
+    p = oracle_problem("rhe_cov_binary")
+    plan = plan_for(p)
+    eng, _, _ = make_engine(p, plan, kernel_path=1)
+    ref = eng.run()
+    S_red = eng.S.cpu().numpy().copy()
+    eng.sum_stored_partials = True
+    a = eng.run()
+    S1 = eng.S.cpu().numpy().copy()
+    P1 = eng.P_all.cpu().numpy()
+    b = eng.run()
+    S2 = eng.S.cpu().numpy()
+    eng.close()
+    np.testing.assert_allclose(S1, S_red, rtol=0, atol=2e-6 * np.abs(S_red).max())
+    np.testing.assert_allclose(S1, P1.astype(np.float64).sum(axis=0), rtol=0, atol=2e-6 * np.abs(S_red).max())
+    np.testing.assert_array_equal(S1, S2)
+    np.testing.assert_allclose(a["XX"], b["XX"], rtol=1e-12)   # (the Gram's own fp64 atomics are not ordered)
+    np.testing.assert_allclose(a["XX"], ref["XX"], rtol=2e-6)

@@ -25,19 +25,23 @@ def tail(pieces, buf=[None]):
     return np.linalg.solve(T, q[..., None])[..., 0]
 
 
-for _ in range(3):
-    tail(eng.run())
-torch.cuda.synchronize()
 n = 10
-t0 = time.perf_counter()
-for _ in range(n):
-    pieces = eng.run()
-torch.cuda.synchronize()
-t1 = time.perf_counter()
-for _ in range(n):
-    tail(pieces)
-t2 = time.perf_counter()
-print(f"run() {1e3 * (t1 - t0) / n:.3f} ms, host tail {1e3 * (t2 - t1) / n:.3f} ms per step")
+for mode in (True, False):
+    eng.sum_stored_partials = mode
+    for _ in range(3):
+        tail(eng.run())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        pieces = eng.run()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(n):
+        tail(pieces)
+    t2 = time.perf_counter()
+    print(f"totals {'summed from the stored partials' if mode else 'by RED in pass B'}: run() {1e3 * (t1 - t0) / n:.3f} ms, "
+          f"host tail {1e3 * (t2 - t1) / n:.3f} ms per step")
+eng.sum_stored_partials = True
 # inside run(): device time of the block loop alone
 S, P_all = eng.reserve_state()
 G_blk = torch.zeros((eng.J, plan.E_reg, plan.Rs, plan.Rs), dtype=torch.float64, device=dev)
