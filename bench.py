@@ -436,6 +436,7 @@ def main():
                 p4 = phases_of(blocks)
                 pass_a_kernels[name_a] = {"blocks": len(blocks), "launch_ms": p4[1]}
                 pb_kernels[name_b] = {"blocks": len(blocks), "launch_ms": p4[3]}
+        del phases_of, S_buf, P_buf, gscr                      # (views of the engine's accumulators must not outlive it)
     dom = max(("pass_a", "pass_b"), key=lambda n: ph[n])
     m_avg = sum(eng.ranges[j][1] - eng.ranges[j][0] for j in eng.own) / max(len(eng.own), 1)
     alg_bytes = float((N + 3) // 4) * m_avg
