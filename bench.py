@@ -463,8 +463,9 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath) and args.kernel_path == 1 and args.workload == "config5":
         tr = json.load(open(tpath))
-        if dom == "pass_a":
-            traffic = tr.get("k_tc_pass_a")
+        if dom == "pass_a":                                    # per launch, averaged over this rank's blocks
+            n_t = len(eng._tiled)
+            traffic = (tr["k_tc_pass_a_retiled"] * n_t + tr["k_tc_pass_a"] * (n_own - n_t)) / n_own
         elif tr.get("k_tc_pass_b2") and tr.get("k_tc_pass_b"):     # per launch, averaged over this rank's blocks
             traffic = (tr["k_tc_pass_b2"] * n_fast + tr["k_tc_pass_b"] * (n_own - n_fast)) / n_own
     block_ms = sum(ph.values())
