@@ -356,3 +356,31 @@ def test_totals_summed_from_stored_partials_are_reproducible():
     np.testing.assert_array_equal(S1, S2)
     np.testing.assert_allclose(a["XX"], b["XX"], rtol=1e-12)   # (the Gram's own fp64 atomics are not ordered)
     np.testing.assert_allclose(a["XX"], ref["XX"], rtol=2e-6)
+
+
+def test_retile_is_refused_beyond_two_million_individuals():
+    """Pass A on re-tiled rows feeds 4 x the count to the MMA, so its int32 accumulation is exact only for
+    8 x 128 x N < 2^31: `rhe_block_tiled_bytes` answers 0 from 2^21 individuals on and the engine keeps the PLINK rows."""
+    from pyrhe_b200.assemble import PathPlan
+    from pyrhe_b200.engine import RheEngine
+    from pyrhe_b200 import synth
+    rng = np.random.default_rng(5)
+    N, M, K, B, J = (1 << 21) + 7, 24, 1, 2, 2
+    packed = synth.pack_counts(synth.random_counts(N, M, rng))
+    eng = RheEngine(PathPlan(model="rhe", K=K, B=B, C=0), n_indv=N, keep=np.ones(N, bool), annot=np.ones((M, K), dtype=np.int64),
+                    num_jack=J, impute="mean", seed=0, kernel_path=1, retile=True)
+    assert int(eng.lib.rhe_block_tiled_bytes(eng._ctx, eng._plans[0])) == 0
+    Z = rng.standard_normal((N, B))
+    y = rng.standard_normal((N, 1))
+    eng.set_rhs(Z, None, y - y.mean())
+    eng.load_genotypes(packed)
+    assert len(eng.gt) == J and not eng._tiled and eng._retile_scratch is None
+    out = eng.run()
+    eng.close()
+    # <X X^T z, z> summed over the vectors against float64 numpy on the decoded counts
+    g = np.where(np.unpackbits(packed[:, :, None], axis=2, bitorder="little").reshape(M, -1, 2)[:, :N].dot([1, 2]) == 2, 1,
+                 np.where(np.unpackbits(packed[:, :, None], axis=2, bitorder="little").reshape(M, -1, 2)[:, :N].dot([1, 2]) == 3, 2, 0))
+    mu = g.mean(axis=1, keepdims=True)
+    X = ((g - mu) / np.sqrt(mu * (1 - mu / 2))).T
+    XXz = X @ (X.T @ Z)
+    np.testing.assert_allclose(out["XX"][J, 0, 0], np.sum(XXz * XXz), rtol=1e-5)
