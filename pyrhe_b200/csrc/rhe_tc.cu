@@ -706,15 +706,21 @@ __device__ __forceinline__ void pb_chunk(uint32_t taddr, uint32_t stride, int nv
 #pragma unroll
   for (int l = 0; l < L; ++l) tmem_ldw_nc<W>(taddr + (uint32_t)l * stride, a[l]);
   tmem_ld_fence<L, W>(a);
+  // all W values first, without branches (their dependent chains interleave), then the stores; a padding column
+  // (j >= nvalid) reads table entries of its neighbour and is dropped
+  float xf[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    double val = (double)a[L - 1][j];
+#pragma unroll
+    for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
+    xf[j] = (float)(rs * (val * lds_f64_nv(dq_a + 8u * (uint32_t)j) - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
+  }
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     if (j < nvalid) {
-      double val = (double)a[L - 1][j];
-#pragma unroll
-      for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
-      const float xf = (float)(rs * (val * lds_f64_nv(dq_a + 8u * (uint32_t)j) - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
-      if (wp) P_out[idx] = xf;
-      if (ws) atomicAdd(S_accum + idx, xf);            // result unused -> RED: no load round trip
+      if (wp) P_out[idx] = xf[j];
+      if (ws) atomicAdd(S_accum + idx, xf[j]);         // result unused -> RED: no load round trip
       idx += Np;
     }
   }
@@ -1052,15 +1058,21 @@ __device__ __forceinline__ void p2_drain_chunk(uint32_t taddr, uint32_t stride, 
   tmem_ld_fence<L, W>(a);
 #pragma unroll
   for (int l = 0; l < L; ++l) tmem_zero_nc<W>(taddr + (uint32_t)l * stride);
+  // all W values first, without branches (the chains of the W columns interleave: the drain warps run alone on their
+  // scheduler slots, so their latency is the dependent chain of whatever sits between two branches), then the stores
+  float xf[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    double val = (double)a[L - 1][j];
+#pragma unroll
+    for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
+    xf[j] = (float)(rs * (val * lds_f64_nv(dq_a + 8u * (uint32_t)j) - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
+  }
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     if (j < nvalid) {
-      double val = (double)a[L - 1][j];
-#pragma unroll
-      for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
-      const float xf = (float)(rs * (val * lds_f64_nv(dq_a + 8u * (uint32_t)j) - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
-      if (wp) P_out[idx] = xf;
-      if (ws) atomicAdd(S_accum + idx, xf);            // result unused -> RED
+      if (wp) P_out[idx] = xf[j];
+      if (ws) atomicAdd(S_accum + idx, xf[j]);         // result unused -> RED
       idx += Np;
     }
   }
