@@ -1025,6 +1025,9 @@ k_tc_pass_b(const __grid_constant__ CUtensorMap tm_uq, const uint8_t* __restrict
 #define P2_MAXRING 8
 #define P2_MAXACC 4               // accumulator buffers (bins in flight between the MMA issuers and the drain warps)
 #define P2_MAXSUB 1024            // sub-tiles (128 positions) of one M-tile, all operands
+#ifndef P2_DRAIN_BY_BIN
+#define P2_DRAIN_BY_BIN 1         // the two drain sets alternate BINS (1) or split the columns of every bin (0)
+#endif
 
 struct P2Smem {
   uint64_t full_a[P2_AS], empty_a[P2_AS], full_u[P2_MAXRING], empty_u[P2_MAXRING], full_g[P2_MAXRING], empty_g[P2_MAXRING];
@@ -1132,7 +1135,10 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
       mbar_init(&sm->full_u[s], 1); mbar_init(&sm->empty_u[s], 4 * n_modes);   // 4 sub-tiles x operands
       mbar_init(&sm->full_g[s], 1); mbar_init(&sm->empty_g[s], 16);     // 4 sub-tiles x 4 warps
     }
-    for (int s = 0; s < P2_MAXACC; ++s) { mbar_init(&sm->bin_full[s], P2_G); mbar_init(&sm->acc_free[s], P2_NDRAIN); }
+    for (int s = 0; s < P2_MAXACC; ++s) {
+      mbar_init(&sm->bin_full[s], P2_G);
+      mbar_init(&sm->acc_free[s], P2_DRAIN_BY_BIN ? P2_NDRAIN / 2 : P2_NDRAIN);
+    }
     fence_barrier_init();
   }
   if (warp == P2_W_PROD) tmem_alloc(&sm->tmem_base, tmem_cols);
@@ -1379,9 +1385,12 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
     // bin, so each accumulator buffer's barriers advance one phase per use and a parity wait is never ambiguous.  Set 0
     // takes the columns [0, c_split) of every weight group, set 1 the columns [c_split, Bp).
     const int t = (warp & 3) * 32 + lane, am = n_acc - 1, sh = n_acc == 4 ? 2 : n_acc - 1;
+    // P2_DRAIN_BY_BIN: set s takes the bins Vg = s (mod 2) whole -- an accumulator buffer (Vg mod n_acc, n_acc even) is then
+    // always drained by the same set, and a set has two bin periods for its bin: with ten vectors a column split is 4 | 6
+    // (two chunks on the critical path of every bin), alternate bins are three chunks per two bin periods.
     const int set = (warp - P2_W_DRAIN) >> 2;
     const int c_split = min(Bp, 4 * ((Bp / 2 + 2) / 4));
-    const int c_lo = set ? c_split : 0, c_hi = set ? Bp : c_split;
+    const int c_lo = P2_DRAIN_BY_BIN ? 0 : (set ? c_split : 0), c_hi = P2_DRAIN_BY_BIN ? Bp : (set ? Bp : c_split);
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t bfull = smem_u32(&sm->bin_full[0]), afree = smem_u32(&sm->acc_free[0]);
     const uint32_t dq_s = smem_u32(sm->dq), cs_s = smem_u32(sm->cs);
@@ -1390,6 +1399,7 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
       const int i = ((int)blockIdx.x + it * (int)gridDim.x) * 128 + t;
       const float rs0 = rowscale[i], rs1 = WG > 1 ? rowscale[(size_t)rs_stride + i] : 0.f;
       for (int v = 0; v < V; ++v, ++Vg) {
+        if (P2_DRAIN_BY_BIN && (Vg & 1) != set) continue;
         const int k = v, buf = Vg & am;
         mbar_wait_s(bfull + 8u * (uint32_t)buf, (uint32_t)(Vg >> sh) & 1u);
         tc_fence_after();
