@@ -1051,7 +1051,7 @@ __device__ __forceinline__ void tmem_zero_nc(uint32_t taddr) {     // zero W col
 // is the individual's entry of the chunk's first column in P / S (32-bit element index: the launch checks that the
 // accumulators hold fewer than 2^31 floats); successive columns are `Np` floats apart.  The columns are zeroed again as
 // soon as they are in registers (all MMAs accumulate).
-template <int L, int W>
+template <int L, int W, int SMALL>
 __device__ __forceinline__ void p2_drain_chunk(uint32_t taddr, uint32_t stride, int nvalid, uint32_t Np, double rs, uint32_t dq_a,
                                                uint32_t cs_a, float* __restrict__ P_out, float* __restrict__ S_accum,
                                                bool wp, bool ws, uint32_t idx) {
@@ -1066,9 +1066,19 @@ __device__ __forceinline__ void p2_drain_chunk(uint32_t taddr, uint32_t stride, 
   float xf[W];
 #pragma unroll
   for (int j = 0; j < W; ++j) {
-    double val = (double)a[L - 1][j];
+    double val;
+    if constexpr (SMALL && L >= 2) {
+      // bins of at most 2^14 positions: |limb sum| <= 2 x 128 x 2^14 = 2^22, so the two low limbs combine exactly in
+      // int32 (one integer multiply-add on the FMA pipe instead of a conversion and an fp64 FMA)
+      const int32_t lo = a[1][j] * 256 + a[0][j];
+      val = (double)lo;
+      if constexpr (L >= 3) val = fma((double)a[2][j], 65536.0, val);
+      if constexpr (L >= 4) val = fma((double)a[3][j], 16777216.0, val);
+    } else {
+      val = (double)a[L - 1][j];
 #pragma unroll
-    for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
+      for (int l = L - 2; l >= 0; --l) val = fma(val, 256.0, (double)a[l][j]);   // exact: |value| < 2^53
+    }
     xf[j] = (float)(rs * (val * lds_f64_nv(dq_a + 8u * (uint32_t)j) - lds_f64_nv(cs_a + 8u * (uint32_t)j)));
   }
 #pragma unroll
@@ -1082,7 +1092,7 @@ __device__ __forceinline__ void p2_drain_chunk(uint32_t taddr, uint32_t stride, 
 }
 
 // Drain the columns [c_lo, c_hi) of every weight group of bin k for this thread's individual.
-template <int L>
+template <int L, int SMALL>
 __device__ __forceinline__ void p2_drain(uint32_t tcol, int c_lo, int c_hi, int k, int i, int K, int WG, int B, int Bp,
                                          uint32_t Np, uint32_t dq_s, uint32_t cs_s, float rs0, float rs1,
                                          float* __restrict__ P_out, float* __restrict__ S_accum) {
@@ -1094,11 +1104,11 @@ __device__ __forceinline__ void p2_drain(uint32_t tcol, int c_lo, int c_hi, int 
     uint32_t idx = (uint32_t)((wg * K + k) * B + c_lo) * Np + (uint32_t)i;
     int c0 = c_lo;
     for (; c0 + 4 <= c_hi; c0 += 4) {
-      p2_drain_chunk<L, 4>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
+      p2_drain_chunk<L, 4, SMALL>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
       dq_a += 32u; cs_a += 32u; idx += 4u * Np;
     }
     for (; c0 < c_hi; c0 += 2) {
-      p2_drain_chunk<L, 2>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
+      p2_drain_chunk<L, 2, SMALL>(base + (uint32_t)c0, (uint32_t)Bp, B - c0, Np, rs, dq_a, cs_a, P_out, S_accum, wp, ws, idx);
       dq_a += 16u; cs_a += 16u; idx += 2u * Np;
     }
   }
@@ -1406,9 +1416,12 @@ k_tc_pass_b2(const __grid_constant__ CUtensorMap tm_uq, const __grid_constant__ 
         const bool has = sm->cnt[k] > 0;
         const uint32_t tcol = lane_base + (uint32_t)(buf * acc_stride);
         if (has) {
-          if (L == 3) p2_drain<3>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
-          else if (L == 2) p2_drain<2>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
-          else p2_drain<4>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
+          // (the operands of RHE-DOM share an accumulator: twice the positions per bin)
+          const bool small = sm->cnt[k] * n_modes <= (1 << 14);
+          if (L == 3 && small) p2_drain<3, 1>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
+          else if (L == 3) p2_drain<3, 0>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
+          else if (L == 2) p2_drain<2, 0>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
+          else p2_drain<4, 0>(tcol, c_lo, c_hi, k, i, K, WG, B, Bp, (uint32_t)Np, dq_s, cs_s, rs0, rs1, P_out, S_accum);
           tmem_st_wait();                              // the columns this warp read are zero again
         } else if (P_out) {                              // a bin without SNPs in this block: X (X^T Z) = 0
           for (int wg = 0; wg < WG; ++wg)
