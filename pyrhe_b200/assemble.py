@@ -170,19 +170,18 @@ def loo_grams(G_blk: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
     return out
 
 
-def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo: np.ndarray, M_tab: np.ndarray,
-                           trait: int = 0, nxe_quirk: bool = True):
-    """Vectorised `normal_equations` over all jackknife samples (the production path).
-
-    XX [S, E, E], G_loo [S, E_reg, Rs, Rs], M_tab [S, E]  ->  T [S, E+1, E+1], q [S, E+1]."""
+def normal_equations_prepare(plan: PathPlan, ht: HostTerms, G_loo: np.ndarray, M_tab: np.ndarray,
+                             nxe_quirk: bool = True) -> dict:
+    """The part of `normal_equations_batch` that needs only the per-bin Gram pieces (every covariate term, the trace
+    column, yXXy): `RheEngine.run(gram_hook=...)` calls it on the host while the device still forms the leave-one-out
+    Grams `XX`, so only `normal_equations_finish` is left once `XX` arrives."""
     E, E_reg, B, C, N = plan.E, plan.E_reg, plan.B, plan.C, ht.N
-    S = XX.shape[0]
-    zs, ws, yc = plan.cols_Z(), plan.cols_W(), plan.col_y(trait)
+    S = G_loo.shape[0]
+    zs, ws = plan.cols_Z(), plan.cols_W()
     Mf = np.asarray(M_tab, dtype=np.float64)
     MM = Mf[:, :, None] * Mf[:, None, :]
-    V = XX.astype(np.float64).copy()
-    T = np.zeros((S, E + 1, E + 1))
-    q = np.zeros((S, E + 1))
+    corr = None
+    H = QWtZ = None
     if C > 0:
         QWtZ = ht.Q @ ht.WtZ
         H = np.empty((S, E, C, B))
@@ -203,9 +202,7 @@ def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo:
         flat = lambda a: a.reshape(S, E, C * B)
         r1 = flat(H) @ flat(QH).transpose(0, 2, 1)                      # sum_cb H[s,a,c,b] QH[s,e,c,b]
         r2 = flat(WtLU) @ flat(QHq).transpose(0, 2, 1)
-        V += r2 - 2 * r1
-    V /= B
-    np.divide(V, MM, out=T[:, :E, :E], where=MM != 0)
+        corr = r2 - 2 * r1
     tr = np.full((S, E), float(N))
     if plan.model == "genie" and E > plan.K:
         zz = np.einsum("sebb->se", G_loo[:, plan.K:E_reg, zs, zs])
@@ -214,8 +211,24 @@ def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo:
             tr[:, E_reg] = ht.nxe_tr / (B * Mf[:, E_reg])
     if C > 0:
         tr = tr - np.einsum("secb,cb->se", H, QWtZ) / (B * Mf)
-    T[:, :E, E] = tr
-    T[:, E, :E] = tr
+    return dict(plan=plan, ht=ht, G_loo=G_loo, Mf=Mf, MM=MM, corr=corr, tr=tr)
+
+
+def normal_equations_finish(prep: dict, XX: np.ndarray, trait: int = 0):
+    """`normal_equations_prepare` + the leave-one-out Grams XX [S, E, E]  ->  T [S, E+1, E+1], q [S, E+1]."""
+    plan, ht, G_loo, Mf, MM = prep["plan"], prep["ht"], prep["G_loo"], prep["Mf"], prep["MM"]
+    E, E_reg, B, C, N = plan.E, plan.E_reg, plan.B, plan.C, ht.N
+    S = XX.shape[0]
+    yc = plan.col_y(trait)
+    V = XX.astype(np.float64).copy()
+    T = np.zeros((S, E + 1, E + 1))
+    q = np.zeros((S, E + 1))
+    if prep["corr"] is not None:
+        V += prep["corr"]
+    V /= B
+    np.divide(V, MM, out=T[:, :E, :E], where=MM != 0)
+    T[:, :E, E] = prep["tr"]
+    T[:, E, :E] = prep["tr"]
     T[:, E, E] = N - C
     yxxy = np.empty((S, E))
     yxxy[:, :E_reg] = G_loo[:, :, yc, yc]
@@ -224,3 +237,11 @@ def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo:
     np.divide(yxxy, Mf, out=q[:, :E], where=Mf != 0)
     q[:, E] = ht.yy_res[trait]
     return T, q
+
+
+def normal_equations_batch(plan: PathPlan, ht: HostTerms, XX: np.ndarray, G_loo: np.ndarray, M_tab: np.ndarray,
+                           trait: int = 0, nxe_quirk: bool = True):
+    """Vectorised `normal_equations` over all jackknife samples (the production path).
+
+    XX [S, E, E], G_loo [S, E_reg, Rs, Rs], M_tab [S, E]  ->  T [S, E+1, E+1], q [S, E+1]."""
+    return normal_equations_finish(normal_equations_prepare(plan, ht, G_loo, M_tab, nxe_quirk), XX, trait)

@@ -24,7 +24,8 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from .. import stats
-from ..assemble import PathPlan, loo_grams, normal_equations, normal_equations_batch, trace_sums_row
+from ..assemble import (PathPlan, loo_grams, normal_equations, normal_equations_batch, normal_equations_finish,
+                        normal_equations_prepare, trace_sums_row)
 from ..hostmath import block_ranges, host_terms
 from ..util.file_processing import (generate_annot, read_annot, read_bim, read_cov, read_fam, read_pheno)
 from ..util.logger import Logger
@@ -164,6 +165,10 @@ class Base(BlockHookDriver, LegacyBlockOps, ABC):
         else:
             index = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = torch.device("cuda", index)
+        if self._world > 1 and torch.cuda.is_available():
+            # one process per GPU: keep this rank's staging threads and pinned ring on its GPU's NUMA node
+            from ..util.numa import bind_to_gpu_node
+            self.log._debug(f"NUMA binding: {bind_to_gpu_node(index)}")
         if device == "cpu":
             self.log._debug("device='cpu' requested: pyrhe_b200 runs the block path on CUDA regardless")
 
@@ -286,8 +291,12 @@ class Base(BlockHookDriver, LegacyBlockOps, ABC):
         # through a ring of block slots (and, for the streaming policy, streams a second time)
         ring = os.environ.get("PYRHE_B200_RING_BLOCKS")       # force the bounded ring (default: only when it must)
         streamer = eng.stream_genotypes(self.geno_bed, ring_blocks=int(ring) if ring else "auto")
+        # the host half of the normal equations that needs only the per-bin Gram pieces runs while the device still
+        # forms the leave-one-out Grams (trait-independent; `_solve_all` finishes it per trait)
+        ht = self._host_terms
         try:
-            self._pieces = eng.run(upload=streamer)
+            self._pieces = eng.run(upload=streamer,
+                                   gram_hook=lambda G: normal_equations_prepare(plan, ht, loo_grams(G), eng.Mjk))
         finally:
             streamer.close()
         self.ingest_report = dict(ring_blocks=eng.ring_blocks, genotype_bytes=eng.genotype_bytes(),
@@ -347,8 +356,11 @@ class Base(BlockHookDriver, LegacyBlockOps, ABC):
         batched = type(self).setup_lhs_rhs_jackknife is Base.setup_lhs_rhs_jackknife and not self._hook_mode
         if batched:       # all J + 1 systems assembled in one vectorised pass (an extender's override is honoured below)
             pc = self._pieces
-            T_all, q_all = normal_equations_batch(self._plan_cached, self._host_terms, pc["XX"], loo_grams(pc["G_blk"]),
-                                                  self.M, trait=self._trait_index())
+            if pc.get("gram_hook") is not None and np.array_equal(self.M, pc["M"]):
+                T_all, q_all = normal_equations_finish(pc["gram_hook"], pc["XX"], trait=self._trait_index())
+            else:
+                T_all, q_all = normal_equations_batch(self._plan_cached, self._host_terms, pc["XX"],
+                                                      loo_grams(pc["G_blk"]), self.M, trait=self._trait_index())
         for j in range(self.num_jack + 1):
             jj = 1 if (self.num_jack == 1 and j == 0) else j          # base.py:654-655
             if batched:

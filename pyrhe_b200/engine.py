@@ -12,6 +12,7 @@ PyTorch is used for device memory, streams and torch.distributed only.
 from __future__ import annotations
 
 import ctypes as C
+import time
 from typing import Optional
 
 import numpy as np
@@ -81,14 +82,34 @@ class BlockStreamer:
             self._fd = os.open(fname, os.O_RDONLY)
             self._file_off = int(packed.offset)
         self.pinned_source = hasattr(packed, "pinned_rows")
-        self.slots = []
-        if not self.pinned_source:
-            with torch.cuda.device(eng.device):
-                self.slots = [torch.empty((eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
-                              for _ in range(self.ring_host)]
-        self.views = [sl.numpy() for sl in self.slots]
-        self.thread = None
+        # the pinned ring: slot 0 now, the others on a helper thread while the first block is being staged (pinning
+        # host memory runs at 1-2 GB/s: at config 5 three 1.25 GB slots would otherwise cost seconds up front)
+        self.slots, self.views = [], []
+        self._slot_ready = []
+        self._slot_thread = None
         self.errors = []
+        if not self.pinned_source:
+            import threading
+            self._slot_ready = [threading.Event() for _ in range(self.ring_host)]
+            self.slots = [None] * self.ring_host
+            self.views = [None] * self.ring_host
+
+            def make_slots(ks):
+                try:
+                    with torch.cuda.device(eng.device):
+                        for k in ks:
+                            self.slots[k] = torch.empty((eng.max_m, eng.row_bytes), dtype=torch.uint8, pin_memory=True)
+                            self.views[k] = self.slots[k].numpy()
+                            self._slot_ready[k].set()
+                except Exception as exc:                       # surfaced by the worker through check()
+                    self.errors.append(exc)
+                    for e in self._slot_ready:
+                        e.set()
+            make_slots([0])
+            if self.ring_host > 1:
+                self._slot_thread = threading.Thread(target=make_slots, args=(range(1, self.ring_host),), daemon=True)
+                self._slot_thread.start()
+        self.thread = None
         self.bytes_staged = 0
         self.passes = 0
 
@@ -122,6 +143,9 @@ class BlockStreamer:
                     if self.pinned_source:
                         src = self.packed.pinned_rows(a, b)
                     else:
+                        self._slot_ready[k].wait()
+                        if self.errors:
+                            return
                         if slot_free[k] is not None:
                             slot_free[k].synchronize()
                         step = -(-m // self.n_workers)
@@ -193,6 +217,9 @@ class BlockStreamer:
         for e in getattr(self, "_released", {}).values():
             e.set()
         self.join()
+        if self._slot_thread is not None:
+            self._slot_thread.join()
+            self._slot_thread = None
         if self._fd is not None:
             os.close(self._fd)
             self._fd = None
@@ -293,6 +320,9 @@ class RheEngine:
         self.retile = bool(retile) and kernel_path == _lib.PATH_TCGEN05
         self._tiled = set()
         self._retile_scratch = None
+        self._pinned = {}
+        self._d2h_stream = None
+        self.tail_seconds = None
         #: with stored partials: S = sum_j P_j in one pass after the blocks (`rhe_sum_partials`: totals that are
         #: bit-reproducible from run to run) instead of RED into S from every pass B.  Off by default: at 13 config-5
         #: blocks per rank the extra pass costs 0.35 ms and the RED-free pass B saves 0.01 ms per block
@@ -542,11 +572,21 @@ class RheEngine:
             if upload is not None:
                 upload.release(j, cur)
 
-    def run(self, upload=None) -> dict:
+    def _host_buf(self, name: str, like):
+        """Pinned host twin of a small device result (allocated once per engine): its D2H copy is asynchronous."""
+        buf = self._pinned.get(name)
+        if buf is None or buf.shape != like.shape:
+            buf = self._pinned[name] = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+        return buf
+
+    def run(self, upload=None, gram_hook=None) -> dict:
         """All own blocks -> totals -> all-reduce -> leave-one-out Grams.
 
         Returns host arrays XX [J+1, E, E] and G_blk [J, E_reg, Rs, Rs] (identical on all ranks).  `upload` is the
-        `BlockStreamer` of `stream_genotypes`; without it the blocks must already be resident (`load_genotypes`)."""
+        `BlockStreamer` of `stream_genotypes`; without it the blocks must already be resident (`load_genotypes`).
+        `gram_hook(G_blk)` (optional) runs on the host as soon as the per-bin Gram pieces have arrived, while the
+        device still reduces `S` and forms the leave-one-out Grams (the covariate terms of the normal equations need
+        nothing else: `assemble.normal_equations_prepare`); its return value comes back as `out["gram_hook"]`."""
         plan = self.plan
         E, E_reg, B, Rs, Np, J = plan.E, plan.E_reg, plan.B, plan.Rs, self.Np, self.J
         dev = self.device
@@ -570,7 +610,20 @@ class RheEngine:
             else:
                 self._pass(upload, lambda jl, j: self._accumulate(j, P_all[jl] if self.store_partials else None, S, G_blk[j]))
             if self.world > 1:
-                allreduce_sum([S, G_blk], self.pg)
+                allreduce_sum([G_blk], self.pg)
+            # the small Gram pieces leave for the host first (pinned, asynchronous): the host works on them while the
+            # device reduces S and forms the leave-one-out Grams
+            st = torch.cuda.current_stream(dev)
+            G_host = self._host_buf("G_blk", G_blk)
+            if self._d2h_stream is None:
+                self._d2h_stream = torch.cuda.Stream(dev)
+            self._d2h_stream.wait_stream(st)
+            with torch.cuda.stream(self._d2h_stream):          # a side stream: the kernels that follow do not wait for it
+                G_host.copy_(G_blk, non_blocking=True)
+                ev_gram = torch.cuda.Event()
+                ev_gram.record(self._d2h_stream)
+            if self.world > 1:
+                allreduce_sum([S], self.pg)
             if plan.has_nxe:
                 S[E_reg].copy_(self.nxe_S)
             length = B * Np
@@ -599,7 +652,22 @@ class RheEngine:
             if self.world > 1:
                 allreduce_sum([XX], self.pg)
             self.S, self.P_all = S, P_all
-            out = dict(XX=XX.cpu().numpy(), G_blk=G_blk.cpu().numpy(), M=self.Mjk)
+            XX_host = self._host_buf("XX", XX)
+            XX_host.copy_(XX, non_blocking=True)
+            ev_xx = torch.cuda.Event()
+            ev_xx.record(st)
+            t0 = time.perf_counter()
+            ev_gram.synchronize()
+            t1 = time.perf_counter()
+            out = dict(G_blk=G_host.numpy().copy(), M=self.Mjk)
+            if gram_hook is not None:
+                out["gram_hook"] = gram_hook(out["G_blk"])
+            t2 = time.perf_counter()
+            ev_xx.synchronize()
+            st.wait_stream(self._d2h_stream)                   # G_blk is reused by the next run
+            out["XX"] = XX_host.numpy().copy()
+            #: host seconds of the last run's tail: waiting for the Gram pieces, inside gram_hook, waiting for XX
+            self.tail_seconds = (t1 - t0, t2 - t1, time.perf_counter() - t2)
             if upload is not None:
                 upload.check()
         return out
