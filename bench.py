@@ -250,12 +250,13 @@ def model_api_e2e(args, dev):
         shutil.rmtree(outdir, ignore_errors=True)
 
 
-def build_problem(wl, args, rank, world, dev):
-    """Synthetic inputs of one workload + an engine with this rank's blocks generated in HBM and ingested."""
+def build_problem(wl, args, rank, world, dev, shard_weights=None, generate=True):
+    """Synthetic inputs of one workload + an engine with this rank's blocks generated in HBM and ingested
+    (`generate=False`: the residency is allocated and left for an upload to fill)."""
     import torch
     from pyrhe_b200 import _lib, synth
     from pyrhe_b200.assemble import PathPlan
-    from pyrhe_b200.engine import RheEngine
+    from pyrhe_b200.engine import RheEngine, shard_sizes
     from pyrhe_b200.hostmath import host_terms
     lib = _lib.load()
     N, M, J, K, Cc, B = wl["N"], wl["M"], wl["J"], wl["K"], wl["C"], wl["B"]
@@ -275,17 +276,18 @@ def build_problem(wl, args, rank, world, dev):
     # memory policy: keep every block's partial in HBM when it fits next to the genotypes
     pitch = (N + 3) // 4
     pitch = (pitch + 127) // 128 * 128
-    per = -(-J // world)
-    own_blocks = max(0, min((rank + 1) * per, J) - rank * per)
+    own_blocks = shard_sizes(J, world, shard_weights)[rank]
     bytes_geno = own_blocks * (M // J + M % J) * pitch
     bytes_part = own_blocks * plan.E * B * pitch * 4 * 4
     free_b, total_b = torch.cuda.mem_get_info(dev)
     store = bytes_geno + bytes_part + 6e9 < free_b
     eng = RheEngine(plan, n_indv=N, keep=keep, annot=annot, num_jack=J, impute="binary", seed=0, device=dev,
                     kernel_path=args.kernel_path, rank=rank, world=world, store_partials=store,
-                    retile=getattr(args, "retile", True))
+                    retile=getattr(args, "retile", True), shard_weights=shard_weights)
     eng.set_rhs(Z, W, Y_res, env)
     eng.alloc_genotypes()
+    if not generate:
+        return dict(eng=eng, plan=plan, ht=ht, Z=Z, W=W, Y_res=Y_res, env=env, store=store, ingest_count_ms=None)
     stream = torch.cuda.current_stream(dev)
     for j in eng.own:                                          # synthetic genotypes generated in HBM
         rows, m = eng.block_view(j)
@@ -319,6 +321,9 @@ def main():
     ap.add_argument("--ring_blocks", type=int, default=4, help="distinct host blocks served cyclically in the e2e leg")
     ap.add_argument("--e2e_source", default="pinned", choices=["pinned", "pageable"])
     ap.add_argument("--no_other_configs", action="store_true")
+    ap.add_argument("--no_weighted_e2e", action="store_true",
+                    help="multi-GPU e2e leg: equal block shares only (default: also shares proportional to the measured H2D rates)")
+    ap.add_argument("--force_e2e_weights", default=None, help="comma-separated shard weights for the second e2e leg (testing)")
     ap.add_argument("--no_api_e2e", action="store_true")
     ap.add_argument("--no_retile", dest="retile", action="store_false",
                     help="keep the PLINK rows of blocks that own an individual-major copy (default: re-tile them for pass A)")
@@ -336,7 +341,7 @@ def main():
     import torch.distributed as dist
     from pyrhe_b200 import _lib
     from pyrhe_b200.assemble import PathPlan, normal_equations_prepare, normal_equations_finish, loo_grams
-    from pyrhe_b200.engine import RheEngine
+    from pyrhe_b200.engine import RheEngine, shard_sizes
     from pyrhe_b200.hostmath import host_terms
     from pyrhe_b200 import synth
 
@@ -498,9 +503,38 @@ def main():
     # still crosses the host staging copy and the link each step.
     e2e = None
     h2d_ceiling = None
-    if not args.no_e2e:
+
+    def measure_h2d_ceiling():
+        """The node's pinned-H2D ceiling with all ranks copying at once (no staging, no kernels): what the links give."""
+        pin = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+        dst = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        dst.copy_(pin, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(8):
+            dst.copy_(pin, non_blocking=True)
+        c1.record(stream)
+        barrier()
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = 8 * (1 << 30) / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank = [float(x) for x in t.tolist()]
+        # a step that hands every rank the same number of blocks ends when the slowest link is done: with unequal
+        # links the ceiling of an equal split is n x the slowest rank's rate, not the sum of the rates
+        return {"aggregate_gbs": float(sum(per_rank)), "per_rank_gbs": [round(x, 2) for x in per_rank],
+                "equal_split_gbs": world * min(per_rank), "n_gpus": world,
+                "how": "8 x 1 GiB pinned->device copies per rank, all ranks concurrently; aggregate = sum of the "
+                       "ranks' rates, equal_split = n x the slowest rank's rate"}
+
+    def e2e_leg(eng):
+        """Every block's rows go host memory -> (staging threads -> pinned ring ->) PCIe -> device slot (+ ingest
+        kernels on arrival) inside the step, through `eng.stream_genotypes` + `eng.run`."""
+        if len(eng.own) == 0:
+            raise RuntimeError("a rank without blocks")
         R = max(1, min(args.ring_blocks, len(eng.own)))
-        host = torch.empty((R * eng.max_m, eng.row_bytes), dtype=torch.uint8).pin_memory()
+        host = torch.empty((R * eng.max_m, eng.row_bytes), dtype=torch.uint8, pin_memory=True)
         tmp = torch.zeros((eng.max_m, eng.pitch), dtype=torch.uint8, device=dev)
         for r in range(R):                                     # the same generator as the resident leg (the resident rows may be re-tiled)
             j = eng.own[r]
@@ -541,46 +575,56 @@ def main():
             d2h_holder["n"] = pieces["XX"].nbytes + pieces["G_blk"].nbytes
             return tail(pieces)
 
-        step_e2e()
-        n_e2e = max(1, min(args.steps, 2))
-        ms_e2e, _ = timed(step_e2e, n_e2e)
-        ms_e2e /= n_e2e
-        t = torch.zeros(world, dtype=torch.float64, device=dev)
-        t[rank] = timed.local_ms / n_e2e
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e_rank_ms = [round(float(x), 1) for x in t.tolist()]
-        e2e = {"value": total_bytes / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_holder["n"]),
-               "ms_per_step_by_rank": e2e_rank_ms, "host_sample_blocks": R, "host_source": args.e2e_source,
-               "staging_threads": 0 if streamer.pinned_source else streamer.n_workers,
-               "path": "RheEngine.stream_genotypes (host rows -> staging threads -> pinned ring -> H2D -> counts) + run"}
-        streamer.close()
-        # the node's pinned-H2D ceiling with all ranks copying at once (no staging, no kernels): what the link gives
-        pin = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
-        dst = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
-        dst.copy_(pin, non_blocking=True)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(stream)
-        for _ in range(8):
-            dst.copy_(pin, non_blocking=True)
-        c1.record(stream)
-        barrier()
-        t = torch.zeros(world, dtype=torch.float64, device=dev)
-        t[rank] = 8 * (1 << 30) / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        per_rank = [float(x) for x in t.tolist()]
-        # the step hands every rank the same number of blocks and ends when the slowest link is done: with unequal
-        # links the ceiling of an equal split is n x the slowest rank's rate, not the sum of the rates
-        h2d_ceiling = {"aggregate_gbs": float(sum(per_rank)), "per_rank_gbs": [round(x, 2) for x in per_rank],
-                       "equal_split_gbs": world * min(per_rank), "n_gpus": world,
-                       "how": "8 x 1 GiB pinned->device copies per rank, all ranks concurrently; aggregate = sum of the "
-                              "ranks' rates, equal_split = n x the slowest rank's rate"}
+        try:
+            step_e2e()
+            n_e2e = max(1, min(args.steps, 2))
+            ms_e2e, sig = timed(step_e2e, n_e2e)
+            ms_e2e /= n_e2e
+            # per rank: when the last block of the last timed step had landed on the device, and the H2D rate that is
+            streamer.join()
+            t = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+            t[rank] = 1e3 * (streamer.copy_seconds or 0.0)
+            t[world + rank] = (sum(eng.ranges[j][1] - eng.ranges[j][0] for j in eng.own) * eng.row_bytes
+                               / max(streamer.copy_seconds or 1.0, 1e-9) / 1e9)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return {"value": total_bytes / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_holder["n"]),
+                    "blocks_by_rank": shard_sizes(J, world, eng.shard_weights),
+                    "upload_ms_by_rank": [round(float(x), 1) for x in t[:world].tolist()],
+                    "upload_gbs_by_rank": [round(float(x), 2) for x in t[world:].tolist()],
+                    "host_sample_blocks": R, "host_source": args.e2e_source,
+                    "staging_threads": 0 if streamer.pinned_source else streamer.n_workers,
+                    "sigma_e": float(sig[-1][-1]),
+                    "path": "RheEngine.stream_genotypes (host rows -> staging threads -> pinned ring -> H2D -> counts) + run"}
+        finally:
+            streamer.close()
+
+    if not args.no_e2e and J >= world:
+        h2d_ceiling = measure_h2d_ceiling()
+        e2e = e2e_leg(eng)
+        rates = h2d_ceiling["per_rank_gbs"]
+        if args.force_e2e_weights:
+            rates = [float(x) for x in args.force_e2e_weights.split(",")]
+        if world > 1 and min(rates) < 0.9 * max(rates) and not args.no_weighted_e2e and J >= 2 * world:
+            # unequal links (on this pool's eight-GPU boxes four GPUs get 23 GB/s and four 35 GB/s when all copy at once):
+            # an upload-bound pass ends with the slowest link, so the same leg runs once more on an engine whose
+            # contiguous block ranges are proportional to the measured rates (`RheEngine(shard_weights=...)`); the
+            # work is the same (every block of the job once; the R-block host sample is laid out per rank, so the two legs
+            # see differently ordered synthetic genotypes and report their own sigma_e); the faster leg is the line's e2e
+            equal = e2e
+            pbw = build_problem(wl, args, rank, world, dev, shard_weights=rates, generate=False)
+            try:
+                weighted = e2e_leg(pbw["eng"])
+            finally:
+                pbw["eng"].close()
+                del pbw
+            weighted["shard_weights"] = rates
+            e2e = dict(weighted if weighted["value"] > equal["value"] else equal)
+            e2e["equal_split"] = {k: equal[k] for k in ("value", "ms_per_step", "blocks_by_rank", "upload_ms_by_rank", "sigma_e")}
+            e2e["rate_weighted_split"] = {k: weighted[k] for k in ("value", "ms_per_step", "blocks_by_rank", "upload_ms_by_rank", "sigma_e")}
         e2e["frac_of_h2d_ceiling"] = e2e["value"] / h2d_ceiling["aggregate_gbs"]
         e2e["frac_of_equal_split_ceiling"] = e2e["value"] / h2d_ceiling["equal_split_gbs"]
-        del pin, dst, host, host_np
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -27,11 +27,32 @@ def _round_up(a, b):
     return (a + b - 1) // b * b
 
 
-def shard_blocks(num_jack: int, world: int, rank: int):
-    """Contiguous range [j0, j1) of jackknife blocks owned by `rank`: ceil(J / world) per rank, exactly
-    how the reference hands block ranges to its worker processes (base.py:530-533)."""
-    per = -(-num_jack // world)
-    return min(rank * per, num_jack), min((rank + 1) * per, num_jack)
+def shard_sizes(num_jack: int, world: int, weights=None):
+    """Blocks per rank.  Default: ceil(J / world) per rank, exactly how the reference hands block ranges to its worker
+    processes (base.py:530-533).  With `weights` (one positive number per rank, e.g. the measured host-to-device rate
+    of each rank's link when a pass is bound by the upload): shares proportional to the weights, largest remainders
+    first, and at least one block per rank when there are enough blocks."""
+    if weights is None:
+        per = -(-num_jack // world)
+        return [max(0, min((r + 1) * per, num_jack) - min(r * per, num_jack)) for r in range(world)]
+    w = np.asarray(weights, dtype=np.float64)
+    if w.shape != (world,) or not np.all(np.isfinite(w)) or np.any(w <= 0):
+        raise ValueError("shard weights: one positive finite number per rank")
+    raw = w / w.sum() * num_jack
+    sizes = np.floor(raw).astype(np.int64)
+    order = np.argsort(-(raw - sizes), kind="stable")
+    sizes[order[: num_jack - int(sizes.sum())]] += 1
+    while num_jack >= world and sizes.min() == 0:              # nobody idles while another rank holds several blocks
+        sizes[int(np.argmax(sizes))] -= 1
+        sizes[int(np.argmin(sizes))] += 1
+    return [int(x) for x in sizes]
+
+
+def shard_blocks(num_jack: int, world: int, rank: int, weights=None):
+    """Contiguous range [j0, j1) of jackknife blocks owned by `rank` (`shard_sizes`)."""
+    sizes = shard_sizes(num_jack, world, weights)
+    j0 = sum(sizes[:rank])
+    return j0, j0 + sizes[rank]
 
 
 def allreduce_sum(tensors, group=None):
@@ -112,6 +133,7 @@ class BlockStreamer:
         self.thread = None
         self.bytes_staged = 0
         self.passes = 0
+        self.copy_seconds = None
 
     # ---- staging
     def _read_chunk(self, dst: np.ndarray, first_row: int):
@@ -133,6 +155,7 @@ class BlockStreamer:
         from concurrent.futures import ThreadPoolExecutor
         eng = self.eng
         R = eng.ring_blocks
+        t_start = time.perf_counter()
         try:
             with torch.cuda.device(eng.device), ThreadPoolExecutor(self.n_workers) as pool:
                 slot_free = [None] * self.ring_host            # event of the last H2D copy that read the pinned slot
@@ -172,6 +195,8 @@ class BlockStreamer:
                     self._events[j] = ev
                     self._ready[j].set()
                 self.copy_stream.synchronize()
+                #: host seconds from the start of the last pass to the arrival of its last block on the device
+                self.copy_seconds = time.perf_counter() - t_start
                 self.ingest_stream.synchronize()
         except Exception as exc:          # surfaced by acquire() / check()
             self.errors.append(exc)
@@ -230,7 +255,7 @@ class RheEngine:
     def __init__(self, plan: PathPlan, *, n_indv: int, keep: np.ndarray, annot: np.ndarray, num_jack: int,
                  impute: str = "binary", seed: int = 0, device: Optional[torch.device] = None,
                  kernel_path: Optional[int] = None, rank: int = 0, world: int = 1,
-                 store_partials: bool = True, process_group=None, retile: bool = False):
+                 store_partials: bool = True, process_group=None, retile: bool = False, shard_weights=None):
         if not torch.cuda.is_available():
             raise _lib.RheError("pyrhe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -257,7 +282,8 @@ class RheEngine:
         self.pitch = _round_up(self.row_bytes, 128)
         self.Np = 4 * self.pitch
         self.ranges = block_ranges(self.M_snps, self.J)
-        self.j0, self.j1 = shard_blocks(self.J, world, rank)
+        self.shard_weights = None if shard_weights is None else [float(x) for x in shard_weights]
+        self.j0, self.j1 = shard_blocks(self.J, world, rank, self.shard_weights)
         self.own = list(range(self.j0, self.j1))
         self.max_m = max(b - a for a, b in self.ranges)
 

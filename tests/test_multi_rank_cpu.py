@@ -69,3 +69,21 @@ def test_shard_blocks_matches_reference_distribution():
                                                            (65, 78), (78, 91), (91, 100)]
     assert [shard_blocks(3, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 3), (3, 3)]
     assert shard_blocks(10, 1, 0) == (0, 10)
+
+
+def test_weighted_shards_are_contiguous_and_proportional():
+    """`shard_sizes(weights=...)`: block shares proportional to per-rank weights (the measured H2D rates of an
+    upload-bound pass), every block owned exactly once, nobody idle while another rank holds several blocks."""
+    from pyrhe_b200.engine import shard_blocks, shard_sizes
+    rates = [23.2, 23.23, 23.29, 23.28, 35.3, 35.47, 35.49, 35.27]
+    assert shard_sizes(100, 8, rates) == [10, 10, 10, 10, 15, 15, 15, 15]
+    ranges = [shard_blocks(100, 8, r, rates) for r in range(8)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == 100
+    assert all(ranges[r][1] == ranges[r + 1][0] for r in range(7))
+    assert shard_sizes(8, 4, [1, 1, 1, 50]) == [1, 1, 1, 5]
+    assert sum(shard_sizes(3, 4, [1, 1, 1, 5])) == 3
+    assert shard_sizes(10, 1, [3.0]) == [10]
+    assert shard_sizes(100, 8, [1.0] * 8) in ([13, 13, 13, 13, 12, 12, 12, 12], [12, 13, 12, 13, 12, 13, 12, 13])
+    import pytest
+    with pytest.raises(ValueError):
+        shard_sizes(10, 2, [1.0, 0.0])
