@@ -346,8 +346,14 @@ class RheEngine:
         self.retile = bool(retile) and kernel_path == _lib.PATH_TCGEN05
         self._tiled = set()
         self._retile_scratch = None
-        self._pinned = {}
-        self._d2h_stream = None
+        # pinned twins of the small results of a pass and their copy stream, created before any large device allocation:
+        # pinning host memory for the first time in a process costs tens of milliseconds (measured: + 50 ms on the first
+        # pass when it happened there, next to 180 GB of mapped HBM)
+        with torch.cuda.device(self.device):
+            self._d2h_stream = torch.cuda.Stream(self.device)
+            self._pinned = {name: torch.empty(shape, dtype=torch.float64, pin_memory=True)
+                            for name, shape in (("G_blk", (self.J, plan.E_reg, plan.Rs, plan.Rs)),
+                                                ("XX", (self.J + 1, plan.E, plan.E)))}
         self.tail_seconds = None
         #: with stored partials: S = sum_j P_j in one pass after the blocks (`rhe_sum_partials`: totals that are
         #: bit-reproducible from run to run) instead of RED into S from every pass B.  Off by default: at 13 config-5
@@ -641,8 +647,6 @@ class RheEngine:
             # device reduces S and forms the leave-one-out Grams
             st = torch.cuda.current_stream(dev)
             G_host = self._host_buf("G_blk", G_blk)
-            if self._d2h_stream is None:
-                self._d2h_stream = torch.cuda.Stream(dev)
             self._d2h_stream.wait_stream(st)
             with torch.cuda.stream(self._d2h_stream):          # a side stream: the kernels that follow do not wait for it
                 G_host.copy_(G_blk, non_blocking=True)
