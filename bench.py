@@ -250,6 +250,16 @@ def model_api_e2e(args, dev):
         shutil.rmtree(outdir, ignore_errors=True)
 
 
+def weighted_shares_fit(J, world, rank, weights, block_bytes, free_bytes, reserve=8e9) -> bool:
+    """Whether this rank's share under `weights` (rows + stored partials of its blocks; the individual-major copies adapt
+    to what is left) fits the free HBM next to the engine that is already resident."""
+    from pyrhe_b200.engine import shard_sizes
+    try:
+        return bool(shard_sizes(J, world, weights)[rank] * block_bytes + reserve < free_bytes)
+    except Exception:
+        return False
+
+
 def build_problem(wl, args, rank, world, dev, shard_weights=None, generate=True):
     """Synthetic inputs of one workload + an engine with this rank's blocks generated in HBM and ingested
     (`generate=False`: the residency is allocated and left for an upload to fill)."""
@@ -606,7 +616,15 @@ def main():
         rates = h2d_ceiling["per_rank_gbs"]
         if args.force_e2e_weights:
             rates = [float(x) for x in args.force_e2e_weights.split(",")]
-        if world > 1 and min(rates) < 0.9 * max(rates) and not args.no_weighted_e2e and J >= 2 * world:
+        weighted_ok = world > 1 and min(rates) > 0 and min(rates) < 0.9 * max(rates) and not args.no_weighted_e2e \
+            and J >= 2 * world
+        if weighted_ok:                                       # every rank must have room for its share (agreed by all ranks)
+            block_bytes = -(-eng.max_m // 128) * 128 * eng.pitch + plan.E * plan.B * eng.Np * 4
+            flag = torch.tensor([int(weighted_shares_fit(J, world, rank, rates, block_bytes,
+                                                         torch.cuda.mem_get_info(dev)[0]))], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            weighted_ok = bool(flag.item())
+        if weighted_ok:
             # unequal links (on this pool's eight-GPU boxes four GPUs get 23 GB/s and four 35 GB/s when all copy at once):
             # an upload-bound pass ends with the slowest link, so the same leg runs once more on an engine whose
             # contiguous block ranges are proportional to the measured rates (`RheEngine(shard_weights=...)`); the

@@ -87,3 +87,24 @@ def test_weighted_shards_are_contiguous_and_proportional():
     import pytest
     with pytest.raises(ValueError):
         shard_sizes(10, 2, [1.0, 0.0])
+
+
+def test_weighted_e2e_leg_is_refused_when_a_share_does_not_fit():
+    """bench.py only runs its rate-weighted e2e leg when every rank has room for its share next to the resident engine."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    block = 10112 * 125056 + 8 * 10 * 500224 * 4             # rows + stored partial of one config-5 block
+    rates = [23.2, 23.23, 23.29, 23.28, 35.3, 35.47, 35.49, 35.27]
+    assert all(bench.weighted_shares_fit(100, 8, r, rates, block, 140e9) for r in range(8))
+    assert not bench.weighted_shares_fit(100, 2, 1, [45.0, 55.0], block, 40e9)
+    assert not bench.weighted_shares_fit(100, 2, 0, [0.0, 55.0], block, 400e9)       # invalid weights: refused, not raised
+
+
+def test_numa_cpulist_parser_and_noop_binding():
+    from pyrhe_b200.util.numa import _parse_cpulist, bind_to_gpu_node
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    rep = bind_to_gpu_node(0)                                   # no GPU here: reports why and leaves the affinity alone
+    assert rep["bound"] is False and "why" in rep
