@@ -355,6 +355,7 @@ class RheEngine:
                             for name, shape in (("G_blk", (self.J, plan.E_reg, plan.Rs, plan.Rs)),
                                                 ("XX", (self.J + 1, plan.E, plan.E)))}
         self.tail_seconds = None
+        self._keep2_host = None
         #: with stored partials: S = sum_j P_j in one pass after the blocks (`rhe_sum_partials`: totals that are
         #: bit-reproducible from run to run) instead of RED into S from every pass B.  Off by default: at 13 config-5
         #: blocks per rank the extra pass costs 0.35 ms and the RED-free pass B saves 0.01 ms per block
@@ -399,16 +400,16 @@ class RheEngine:
     def set_rhs(self, Z: np.ndarray, W, Y_res: np.ndarray, env=None):
         """Right-hand sides [Z | W | y_res] (+ env-scaled set) -> fp32 on the device (mat_mul.py:12)."""
         plan = self.plan
-        R, rowscale = rhs_matrix(plan, Z, W, Y_res, env, self.keep)
-        Rp = np.zeros((R.shape[0], self.Np), dtype=np.float32)
-        Rp[:, : self.n_indv] = R
-        rs = np.zeros((plan.n_sets, self.Np), dtype=np.float32)
-        rs[:, : self.n_indv] = rowscale
-        bits = np.zeros(self.Np, dtype=np.uint32)
-        bits[: self.n_indv] = self.keep.astype(np.uint32) * 3
-        keep2 = np.zeros(self.Np // 16, dtype=np.uint32)
-        for t in range(16):
-            keep2 |= bits[t::16] << np.uint32(2 * t)
+        # fp32, padded to the device row length, in one pass over the inputs
+        Rp, rs = rhs_matrix(plan, Z, W, Y_res, env, self.keep, dtype=np.float32, width=self.Np)
+        if self._keep2_host is None:                           # 2-bit keep mask per packed word (the keep set is fixed)
+            bits = np.zeros(self.Np, dtype=np.uint32)
+            bits[: self.n_indv] = self.keep.astype(np.uint32) * 3
+            keep2 = np.zeros(self.Np // 16, dtype=np.uint32)
+            for t in range(16):
+                keep2 |= bits[t::16] << np.uint32(2 * t)
+            self._keep2_host = keep2
+        keep2 = self._keep2_host
         with torch.cuda.device(self.device):
             self.R = torch.from_numpy(Rp).to(self.device)
             self.rowscale = torch.from_numpy(rs).to(self.device)

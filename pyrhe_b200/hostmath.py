@@ -67,22 +67,41 @@ def host_terms(plan: PathPlan, Z: np.ndarray, W, Y: np.ndarray, env) -> tuple:
     return ht, Y_res
 
 
-def rhs_matrix(plan: PathPlan, Z, W, Y_res, env, keep: np.ndarray):
+def rhs_matrix(plan: PathPlan, Z, W, Y_res, env, keep: np.ndarray, dtype=np.float64, width: int | None = None):
     """Right-hand sides in FILE order (row i = individual i of the .fam; rows of dropped
     individuals are zero so they add nothing to X^T R).
 
-    Returns (R [n_sets*Rs, N0], rowscale [n_sets, N0]).  Set 0 = [Z | W | y_res]; set 1 (GxE) =
+    Returns (R [n_sets*Rs, width], rowscale [n_sets, width]), `width` >= N0 (default N0; the engine asks for its padded
+    row length and fp32 so that no second pass over the matrix is needed).  Set 0 = [Z | W | y_res]; set 1 (GxE) =
     env * set 0, because (diag(env) X)^T r = X^T (env * r) (genie.py:65-67).  `rowscale` is
     what pass B multiplies its output rows by: keep mask, times env for the GxE set."""
     n0 = keep.shape[0]
-    cols = [Z] + ([W] if W is not None else []) + [Y_res]
-    base = np.concatenate(cols, axis=1)                        # [N, Rs]
-    R = np.zeros((plan.n_sets * plan.Rs, n0))
-    rowscale = np.zeros((plan.n_sets, n0))
-    R[: plan.Rs, keep] = base.T
-    rowscale[0, keep] = 1.0
+    width = n0 if width is None else int(width)
+    assert width >= n0
+    cols = [np.asarray(c, dtype=np.float64) for c in [Z] + ([W] if W is not None else []) + [Y_res]]
+    R = np.zeros((plan.n_sets * plan.Rs, width), dtype=dtype)
+    rowscale = np.zeros((plan.n_sets, width), dtype=dtype)
+    # column block by column block, straight into its rows (no [N, Rs] concatenation, no boolean-mask scatter: at
+    # N = 500k those cost 70-160 ms of every set_rhs; values are the same to the last bit)
+    idx = None if keep.all() else np.flatnonzero(keep)
+
+    def put(row0, block):
+        c = block.shape[1]
+        if idx is None:
+            for a in range(0, n0, 8192):                       # cache-sized pieces of the transposition
+                R[row0: row0 + c, a: min(a + 8192, n0)] = block[a: a + 8192].T
+        else:
+            R[row0: row0 + c, idx] = block.T
+        return row0 + c
+
+    r = 0
+    for c in cols:
+        r = put(r, c)
+    assert r == plan.Rs
+    rowscale[0, :n0][keep] = 1.0
     if plan.n_sets == 2:
         e = np.asarray(env, dtype=np.float64)
-        R[plan.Rs:, keep] = (base * e[:, None]).T
-        rowscale[1, keep] = e
+        for c in cols:
+            r = put(r, c * e[:, None])
+        rowscale[1, :n0][keep] = e
     return R, rowscale
