@@ -11,7 +11,10 @@ Grams, the D2H of the Gram pieces, host assembly of the J+1 normal equations and
 (packed rows + the per-SNP allele counts the ingest kernel takes when a block lands, DESIGN.md §2);
 `e2e` = the same job through the engine's ingest API (`stream_genotypes`: host rows -> staging threads ->
 pinned ring -> PCIe -> device, counts on arrival) with every byte crossing host memory and PCIe inside the
-timed region; `e2e_model_api` = `StreamingRHE(...)(trait=0)` on a real `.bed` file at config-2 size;
+timed region (with several GPUs whose links differ by more than 10 % -- `h2d_ceiling.per_rank_gbs`, measured with all
+ranks copying at once -- the leg runs a second time with block shares proportional to the measured rates and both legs
+are recorded); `e2e_model_api` = `StreamingRHE(...)(trait=0)` on a real `.bed` file at config-2 size (first call of the
+process = `value`, the same call again = `warm_value`);
 `first_pass_ms` = the very first pass of a fresh context (what a model run actually executes), and
 `step_recount_ms` the step when every block's allele counts are re-taken inside it (three reads per block,
 the round-1 structure).  The problem size is fixed as GPUs are added ("scaling": "strong"), as
