@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _rank_main(rank, world, port, name, out_dir):
+def _rank_main(rank, world, port, name, out_dir, weights=None):
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
         sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -30,7 +30,7 @@ def _rank_main(rank, world, port, name, out_dir):
     full = run_model(p.packed, p.n_indv_original, p.annot, p.Z, Y_res, p.W, p.env, p.missing_indv, p.num_jack,
                      p.impute, p.seed, plan)
     J, E, E_reg = p.num_jack, plan.E, plan.E_reg
-    j0, j1 = shard_blocks(J, world, rank)
+    j0, j1 = shard_blocks(J, world, rank, weights)
     # rank-local partials: only the own blocks are "computed"
     P_own = torch.from_numpy(full["P"][j0:j1].copy())
     S = P_own.sum(dim=0)
@@ -52,10 +52,11 @@ def _rank_main(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["rhe_cov_binary", "genie_full_cov"])
-def test_two_rank_sharding_reproduces_single_rank(name, tmp_path):
+@pytest.mark.parametrize("name,weights", [("rhe_cov_binary", None), ("genie_full_cov", None),
+                                          ("rhe_cov_binary", [1.0, 3.0])])       # unequal shares (rate-weighted shards)
+def test_two_rank_sharding_reproduces_single_rank(name, weights, tmp_path):
     port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_rank_main, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_rank_main, args=(2, port, name, str(tmp_path), weights), nprocs=2, join=True)
     for r in range(2):
         d = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
         np.testing.assert_allclose(d["XX"], d["XX_ref"], rtol=1e-12, atol=1e-12 * np.abs(d["XX_ref"]).max())
